@@ -1,0 +1,131 @@
+"""TEST INFRASTRUCTURE ONLY — independent 50-digit mpmath restatement of the same maths
+as oracle/gp_oracle.py, for tiny cases (n <= ~16).  Its purpose is to bound the FP64
+oracle's own error, because the reference ships nothing to pin against (SURVEY.md F2,
+§8c "What pins results instead" item 2).  Written from the formulas, not from
+gp_oracle.py, and deliberately in a different style (explicit loops, exact inverse).
+
+Formulas: ForOptimisationLog.R:34-40,63 (NLML), OptimisationGradientLog.R:50-57 in
+W-form (gradient), GPPredict.R:49-56 (prediction), AdjustTrainingSurvivalMeanVariance.R:
+10,21-26 (truncated-normal moments, here with the *exact* upper tail).
+"""
+from __future__ import annotations
+
+import mpmath as mp
+
+mp.mp.dps = 50
+
+
+def _cov(x1, x2, sf2, ell):
+    n1, n2, d = len(x1), len(x2), len(x1[0])
+    K = mp.zeros(n1, n2)
+    for i in range(n1):
+        for j in range(n2):
+            r2 = mp.mpf(0)
+            for k in range(d):
+                lk = ell[k] if len(ell) > 1 else ell[0]
+                r2 += ((mp.mpf(x1[i][k]) - mp.mpf(x2[j][k])) / lk) ** 2
+            K[i, j] = sf2 * mp.exp(-r2 / 2)
+    return K
+
+
+def _unpack(par, d, ard, linear_mean, gps2):
+    par = [mp.mpf(float(p)) for p in par]
+    sc2 = None
+    if gps2:
+        sc2 = mp.exp(par[-1])
+        par = par[:-1]
+    p = d if ard else 1
+    sn2, sf2 = mp.exp(par[0]), mp.exp(par[1])
+    ell = [mp.exp(v) for v in par[2:2 + p]]
+    w = par[len(par) - d - 1:] if linear_mean else [mp.mpf(0)] * (d + 1)
+    return sn2, sf2, ell, w, sc2
+
+
+def _mean(w, x):
+    d = len(x[0])
+    return [sum(mp.mpf(x[i][k]) * w[k] for k in range(d)) + w[d] for i in range(len(x))]
+
+
+def _ky(par, X, events, ard, linear_mean, gps2, sc2_vec):
+    n, d = len(X), len(X[0])
+    sn2, sf2, ell, w, sc2 = _unpack(par, d, ard, linear_mean, gps2)
+    K = _cov(X, X, sf2, ell)
+    Ky = K.copy()
+    c = 0
+    for i in range(n):
+        Ky[i, i] += sn2
+        if events[i] == 0:
+            if gps2:
+                Ky[i, i] += sc2
+            elif sc2_vec is not None:
+                Ky[i, i] += mp.exp(mp.mpf(float(sc2_vec[c])))
+            c += 1
+    return K, Ky, (sn2, sf2, ell, w, sc2)
+
+
+def nlml(par, X, y, events, ard=False, linear_mean=False, gps2=False, log_sc2_vec=None):
+    n = len(X)
+    K, Ky, (sn2, sf2, ell, w, sc2) = _ky(par, X, events, ard, linear_mean, gps2, log_sc2_vec)
+    m = _mean(w, X)
+    r = mp.matrix([mp.mpf(float(y[i])) - m[i] for i in range(n)])
+    L = mp.cholesky(Ky)
+    alpha = mp.lu_solve(Ky, r)
+    quad = sum(r[i] * alpha[i] for i in range(n))
+    return quad / 2 + sum(mp.log(L[i, i]) for i in range(n)) + mp.mpf(n) / 2 * mp.log(2 * mp.pi)
+
+
+def nlml_grad(par, X, y, events, ard=False, linear_mean=False, gps2=False, log_sc2_vec=None):
+    """True derivative of nlml() w.r.t. par, with the reference's quirk that the W
+    quadratic forms use y rather than y - m (OptimisationGradientLog.R:51-53,57)."""
+    n, d = len(X), len(X[0])
+    K, Ky, (sn2, sf2, ell, w, sc2) = _ky(par, X, events, ard, linear_mean, gps2, log_sc2_vec)
+    Kinv = Ky ** -1
+    yv = mp.matrix([mp.mpf(float(v)) for v in y])
+    a = Kinv * yv
+    W = a * a.T - Kinv
+    g = [-(sum(W[i, i] for i in range(n))) * sn2 / 2,
+         -sum(W[i, j] * K[i, j] for i in range(n) for j in range(n)) / 2]
+    p = d if ard else 1
+    for k in range(p):
+        s = mp.mpf(0)
+        for i in range(n):
+            for j in range(n):
+                if ard:
+                    r2 = ((mp.mpf(X[i][k]) - mp.mpf(X[j][k])) / ell[k]) ** 2
+                else:
+                    r2 = sum(((mp.mpf(X[i][q]) - mp.mpf(X[j][q])) / ell[0]) ** 2 for q in range(d))
+                s += W[i, j] * K[i, j] * r2
+        g.append(-s / 2)
+    if linear_mean:
+        m = _mean(w, X)
+        ac = Kinv * mp.matrix([yv[i] - m[i] for i in range(n)])
+        for k in range(d):
+            g.append(-sum(mp.mpf(X[i][k]) * ac[i] for i in range(n)))
+        g.append(-sum(ac[i] for i in range(n)))
+    if gps2:
+        g.append(-sum(W[i, i] for i in range(n) if events[i] == 0) * sc2 / 2)
+    return g
+
+
+def predict(par, X, y, events, Xstar, ard=False, linear_mean=False, gps2=False, log_sc2_vec=None):
+    n = len(X)
+    K, Ky, (sn2, sf2, ell, w, sc2) = _ky(par, X, events, ard, linear_mean, gps2, log_sc2_vec)
+    m = _mean(w, X)
+    ms = _mean(w, Xstar)
+    Kinv = Ky ** -1
+    alpha = Kinv * mp.matrix([mp.mpf(float(y[i])) - m[i] for i in range(n)])
+    ks = _cov(X, Xstar, sf2, ell)
+    mu, varf = [], []
+    for j in range(len(Xstar)):
+        col = ks[:, j]
+        mu.append(ms[j] + sum(col[i] * alpha[i] for i in range(n)))
+        varf.append(sf2 - (col.T * Kinv * col)[0, 0])
+    return mu, varf, [v + sn2 for v in varf]
+
+
+def truncated_moments(a, mu, s):
+    """Lower-truncated normal mean / variance with the exact upper tail (no 1-Phi loss)."""
+    a, mu, s = mp.mpf(float(a)), mp.mpf(float(mu)), mp.mpf(float(s))
+    al = (a - mu) / s
+    lam = mp.npdf(al) / (mp.erfc(al / mp.sqrt(2)) / 2)
+    return mu + s * lam, s ** 2 * (1 - lam * (lam - al))
