@@ -1,0 +1,97 @@
+"""ctypes binding of include/gpsurv.h.  There is no fallback: if libgpsurv.so is missing or
+cannot be loaded this module raises, and without an sm_100 GPU ``gps_create`` fails."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libgpsurv.so")
+
+GPS_OK, GPS_ERR_ARG, GPS_ERR_CUDA, GPS_ERR_NOT_PD, GPS_ERR_UNSUPPORTED, GPS_ERR_STATE = range(6)
+COV = {"SqExp": 0, "ARD": 1}
+MEAN = {"Zero": 0, "Linear": 1}
+NOISE_CORR = {False: 0, None: 0, "none": 0, "noiseCorrLearned": 1, "noiseCorrVec": 2}
+ARD_MODE = {"intended": 0, "as_written": 1}
+
+_dp = C.POINTER(C.c_double)
+_h = C.c_void_p
+
+# name -> (restype, argtypes); every symbol include/gpsurv.h declares
+PROTOTYPES = {
+    "gps_version": (C.c_char_p, []),
+    "gps_last_error": (C.c_char_p, [_h]),
+    "gps_last_pivot": (C.c_int, [_h]),
+    "gps_create": (C.c_int, [C.c_int, C.POINTER(_h)]),
+    "gps_create_batch": (C.c_int, [C.c_int, C.c_int, C.POINTER(_h)]),
+    "gps_destroy": (C.c_int, [_h]),
+    "gps_set_options": (C.c_int, [_h, C.c_int, C.c_int, C.c_int, C.c_int]),
+    "gps_set_data": (C.c_int, [_h, _dp, C.c_int, C.c_int, _dp, _dp]),
+    "gps_set_targets": (C.c_int, [_h, _dp]),
+    "gps_set_noise_corr": (C.c_int, [_h, _dp, C.c_int]),
+    "gps_cov": (C.c_int, [_h, _dp, C.c_int, _dp, C.c_int, C.c_int, C.c_double, _dp, C.c_int, C.c_int, C.c_int, _dp]),
+    "gps_nlml": (C.c_int, [_h, _dp, C.c_int, _dp]),
+    "gps_nlml_grad": (C.c_int, [_h, _dp, C.c_int, _dp, _dp]),
+    "gps_regress_finalize": (C.c_int, [_h, _dp, C.c_int, _dp, _dp, _dp, _dp, _dp]),
+    "gps_predict": (C.c_int, [_h, _dp, C.c_int, C.c_int, _dp, C.c_int, _dp, _dp, _dp]),
+    "gps_adjust": (C.c_int, [_h, _dp, _dp, _dp, C.c_int, _dp, _dp]),
+    "gps_launch_count": (C.c_longlong, [_h]),
+    "gps_last_device_ms": (C.c_double, [_h]),
+    "gps_set_graphs": (C.c_int, [_h, C.c_int]),
+    "gps_time_eval": (C.c_int, [_h, C.c_int, C.c_int, _dp]),
+    "gps_time_stages": (C.c_int, [_h, _dp]),
+    "gps_bench_gemm": (C.c_int, [_h, C.c_int, C.c_int, C.c_int, C.c_int, _dp]),
+}
+
+_lib = None
+
+
+class GpsError(RuntimeError):
+    def __init__(self, code, msg, pivot=0):
+        super().__init__(f"libgpsurv error {code}: {msg}")
+        self.code = code
+        self.pivot = pivot
+
+
+class NotPositiveDefinite(GpsError):
+    """GPS_ERR_NOT_PD — lets a caller keep the reference's nearPD fallback host-side
+    (ForOptimisationLog.R:43-51)."""
+
+
+def load():
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            f"{LIB_PATH} not found: build it with `python -m gpsurvival_b200.build` "
+            "(gpsurvival_b200 has no CPU fallback)")
+    lib = C.CDLL(LIB_PATH)
+    for name, (res, args) in PROTOTYPES.items():
+        fn = getattr(lib, name)     # AttributeError if the library does not export it
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def dptr(a):
+    return None if a is None else a.ctypes.data_as(_dp)
+
+
+def f64(a, order="F"):
+    """Contiguous FP64 copy in R (column-major) layout."""
+    return np.require(np.asarray(a, dtype=np.float64), requirements=["F" if order == "F" else "C", "A"])
+
+
+def check(rc, handle=None):
+    if rc == GPS_OK:
+        return
+    lib = load()
+    msg = lib.gps_last_error(handle)
+    msg = msg.decode() if msg else ""
+    if rc == GPS_ERR_NOT_PD:
+        raise NotPositiveDefinite(rc, msg, lib.gps_last_pivot(handle) if handle else 0)
+    raise GpsError(rc, msg)

@@ -1,0 +1,399 @@
+// dmma_gemm.cuh — FP64 tensor-core (DMMA.8x8x4) GEMM engine for sm_100a.
+//
+// tcgen05 has no f64 kind, so FP64 tensor math is warp-level
+// mma.sync.m8n8k4 with register accumulators and shared-memory staged operands:
+// a cp.async (LDGSTS, 16-byte, zero-filling) multi-stage pipeline feeds padded,
+// bank-conflict-free tiles.  Everything is column-major (R layout).
+//
+//   C[m,n] (op)= alpha * sum_k A[m,k] * B[k,n]
+//
+// Operand layouts (template flags) describe which index is contiguous in global memory:
+//   A_KC = false : A[m,k] at A[m + k*lda]   ("m-contiguous", a column-major M x K matrix)
+//   A_KC = true  : A[m,k] at A[k + m*lda]   (the transpose of a column-major K x M matrix)
+//   B_KC = false : B[k,n] at B[n + k*ldb]   (the transpose of a column-major N x K matrix)
+//   B_KC = true  : B[k,n] at B[k + n*ldb]   (a column-major K x N matrix)
+// Shared-memory tiles keep the global contiguous index contiguous (so the 16-byte async
+// copies are legal) and pad the leading dimension to == 4 (mod 16) doubles, which makes the
+// per-thread 8-byte fragment loads of a half-warp hit 16 distinct 8-byte banks.
+//
+// MMA mapping: the instruction computes D(8x8) = Amma(8x4,row) * Bmma(4x8,col).  We put our
+// n index on the MMA row and our m index on the MMA column, so that the two accumulator
+// values a thread owns are two *consecutive m* of one column n — a 16-byte vector in the
+// column-major C.  lane = 4*g + t:  Amma(row g, k t) <- B[k0+t, n0+g];  Bmma(k t, col g) <-
+// A[m0+g, k0+t];  acc[0/1] <-> C[m0 + 2t + {0,1}, n0 + g].
+//
+// Requirements: lda/ldb/ldc even, base pointers 16-byte aligned, tile origins even (they
+// are multiples of the tile sizes).  Edges are handled by zero-filling loads and predicated
+// stores; no padding of M, N, K is needed.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace gps {
+
+struct GemmParams {
+  const double* A;
+  const double* B;
+  int M, N, K;
+  int lda, ldb;
+  long long strideA, strideB;   // per batch entry (blockIdx.z / ksplit)
+  // tile skipping: with lower != 0 a tile is skipped when it lies entirely above the
+  // diagonal  row + diag_off == col  (tile rows m0..m0+BM-1, tile cols n0..)
+  int lower;
+  int diag_off;
+  // triangular operands: restrict the k range per tile (local coordinates)
+  int klo_n;   // k >= n0          (B lower-triangular in (k,n): B[k,n] = 0 for k < n)
+  int klo_m;   // k >= m0          (A upper-triangular in (m,k): A[m,k] = 0 for k < m)
+  int khi_m;   // k <  m0 + BM     (A lower-triangular in (m,k): A[m,k] = 0 for k > m)
+  int ksplit;  // split-K factor (>= 1); gridDim.z = batch * ksplit
+};
+
+__device__ __forceinline__ void dmma884(double& d0, double& d1, double a_mma, double b_mma) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+               : "+d"(d0), "+d"(d1)
+               : "d"(a_mma), "d"(b_mma));
+}
+
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src, int src_bytes) {
+  unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(s), "l"(gmem_src), "r"(src_bytes));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;\n" ::"n"(N));
+}
+
+template <int BM_, int BN_, int BK_, int WARPS_M_, int WARPS_N_, int STAGES_>
+struct TileCfg {
+  static constexpr int BM = BM_, BN = BN_, BK = BK_, WARPS_M = WARPS_M_, WARPS_N = WARPS_N_, STAGES = STAGES_;
+  static constexpr int NT = WARPS_M * WARPS_N * 32;
+  static constexpr int WM = BM / WARPS_M, WN = BN / WARPS_N;
+  static constexpr int FM = WM / 8, FN = WN / 8;
+  static_assert(BM % (8 * WARPS_M) == 0 && BN % (8 * WARPS_N) == 0, "warp tiling");
+  static_assert(BK % 4 == 0 && BM % BK == 0, "k tiling");
+};
+
+// Accumulator view handed to epilogues: acc[mi][ni][0..1] <-> element
+// (m = m_base + 8*mi + {0,1}, n = n_base + 8*ni) where m_base/n_base already include the
+// per-thread offsets (2t and g).
+template <class Cfg>
+struct AccTile {
+  double v[Cfg::FM][Cfg::FN][2];
+  int m_base, n_base;      // global (tile + warp + lane) coordinates of v[0][0][0]
+  int m0, n0;              // tile origin
+  int batch, split;
+};
+
+template <class Cfg, bool A_KC, bool B_KC>
+struct SmemLayout {
+  static constexpr int LDA = (A_KC ? Cfg::BK : Cfg::BM) + 4;
+  static constexpr int LDB = (B_KC ? Cfg::BK : Cfg::BN) + 4;
+  static constexpr int A_STAGE = (A_KC ? Cfg::BM : Cfg::BK) * LDA;
+  static constexpr int B_STAGE = (B_KC ? Cfg::BN : Cfg::BK) * LDB;
+  static constexpr size_t BYTES = (size_t)Cfg::STAGES * (A_STAGE + B_STAGE) * sizeof(double);
+};
+
+// Load one operand tile (R rows of the "other" index x BK of k) into a stage.
+//   KC == false: tile is BK "rows" of k, each CONT contiguous elements of the m/n index
+//   KC == true : tile is CONT "rows" of the m/n index, each BK contiguous elements of k
+template <int CONT, int BK, int LDS, int NT, bool KC>
+__device__ __forceinline__ void load_tile(double* __restrict__ s, const double* __restrict__ g, int ld,
+                                          int x0, int X, int kbase, int K, int tid) {
+  if (!KC) {
+    constexpr int CH = CONT / 2;   // 16-byte chunks per k row
+#pragma unroll
+    for (int c = tid; c < BK * CH; c += NT) {
+      int kk = c / CH, xc = (c % CH) * 2;
+      int gx = x0 + xc, gk = kbase + kk;
+      int valid = (gk < K) ? min(max(X - gx, 0), 2) : 0;
+      const double* src = valid ? (g + (size_t)gx + (size_t)gk * ld) : g;
+      cp_async16(s + kk * LDS + xc, src, valid * 8);
+    }
+  } else {
+    constexpr int CH = BK / 2;
+#pragma unroll
+    for (int c = tid; c < CONT * CH; c += NT) {
+      int xx = c / CH, kc = (c % CH) * 2;
+      int gx = x0 + xx, gk = kbase + kc;
+      int valid = (gx < X) ? min(max(K - gk, 0), 2) : 0;
+      const double* src = valid ? (g + (size_t)gk + (size_t)gx * ld) : g;
+      cp_async16(s + xx * LDS + kc, src, valid * 8);
+    }
+  }
+}
+
+// The kernel.  Epi must provide:
+//   __device__ void operator()(const GemmParams&, AccTile<Cfg>&, double* smem_scratch) const
+// called by every thread of the CTA after the main loop (smem is free to reuse after a
+// __syncthreads()).
+template <class Cfg, bool A_KC, bool B_KC, class Epi>
+__global__ void __launch_bounds__(Cfg::NT) dmma_gemm_kernel(GemmParams p, Epi epi) {
+  using SL = SmemLayout<Cfg, A_KC, B_KC>;
+  constexpr int BM = Cfg::BM, BN = Cfg::BN, BK = Cfg::BK, STAGES = Cfg::STAGES, NT = Cfg::NT;
+  constexpr int FM = Cfg::FM, FN = Cfg::FN;
+  extern __shared__ __align__(16) double smem[];
+  double* sA = smem;
+  double* sB = smem + STAGES * SL::A_STAGE;
+
+  const int tid = threadIdx.x;
+  const int warp = tid >> 5, lane = tid & 31;
+  const int g = lane >> 2, t = lane & 3;
+  const int wm0 = (warp % Cfg::WARPS_M) * Cfg::WM;
+  const int wn0 = (warp / Cfg::WARPS_M) * Cfg::WN;
+  const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
+  const int batch = blockIdx.z / p.ksplit, split = blockIdx.z % p.ksplit;
+
+  if (p.lower && (m0 + BM - 1 + p.diag_off < n0)) return;
+
+  const double* __restrict__ A = p.A + (size_t)batch * p.strideA;
+  const double* __restrict__ B = p.B + (size_t)batch * p.strideB;
+
+  int k_lo = 0, k_hi = p.K;
+  if (p.klo_n) k_lo = max(k_lo, n0);
+  if (p.klo_m) k_lo = max(k_lo, m0);
+  if (p.khi_m) k_hi = min(k_hi, m0 + BM);
+  if (p.ksplit > 1) {
+    int kc = ((p.K + BK - 1) / BK + p.ksplit - 1) / p.ksplit * BK;
+    k_lo = max(k_lo, split * kc);
+    k_hi = min(k_hi, split * kc + kc);
+  }
+  k_lo = (k_lo / BK) * BK;
+  const int nkt = (k_hi > k_lo) ? (k_hi - k_lo + BK - 1) / BK : 0;
+
+  AccTile<Cfg> acc;
+#pragma unroll
+  for (int i = 0; i < FM; i++)
+#pragma unroll
+    for (int j = 0; j < FN; j++) acc.v[i][j][0] = acc.v[i][j][1] = 0.0;
+
+  auto issue = [&](int stage, int kt) {
+    const int kbase = k_lo + kt * BK;
+    load_tile<BM, BK, SL::LDA, NT, A_KC>(sA + stage * SL::A_STAGE, A, p.lda, m0, p.M, kbase, p.K, tid);
+    load_tile<BN, BK, SL::LDB, NT, B_KC>(sB + stage * SL::B_STAGE, B, p.ldb, n0, p.N, kbase, p.K, tid);
+  };
+
+#pragma unroll
+  for (int s = 0; s < STAGES - 1; s++) {
+    if (s < nkt) issue(s, s);
+    cp_async_commit();
+  }
+
+  for (int kt = 0; kt < nkt; kt++) {
+    cp_async_wait<STAGES - 2>();
+    __syncthreads();
+    {
+      int nx = kt + STAGES - 1;
+      if (nx < nkt) issue(nx % STAGES, nx);
+      cp_async_commit();
+    }
+    const double* a_s = sA + (kt % STAGES) * SL::A_STAGE;
+    const double* b_s = sB + (kt % STAGES) * SL::B_STAGE;
+#pragma unroll
+    for (int ks = 0; ks < BK / 4; ks++) {
+      double af[FM], bf[FN];
+#pragma unroll
+      for (int i = 0; i < FM; i++) {
+        int m = wm0 + 8 * i + g, k = 4 * ks + t;
+        af[i] = A_KC ? a_s[m * SL::LDA + k] : a_s[k * SL::LDA + m];
+      }
+#pragma unroll
+      for (int j = 0; j < FN; j++) {
+        int n = wn0 + 8 * j + g, k = 4 * ks + t;
+        bf[j] = B_KC ? b_s[n * SL::LDB + k] : b_s[k * SL::LDB + n];
+      }
+#pragma unroll
+      for (int i = 0; i < FM; i++)
+#pragma unroll
+        for (int j = 0; j < FN; j++) dmma884(acc.v[i][j][0], acc.v[i][j][1], bf[j], af[i]);
+    }
+  }
+  cp_async_wait<0>();
+  __syncthreads();   // smem reusable by the epilogue
+
+  acc.m0 = m0;
+  acc.n0 = n0;
+  acc.m_base = m0 + wm0 + 2 * t;
+  acc.n_base = n0 + wn0 + g;
+  acc.batch = batch;
+  acc.split = split;
+  epi(p, acc, smem);
+}
+
+// ---------------------------------------------------------------------------------------
+// Epilogues
+// ---------------------------------------------------------------------------------------
+
+// C = alpha*acc + beta*C.  With ksplit > 1 the split index selects a workspace slice
+// (strideSplit) and beta must be 0.
+struct EpiPlain {
+  double* C;
+  int ldc;
+  long long strideC;       // per batch
+  long long strideSplit;   // per split slice (0 if ksplit == 1)
+  double alpha, beta;
+  int lower_strict_mask;   // 1: do not write elements with row + diag_off < col (keeps upper triangle untouched)
+  int diag_off;
+  template <class Cfg>
+  __device__ __forceinline__ void operator()(const GemmParams& p, AccTile<Cfg>& a, double*) const {
+    double* __restrict__ Cb = C + (size_t)a.batch * strideC + (size_t)a.split * strideSplit;
+#pragma unroll
+    for (int j = 0; j < Cfg::FN; j++) {
+      int n = a.n_base + 8 * j;
+      if (n >= p.N) continue;
+#pragma unroll
+      for (int i = 0; i < Cfg::FM; i++) {
+        int m = a.m_base + 8 * i;
+        if (m >= p.M) continue;
+        double* c = Cb + (size_t)m + (size_t)n * ldc;
+        bool w0 = !lower_strict_mask || (m + diag_off >= n);
+        bool w1 = (m + 1 < p.M) && (!lower_strict_mask || (m + 1 + diag_off >= n));
+        double r0 = alpha * a.v[i][j][0], r1 = alpha * a.v[i][j][1];
+        if (w0 && w1) {
+          double2 o = make_double2(0.0, 0.0);
+          if (beta != 0.0) o = *reinterpret_cast<const double2*>(c);
+          *reinterpret_cast<double2*>(c) = make_double2(r0 + beta * o.x, r1 + beta * o.y);
+        } else {
+          if (w0) c[0] = r0 + (beta != 0.0 ? beta * c[0] : 0.0);
+          if (w1) c[1] = r1 + (beta != 0.0 ? beta * c[1] : 0.0);
+        }
+      }
+    }
+  }
+};
+
+// Squared-exponential covariance epilogue (CovFunc.R:38-39 on the Gram form):
+//   r2 = max(0, sA[m] + sB[n] - 2*G[m,n]);  K = sf2 * exp(-r2/2);
+// symmetric case (sym != 0): the diagonal is written as exactly sf2 and Ky additionally gets
+// noise_diag[m] on the diagonal (ForOptimisationLog.R:35-40).  Hyper-parameters are read
+// from device memory so that the launch is CUDA-graph static.
+struct EpiCov {
+  const double* normA;     // [batch][ldn] squared row norms of the scaled A rows
+  const double* normB;
+  const double* hyp;       // [batch][4]: sn2, sf2, sc2, -
+  const double* noise_diag;   // [batch][ldn] or nullptr
+  double* Kout;            // noise-free covariance (may be nullptr)
+  double* Kyout;           // covariance + noise on the diagonal (may be nullptr)
+  int ldk, ldn, ldnB;      // ldn / ldnB: per-batch strides of normA (and noise_diag) / normB
+  long long strideK;
+  int sym;
+  template <class Cfg>
+  __device__ __forceinline__ void operator()(const GemmParams& p, AccTile<Cfg>& a, double*) const {
+    const double s2 = hyp[a.batch * 4 + 1];
+    const double* nA = normA + (size_t)a.batch * ldn;
+    const double* nB = normB + (size_t)a.batch * ldnB;
+    const double* nd = noise_diag ? noise_diag + (size_t)a.batch * ldn : nullptr;
+    double* Kb = Kout ? Kout + (size_t)a.batch * strideK : nullptr;
+    double* Kyb = Kyout ? Kyout + (size_t)a.batch * strideK : nullptr;
+#pragma unroll
+    for (int j = 0; j < Cfg::FN; j++) {
+      int n = a.n_base + 8 * j;
+      if (n >= p.N) continue;
+      double sn = nB[n];
+#pragma unroll
+      for (int i = 0; i < Cfg::FM; i++) {
+        int m = a.m_base + 8 * i;
+#pragma unroll
+        for (int e = 0; e < 2; e++) {
+          int mm = m + e;
+          if (mm >= p.M) continue;
+          double r2 = fmax(0.0, nA[mm] + sn - 2.0 * a.v[i][j][e]);
+          double k = s2 * exp(-0.5 * r2);
+          double ky = k;
+          if (sym && mm == n) {
+            k = s2;
+            ky = nd ? s2 + nd[mm] : s2;
+          }
+          size_t off = (size_t)mm + (size_t)n * ldk;
+          if (Kb) Kb[off] = k;
+          if (Kyb) Kyb[off] = ky;
+        }
+      }
+    }
+  }
+};
+
+// Gradient contraction epilogue (north_star item 4): P = M * Xaug is never written.
+//   colpart[mtile][n] = sum_{m in tile} Xaug[m,n] * P[m,n]      (deterministic per-tile partials)
+//   rs[m]            = P[m, N-1]                                  (Xaug's last column is all ones => rowsum(M))
+struct EpiColDot {
+  const double* X;   // Xaug, column-major, ldx
+  int ldx;
+  long long strideX;
+  double* colpart;   // [batch][mtiles][ldp]
+  int ldp, mtiles;
+  double* rs;        // [batch][ldn]
+  int ldn;
+  template <class Cfg>
+  __device__ __forceinline__ void operator()(const GemmParams& p, AccTile<Cfg>& a, double* smem) const {
+    const double* __restrict__ Xb = X + (size_t)a.batch * strideX;
+    double part[Cfg::FN];
+#pragma unroll
+    for (int j = 0; j < Cfg::FN; j++) {
+      int n = a.n_base + 8 * j;
+      double s = 0.0;
+      if (n < p.N) {
+#pragma unroll
+        for (int i = 0; i < Cfg::FM; i++) {
+          int m = a.m_base + 8 * i;
+          if (m < p.M) s += Xb[(size_t)m + (size_t)n * ldx] * a.v[i][j][0];
+          if (m + 1 < p.M) s += Xb[(size_t)m + 1 + (size_t)n * ldx] * a.v[i][j][1];
+          if (n == p.N - 1) {
+            double* r = rs + (size_t)a.batch * ldn;
+            if (m < p.M) r[m] = a.v[i][j][0];
+            if (m + 1 < p.M) r[m + 1] = a.v[i][j][1];
+          }
+        }
+      }
+      // fixed-order reduction over the 4 lanes (t) that share column n
+      s += __shfl_xor_sync(0xffffffffu, s, 1);
+      s += __shfl_xor_sync(0xffffffffu, s, 2);
+      part[j] = s;
+    }
+    // across the WARPS_M warps that share the same columns: shared memory, fixed order
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int wmi = warp % Cfg::WARPS_M;
+    const int wn0 = (warp / Cfg::WARPS_M) * Cfg::WN;
+    double* red = smem;   // [WARPS_M][BN]
+    if ((lane & 3) == 0) {
+#pragma unroll
+      for (int j = 0; j < Cfg::FN; j++) red[wmi * Cfg::BN + wn0 + 8 * j + (lane >> 2)] = part[j];
+    }
+    __syncthreads();
+    for (int c = threadIdx.x; c < Cfg::BN; c += Cfg::NT) {
+      int n = a.n0 + c;
+      if (n < p.N) {
+        double s = 0.0;
+#pragma unroll
+        for (int w = 0; w < Cfg::WARPS_M; w++) s += red[w * Cfg::BN + c];
+        colpart[((size_t)a.batch * mtiles + blockIdx.x) * ldp + n] = s;
+      }
+    }
+  }
+};
+
+// ---------------------------------------------------------------------------------------
+// Launch helper
+// ---------------------------------------------------------------------------------------
+using CfgLarge = TileCfg<128, 128, 16, 2, 4, 4>;
+using CfgSmall = TileCfg<64, 64, 16, 2, 2, 4>;
+
+template <class Cfg, bool A_KC, bool B_KC, class Epi>
+cudaError_t launch_gemm(const GemmParams& p, const Epi& epi, int batch, cudaStream_t st) {
+  using SL = SmemLayout<Cfg, A_KC, B_KC>;
+  auto kern = dmma_gemm_kernel<Cfg, A_KC, B_KC, Epi>;
+  static bool attr_set[64] = {false};   // per instantiation, per device
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (!attr_set[dev & 63]) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SL::BYTES);
+    if (e != cudaSuccess) return e;
+    attr_set[dev & 63] = true;
+  }
+  if (p.M <= 0 || p.N <= 0) return cudaSuccess;
+  dim3 grid((p.M + Cfg::BM - 1) / Cfg::BM, (p.N + Cfg::BN - 1) / Cfg::BN, batch * p.ksplit);
+  kern<<<grid, Cfg::NT, SL::BYTES, st>>>(p, epi);
+  return cudaGetLastError();
+}
+
+}  // namespace gps

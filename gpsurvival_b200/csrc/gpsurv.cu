@@ -1,0 +1,1239 @@
+// gpsurv.cu — libgpsurv.so: handle, evaluation sequences and the C ABI (include/gpsurv.h).
+//
+// One evaluation of the reference's ForOptimisationLog (+ OptimisationGradientLog) is a fixed
+// sequence of launches whose every parameter lives in device memory, replayed as a CUDA graph:
+//
+//   hyp_prep -> prescale/rownorm -> DMMA Gram + SE epilogue (K, Ky) -> fill_aug (y rows)
+//   -> recursive blocked Cholesky (potf2+inverse leaves, DMMA TRSM-as-GEMM panels, DMMA
+//      SYRK/GEMM trailing updates; the appended y row makes the forward solve free)
+//   -> nlml_finish                                               [level 1: NLML]
+//   -> recursive triangular inverse (DMMA) -> alpha = L^-T z     [level 2: model]
+//   -> Kinv = Linv' Linv (DMMA) -> W o K -> (W o K) Xaug (DMMA, fused column-dot epilogue)
+//   -> grad_cols -> grad_finish                                  [level 3: gradient]
+//
+// There is no CPU fallback anywhere in this file: without a CUDA device every entry point
+// returns GPS_ERR_CUDA.
+#include "../../include/gpsurv.h"
+
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <string>
+#include <vector>
+
+#include "dmma_gemm.cuh"
+#include "kernels.cuh"
+
+using namespace gps;
+
+namespace {
+
+inline int round_up(int x, int m) { return (x + m - 1) / m * m; }
+inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
+
+thread_local std::string g_tls_error;
+
+struct DevBuf {
+  void* p = nullptr;
+  size_t bytes = 0;
+};
+
+}  // namespace
+
+struct gps_handle_s {
+  int device = 0;
+  int batch = 1;
+  cudaStream_t st = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  ModelOpts o{0, 0, 0, 0};
+  bool have_data = false;
+  int n = 0, d = 0, p = 1, ne = 0, nrhs = 1, naug = 0;
+  int ld = 0, ldx = 0, ldmu = 0, ldc = 0;
+  long long strideM = 0, strideX = 0;
+  int ncens_max = 0;
+  std::vector<int> ncens;
+
+  // data
+  double *Xaug = nullptr, *Z = nullptr, *mu = nullptr, *y = nullptr, *events = nullptr, *lsc = nullptr;
+  int *cens_rank = nullptr, *d_ncens = nullptr;
+  // per-evaluation small state
+  double *par = nullptr, *hyp = nullptr, *ell = nullptr, *meanw = nullptr, *noise_diag = nullptr;
+  double *rnpart = nullptr, *rnorm = nullptr, *meanv = nullptr, *zvec = nullptr, *alpha = nullptr;
+  double *wdiag = nullptr, *rs = nullptr, *colpart = nullptr, *qtu = nullptr, *d_nlml = nullptr, *d_logdet = nullptr,
+         *d_grad = nullptr;
+  int* info = nullptr;
+  int par_cap = 0;
+  int rn_ksplit = 1, gram_ksplit = 1, mtiles_grad = 1;
+  // matrices (work set)
+  double *K = nullptr, *Ky = nullptr, *L = nullptr, *Linv = nullptr, *Kinv = nullptr, *gsplit = nullptr;
+  size_t gsplit_elems = 0;
+  // resident model (after gps_regress_finalize)
+  double *mL = nullptr, *mLinv = nullptr, *m_alpha = nullptr, *m_hyp = nullptr, *m_ell = nullptr, *m_meanw = nullptr;
+  bool model_valid = false;
+  std::vector<double> model_par;
+  long long model_tv = -1, model_ncv = -1;
+  // predict scratch
+  double *Xs = nullptr, *Zs = nullptr, *snorm = nullptr, *snpart = nullptr, *Ks = nullptr, *V = nullptr, *mstar = nullptr,
+         *pout = nullptr;
+  int m_cap = 0, lds = 0;
+  // adjust scratch
+  double* adj = nullptr;
+  int adj_cap = 0;
+  // pinned staging
+  double* pin = nullptr;
+  size_t pin_elems = 0;
+  int* pin_info = nullptr;
+  // cache keys
+  std::vector<double> fact_par;
+  long long targets_version = 0, nc_version = 0, fact_tv = -1, fact_ncv = -1;
+  int fact_level = 0;
+  // graphs
+  bool graphs_enabled = true;
+  cudaGraphExec_t g_factor = nullptr, g_inverse = nullptr, g_grad = nullptr;
+  int warm_factor = 0, warm_inverse = 0, warm_grad = 0;
+  long long cnt_factor = 0, cnt_inverse = 0, cnt_grad = 0;
+  // bookkeeping
+  long long launches = 0;
+  long long seq_launches = 0;   // launches issued by the sequence being recorded
+  double last_ms = 0.0;
+  int last_pivot = 0;
+  std::string err;
+  cudaError_t cu_err = cudaSuccess;
+};
+
+typedef gps_handle_s H;
+
+namespace {
+
+int fail(H* h, int code, const std::string& msg) {
+  if (h) h->err = msg;
+  g_tls_error = msg;
+  return code;
+}
+
+#define CK(h, call)                                                                          \
+  do {                                                                                       \
+    cudaError_t e__ = (call);                                                                \
+    if (e__ != cudaSuccess) {                                                                \
+      char buf__[512];                                                                       \
+      snprintf(buf__, sizeof buf__, "CUDA error %s at %s:%d (%s)", cudaGetErrorString(e__), __FILE__, __LINE__, #call); \
+      return fail(h, GPS_ERR_CUDA, buf__);                                                   \
+    }                                                                                        \
+  } while (0)
+
+// inside the void enqueue_* helpers: remember the first error, keep going
+#define CKV(h, call)                                             \
+  do {                                                           \
+    cudaError_t e__ = (call);                                    \
+    if (e__ != cudaSuccess && (h)->cu_err == cudaSuccess) {      \
+      (h)->cu_err = e__;                                         \
+      char buf__[512];                                           \
+      snprintf(buf__, sizeof buf__, "CUDA error %s at %s:%d (%s)", cudaGetErrorString(e__), __FILE__, __LINE__, #call); \
+      (h)->err = buf__;                                          \
+    }                                                            \
+  } while (0)
+
+#define LAUNCHED(h) do { (h)->seq_launches++; CKV(h, cudaGetLastError()); } while (0)
+
+// All zero-fills and copies are issued on the handle's own (non-blocking) stream: the legacy
+// default stream is NOT ordered with it, and a "synchronous" pageable H2D copy may return
+// before its DMA has landed.
+thread_local cudaStream_t g_alloc_stream = nullptr;
+template <class T>
+cudaError_t dalloc(T** p, size_t elems, bool zero = true) {
+  if (elems == 0) elems = 1;
+  cudaError_t e = cudaMalloc((void**)p, elems * sizeof(T));
+  if (e != cudaSuccess) return e;
+  if (zero) return cudaMemsetAsync(*p, 0, elems * sizeof(T), g_alloc_stream);
+  return cudaSuccess;
+}
+template <class T>
+void dfree(T*& p) {
+  if (p) cudaFree(p);
+  p = nullptr;
+}
+
+void free_data(H* h) {
+  dfree(h->Xaug); dfree(h->Z); dfree(h->mu); dfree(h->y); dfree(h->events); dfree(h->lsc);
+  dfree(h->cens_rank); dfree(h->d_ncens);
+  dfree(h->par); dfree(h->hyp); dfree(h->ell); dfree(h->meanw); dfree(h->noise_diag);
+  dfree(h->rnpart); dfree(h->rnorm); dfree(h->meanv); dfree(h->zvec); dfree(h->alpha);
+  dfree(h->wdiag); dfree(h->rs); dfree(h->colpart); dfree(h->qtu); dfree(h->d_nlml); dfree(h->d_logdet);
+  dfree(h->d_grad); dfree(h->info);
+  dfree(h->K); dfree(h->Ky); dfree(h->L); dfree(h->Linv); dfree(h->Kinv); dfree(h->gsplit);
+  dfree(h->mL); dfree(h->mLinv); dfree(h->m_alpha); dfree(h->m_hyp); dfree(h->m_ell); dfree(h->m_meanw);
+  dfree(h->Xs); dfree(h->Zs); dfree(h->snorm); dfree(h->snpart); dfree(h->Ks); dfree(h->V); dfree(h->mstar);
+  dfree(h->pout);
+  h->m_cap = 0;
+  h->gsplit_elems = 0;
+  h->par_cap = 0;
+  h->have_data = false;
+  h->model_valid = false;
+  h->fact_level = 0;
+}
+
+void drop_graphs(H* h) {
+  if (h->g_factor) cudaGraphExecDestroy(h->g_factor);
+  if (h->g_inverse) cudaGraphExecDestroy(h->g_inverse);
+  if (h->g_grad) cudaGraphExecDestroy(h->g_grad);
+  h->g_factor = h->g_inverse = h->g_grad = nullptr;
+  h->warm_factor = h->warm_inverse = h->warm_grad = 0;
+}
+
+int expected_len(const H* h) {
+  return 2 + h->p + (h->o.mean_form == 1 ? h->d + 1 : 0) + (h->o.noise_corr == 1 ? 1 : 0);
+}
+
+// ---------------------------------------------------------------------------------------
+// GEMM dispatch: pick the tile configuration from the amount of tile-level parallelism.
+// ---------------------------------------------------------------------------------------
+template <bool A_KC, bool B_KC, class Epi>
+void gemm(H* h, const GemmParams& p, const Epi& epi) {
+  long long tl = (long long)ceil_div(p.M, 128) * ceil_div(p.N, 128);
+  if (p.lower) tl = tl / 2 + 1;
+  tl *= (long long)h->batch * p.ksplit;
+  cudaError_t e;
+  if (tl >= 100 && p.N >= 96)
+    e = launch_gemm<CfgLarge, A_KC, B_KC, Epi>(p, epi, h->batch, h->st);
+  else
+    e = launch_gemm<CfgSmall, A_KC, B_KC, Epi>(p, epi, h->batch, h->st);
+  h->seq_launches++;
+  CKV(h, e);
+}
+
+GemmParams gp(const double* A, int lda, long long sA, const double* B, int ldb, long long sB, int M, int N, int K) {
+  GemmParams p;
+  memset(&p, 0, sizeof p);
+  p.A = A; p.B = B; p.M = M; p.N = N; p.K = K; p.lda = lda; p.ldb = ldb; p.strideA = sA; p.strideB = sB;
+  p.ksplit = 1;
+  return p;
+}
+
+EpiPlain plain(double* C, int ldc, long long sC, double alpha, double beta) {
+  EpiPlain e;
+  e.C = C; e.ldc = ldc; e.strideC = sC; e.strideSplit = 0; e.alpha = alpha; e.beta = beta;
+  e.lower_strict_mask = 0; e.diag_off = 0;
+  return e;
+}
+
+// ---------------------------------------------------------------------------------------
+// Covariance: Z (n1 x d), Zs (n2 x d) already scaled; writes Kout / Kyout.
+// ---------------------------------------------------------------------------------------
+int pick_gram_ksplit(const H* h, int n1, int n2, int d, bool sym) {
+  if (const char* ev = getenv("GPS_KSPLIT")) {   // developer override (tests of the split-K path)
+    int v = atoi(ev);
+    if (v >= 1) return v > 32 ? 32 : v;
+  }
+  long long tiles = (long long)ceil_div(n1, 64) * ceil_div(n2, 64);
+  if (sym) tiles = tiles / 2 + 1;
+  tiles *= h->batch;
+  if (tiles >= 148 || d < 256) return 1;
+  int ks = (int)((2 * 148 + tiles - 1) / tiles);
+  int maxks = d / 128;
+  if (ks > maxks) ks = maxks;
+  if (ks > 32) ks = 32;
+  return ks < 1 ? 1 : ks;
+}
+
+void enqueue_cov(H* h, const double* Za, int n1, int lda, long long sA, const double* normA, const double* Zb,
+                 int n2, int ldb, long long sB, const double* normB, int d, const double* hyp,
+                 const double* noise_diag, double* Kout, double* Kyout, int ldk, long long sK, bool sym, int ksplit) {
+  GemmParams p = gp(Za, lda, sA, Zb, ldb, sB, n1, n2, d);
+  p.lower = sym ? 1 : 0;
+  if (ksplit <= 1) {
+    EpiCov e;
+    e.normA = normA; e.normB = normB; e.hyp = hyp; e.noise_diag = noise_diag; e.Kout = Kout; e.Kyout = Kyout;
+    e.ldk = ldk; e.ldn = h->ld; e.ldnB = h->ld; e.strideK = sK; e.sym = sym ? 1 : 0;
+    gemm<false, false>(h, p, e);
+  } else {
+    p.ksplit = ksplit;
+    EpiPlain e = plain(h->gsplit, ldk, (long long)ksplit * sK, 1.0, 0.0);
+    e.strideSplit = sK;
+    gemm<false, false>(h, p, e);
+    dim3 grid(ceil_div(n1, 32), ceil_div(n2, 8), h->batch), block(32, 8);
+    cov_finish_kernel<<<grid, block, 0, h->st>>>(h->gsplit, n1, n2, ldk, sK, (long long)ksplit * sK, ksplit, normA,
+                                                  normB, h->ld, hyp, noise_diag, Kout, Kyout, ldk, sK, sym ? 1 : 0);
+    LAUNCHED(h);
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// Recursive blocked Cholesky over block columns [j0, j1) (units of NB).  Precondition: all
+// updates from columns < j0*NB are already applied to Ky[:, j0*NB : j1*NB].  Rows run to
+// naug, i.e. the appended right-hand-side rows are carried along (forward solve for free).
+// ---------------------------------------------------------------------------------------
+void potrf_range(H* h, int j0, int j1) {
+  const int ld = h->ld;
+  const long long sM = h->strideM;
+  if (j1 - j0 == 1) {
+    int e0 = j0 * NB, nb = (h->ne - e0 < NB) ? h->ne - e0 : NB;
+    potf2_inv_kernel<<<h->batch, 256, LEAF_SMEM, h->st>>>(h->Ky, h->L, h->Linv, ld, sM, e0, nb, h->info);
+    LAUNCHED(h);
+    int e1 = e0 + nb, M = h->naug - e1;
+    if (M > 0) {
+      // L[e1:, e0:e1] = Ky[e1:, e0:e1] * Linv11'   (TRSM as a GEMM with the inverted leaf)
+      GemmParams p = gp(h->Ky + e1 + (size_t)e0 * ld, ld, sM, h->Linv + e0 + (size_t)e0 * ld, ld, sM, M, nb, nb);
+      gemm<false, false>(h, p, plain(h->L + e1 + (size_t)e0 * ld, ld, sM, 1.0, 0.0));
+    }
+    return;
+  }
+  int mid = j0 + (j1 - j0 + 1) / 2;
+  potrf_range(h, j0, mid);
+  int r0 = mid * NB, c0 = j0 * NB, c1 = (j1 * NB < h->ne) ? j1 * NB : h->ne;
+  // Ky[r0:naug, r0:c1] -= L[r0:naug, c0:r0] * L[r0:c1, c0:r0]'
+  GemmParams p = gp(h->L + r0 + (size_t)c0 * ld, ld, sM, h->L + r0 + (size_t)c0 * ld, ld, sM, h->naug - r0, c1 - r0,
+                    r0 - c0);
+  p.lower = 1;
+  gemm<false, false>(h, p, plain(h->Ky + r0 + (size_t)r0 * ld, ld, sM, -1.0, 1.0));
+  potrf_range(h, mid, j1);
+}
+
+// Recursive inverse of the lower-triangular factor: the NB leaves were inverted by
+// potf2_inv_kernel; merge  Linv21 = -Linv22 * (L21 * Linv11)  bottom-up.  Kinv is the temporary.
+void trtri_range(H* h, int j0, int j1) {
+  if (j1 - j0 <= 1) return;
+  const int ld = h->ld;
+  const long long sM = h->strideM;
+  int mid = j0 + (j1 - j0 + 1) / 2;
+  trtri_range(h, j0, mid);
+  trtri_range(h, mid, j1);
+  int c0 = j0 * NB, r0 = mid * NB, r1 = (j1 * NB < h->ne) ? j1 * NB : h->ne;
+  int Mr = r1 - r0, Kc = r0 - c0;
+  if (Mr <= 0) return;
+  double* T = h->Kinv + r0 + (size_t)c0 * ld;
+  {  // T = L21 * Linv11   (Linv11 lower: k >= n)
+    GemmParams p = gp(h->L + r0 + (size_t)c0 * ld, ld, sM, h->Linv + c0 + (size_t)c0 * ld, ld, sM, Mr, Kc, Kc);
+    p.klo_n = 1;
+    gemm<false, true>(h, p, plain(T, ld, sM, 1.0, 0.0));
+  }
+  {  // Linv21 = -Linv22 * T   (Linv22 lower: k <= m)
+    GemmParams p = gp(h->Linv + r0 + (size_t)r0 * ld, ld, sM, T, ld, sM, Mr, Kc, Mr);
+    p.khi_m = 1;
+    gemm<false, true>(h, p, plain(h->Linv + r0 + (size_t)c0 * ld, ld, sM, -1.0, 0.0));
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// Evaluation sequences (enqueue only; no host synchronisation inside)
+// ---------------------------------------------------------------------------------------
+void enqueue_prescale_train(H* h, const double* ell, int ell_batched) {
+  dim3 grid(ceil_div(h->n, 128), h->rn_ksplit, h->batch);
+  prescale_kernel<<<grid, 128, 0, h->st>>>(h->Xaug, h->n, h->d, h->ldx, h->strideX, h->mu, h->ldmu, ell, h->ldmu,
+                                            h->p, h->o.ard_mode == 1 && h->p > 1, h->n, h->Z, h->ldx, h->strideX,
+                                            h->rnpart, h->ld, h->rn_ksplit, ell_batched, 1);
+  LAUNCHED(h);
+  rownorm_finish_kernel<<<dim3(ceil_div(h->n, 256), h->batch), 256, 0, h->st>>>(h->rnpart, h->n, h->ld,
+                                                                                 h->rn_ksplit, h->rnorm);
+  LAUNCHED(h);
+}
+
+void enqueue_factor(H* h) {
+  const int n = h->n;
+  CKV(h, cudaMemsetAsync(h->info, 0, sizeof(int) * h->batch, h->st));
+  hyp_prep_kernel<<<h->batch, 256, 0, h->st>>>(h->par, h->par_cap, h->o, n, h->d, h->p, h->events, h->cens_rank, h->lsc,
+                                                h->ldc, h->ld, h->mu, h->ldmu, h->hyp, h->ell, h->ldmu, h->meanw,
+                                                h->noise_diag);
+  LAUNCHED(h);
+  enqueue_prescale_train(h, h->ell, 1);
+  enqueue_cov(h, h->Z, n, h->ldx, h->strideX, h->rnorm, h->Z, n, h->ldx, h->strideX, h->rnorm, h->d, h->hyp,
+              h->noise_diag, h->K, h->Ky, h->ld, h->strideM, true, h->gram_ksplit);
+  fill_aug_kernel<<<dim3(ceil_div(h->ne, 128), h->batch), 128, 0, h->st>>>(
+      h->Xaug, n, h->ne, h->d, h->ldx, h->strideX, h->meanw, h->ldmu, h->o.mean_form == 1, h->y, h->ld, h->meanv, h->Ky,
+      h->ld, h->strideM, h->nrhs);
+  LAUNCHED(h);
+  potrf_range(h, 0, ceil_div(h->ne, NB));
+  nlml_finish_kernel<<<h->batch, 256, 0, h->st>>>(h->L, n, h->ne, h->ld, h->strideM, h->nrhs, h->zvec, h->ld, h->d_nlml,
+                                                   h->d_logdet);
+  LAUNCHED(h);
+}
+
+void enqueue_inverse(H* h) {
+  trtri_range(h, 0, ceil_div(h->ne, NB));
+  alpha_kernel<<<dim3(ceil_div(h->n, 8), h->nrhs, h->batch), 256, 0, h->st>>>(h->Linv, h->n, h->ld, h->strideM, h->zvec,
+                                                                               h->ld, h->alpha);
+  LAUNCHED(h);
+}
+
+void enqueue_grad(H* h) {
+  const int n = h->n, ld = h->ld;
+  const long long sM = h->strideM;
+  {  // Kinv = Linv' * Linv  (lower tiles; k >= m because Linv is lower triangular)
+    GemmParams p = gp(h->Linv, ld, sM, h->Linv, ld, sM, h->ne, h->ne, h->ne);
+    p.lower = 1;
+    p.klo_m = 1;
+    gemm<true, true>(h, p, plain(h->Kinv, ld, sM, 1.0, 0.0));
+  }
+  // M = (a a' - Kinv) o K  into the (now free) Ky buffer
+  const double* aw = h->alpha + (h->nrhs == 2 ? h->ld : 0);
+  wk_kernel<<<dim3(ceil_div(n, 32), ceil_div(n, 32), h->batch), dim3(32, 8), 0, h->st>>>(h->Kinv, h->K, n, ld, sM, aw,
+                                                                                       h->ld, h->Ky, h->wdiag);
+  LAUNCHED(h);
+  {  // (M Xaug) contracted with Xaug column by column; last column gives rowsum(M)
+    GemmParams p = gp(h->Ky, ld, sM, h->Xaug, h->ldx, h->strideX, n, h->d + 1, n);
+    EpiColDot e;
+    e.X = h->Xaug; e.ldx = h->ldx; e.strideX = h->strideX; e.colpart = h->colpart; e.ldp = h->ldmu;
+    e.rs = h->rs; e.ldn = h->ld;
+    // the tile config decides the number of m tiles: mirror gemm()'s choice
+    long long tl = (long long)ceil_div(n, 128) * ceil_div(h->d + 1, 128) * h->batch;
+    bool large = (tl >= 100 && h->d + 1 >= 96);
+    e.mtiles = ceil_div(n, large ? 128 : 64);
+    h->mtiles_grad = e.mtiles;
+    gemm<false, true>(h, p, e);
+  }
+  grad_cols_kernel<<<dim3(ceil_div(h->d + 1, 8), h->batch), 256, 0, h->st>>>(h->Xaug, n, h->d, h->ldx, h->strideX,
+                                                                             h->colpart, h->ldmu, h->mtiles_grad, h->rs,
+                                                                             h->alpha, h->ld, h->qtu);
+  LAUNCHED(h);
+  grad_finish_kernel<<<h->batch, 256, 0, h->st>>>(h->qtu, h->ldmu, n, h->d, h->p, h->o, h->wdiag, h->cens_rank, h->ld,
+                                                   h->hyp, h->ell, h->ldmu, h->mu, h->ldmu, h->par_cap, h->d_grad);
+  LAUNCHED(h);
+}
+
+typedef void (*SeqFn)(H*);
+
+// Run a sequence: first call direct (also sets kernel attributes), second call captures a
+// CUDA graph, later calls replay it.
+int run_seq(H* h, SeqFn fn, cudaGraphExec_t* gexec, int* warm, long long* cnt) {
+  h->cu_err = cudaSuccess;
+  if (h->graphs_enabled && *gexec) {
+    CK(h, cudaGraphLaunch(*gexec, h->st));
+    h->launches += *cnt;
+    return GPS_OK;
+  }
+  if (h->graphs_enabled && *warm >= 1) {
+    cudaGraph_t graph = nullptr;
+    h->seq_launches = 0;
+    CK(h, cudaStreamBeginCapture(h->st, cudaStreamCaptureModeThreadLocal));
+    fn(h);
+    cudaError_t e = cudaStreamEndCapture(h->st, &graph);
+    if (e != cudaSuccess || h->cu_err != cudaSuccess) {
+      if (graph) cudaGraphDestroy(graph);
+      (void)cudaGetLastError();
+      return fail(h, GPS_ERR_CUDA, std::string("graph capture failed: ") + (h->err.empty() ? cudaGetErrorString(e) : h->err));
+    }
+    *cnt = h->seq_launches;
+    e = cudaGraphInstantiate(gexec, graph, 0);
+    cudaGraphDestroy(graph);
+    if (e != cudaSuccess) {
+      *gexec = nullptr;
+      return fail(h, GPS_ERR_CUDA, std::string("graph instantiate failed: ") + cudaGetErrorString(e));
+    }
+    CK(h, cudaGraphLaunch(*gexec, h->st));
+    h->launches += *cnt;
+    return GPS_OK;
+  }
+  h->seq_launches = 0;
+  fn(h);
+  h->launches += h->seq_launches;
+  *cnt = h->seq_launches;
+  (*warm)++;
+  if (h->cu_err != cudaSuccess) return fail(h, GPS_ERR_CUDA, h->err);
+  return GPS_OK;
+}
+
+int run_factor(H* h) { return run_seq(h, enqueue_factor, &h->g_factor, &h->warm_factor, &h->cnt_factor); }
+int run_inverse(H* h) { return run_seq(h, enqueue_inverse, &h->g_inverse, &h->warm_inverse, &h->cnt_inverse); }
+int run_grad(H* h) { return run_seq(h, enqueue_grad, &h->g_grad, &h->warm_grad, &h->cnt_grad); }
+
+int ensure_pin(H* h, size_t elems) {
+  if (h->pin_elems >= elems) return GPS_OK;
+  if (h->pin) cudaFreeHost(h->pin);
+  h->pin = nullptr;
+  CK(h, cudaMallocHost((void**)&h->pin, elems * sizeof(double)));
+  h->pin_elems = elems;
+  return GPS_OK;
+}
+
+bool par_close(const std::vector<double>& a, const double* b, size_t len) {
+  if (a.size() != len) return false;
+  for (size_t i = 0; i < len; i++) {
+    double x = a[i], y = b[i];
+    if (x == y) continue;
+    // hyper-parameters that went through the reference's log(exp(.)) round trip
+    // (GPRegression.R:73 -> GPPredict.R:24-28) differ by a few ulp; treat them as equal
+    double tol = 8.0 * 2.220446049250313e-16 * fmax(1.0, fmax(fabs(x), fabs(y)));
+    if (!(fabs(x - y) <= tol)) return false;
+  }
+  return true;
+}
+
+int upload_par(H* h, const double* par, int len) {
+  if (!h->have_data) return fail(h, GPS_ERR_STATE, "gps_set_data has not been called");
+  if (!par) return fail(h, GPS_ERR_ARG, "par is NULL");
+  if (len != expected_len(h)) {
+    char b[256];
+    snprintf(b, sizeof b, "par has length %d, expected %d for these options", len, expected_len(h));
+    return fail(h, GPS_ERR_ARG, b);
+  }
+  size_t tot = (size_t)len * h->batch;
+  for (size_t i = 0; i < tot; i++)
+    if (!isfinite(par[i])) return fail(h, GPS_ERR_ARG, "par contains NaN or Inf");
+  int rc = ensure_pin(h, tot + 4096);
+  if (rc) return rc;
+  memcpy(h->pin, par, tot * sizeof(double));
+  if (h->par_cap != len) {   // par length is baked into graphs via par_cap
+    h->par_cap = len;
+    drop_graphs(h);
+  }
+  CK(h, cudaMemcpyAsync(h->par, h->pin, tot * sizeof(double), cudaMemcpyHostToDevice, h->st));
+  return GPS_OK;
+}
+
+// Level-1 evaluation with cache: returns nlml values in h->pin[0..batch)
+int do_factor(H* h, const double* par, int len, bool force) {
+  size_t tot = (size_t)len * h->batch;
+  bool hit = !force && h->fact_level >= 1 && h->fact_tv == h->targets_version && h->fact_ncv == h->nc_version &&
+             h->fact_par.size() == tot && memcmp(h->fact_par.data(), par, tot * sizeof(double)) == 0;
+  if (hit) return GPS_OK;
+  h->fact_level = 0;
+  int rc = upload_par(h, par, len);
+  if (rc) return rc;
+  CK(h, cudaEventRecord(h->ev0, h->st));
+  rc = run_factor(h);
+  if (rc) return rc;
+  CK(h, cudaEventRecord(h->ev1, h->st));
+  return GPS_OK;
+}
+
+int fetch_info(H* h) {
+  CK(h, cudaMemcpyAsync(h->pin_info, h->info, sizeof(int) * h->batch, cudaMemcpyDeviceToHost, h->st));
+  CK(h, cudaStreamSynchronize(h->st));
+  float ms = 0.f;
+  if (cudaEventElapsedTime(&ms, h->ev0, h->ev1) == cudaSuccess) h->last_ms = ms;
+  else (void)cudaGetLastError();
+  for (int b = 0; b < h->batch; b++)
+    if (h->pin_info[b] != 0) {
+      h->last_pivot = h->pin_info[b];
+      h->fact_level = 0;
+      char buf[256];
+      snprintf(buf, sizeof buf, "covariance matrix is not positive definite (fit %d, pivot %d)", b, h->pin_info[b]);
+      return fail(h, GPS_ERR_NOT_PD, buf);
+    }
+  h->last_pivot = 0;
+  return GPS_OK;
+}
+
+void remember_fact(H* h, const double* par, int len, int level) {
+  size_t tot = (size_t)len * h->batch;
+  h->fact_par.assign(par, par + tot);
+  h->fact_tv = h->targets_version;
+  h->fact_ncv = h->nc_version;
+  h->fact_level = level;
+}
+
+int check_handle(H* h) {
+  if (!h) return fail(nullptr, GPS_ERR_ARG, "handle is NULL");
+  cudaError_t e = cudaSetDevice(h->device);
+  if (e != cudaSuccess) return fail(h, GPS_ERR_CUDA, std::string("cudaSetDevice: ") + cudaGetErrorString(e));
+  g_alloc_stream = h->st;
+  return GPS_OK;
+}
+
+int copy_out_matrix(H* h, double* dst, const double* src, int rows, int cols, int ld) {
+  CK(h, cudaMemcpy2DAsync(dst, (size_t)rows * sizeof(double), src, (size_t)ld * sizeof(double),
+                          (size_t)rows * sizeof(double), cols, cudaMemcpyDeviceToHost, h->st));
+  return GPS_OK;
+}
+
+}  // namespace
+
+// =========================================================================================
+// C ABI
+// =========================================================================================
+extern "C" {
+
+const char* gps_version(void) { return "gpsurv-b200 0.1.0 (sm_100a, FP64 DMMA)"; }
+
+const char* gps_last_error(gps_handle h) { return h ? h->err.c_str() : g_tls_error.c_str(); }
+
+int gps_last_pivot(gps_handle h) { return h ? h->last_pivot : 0; }
+
+int gps_create_batch(int device, int batch, gps_handle* out) {
+  if (!out || batch < 1) return fail(nullptr, GPS_ERR_ARG, "gps_create: bad arguments");
+  *out = nullptr;
+  int count = 0;
+  cudaError_t e = cudaGetDeviceCount(&count);
+  if (e != cudaSuccess || count == 0) {
+    (void)cudaGetLastError();
+    return fail(nullptr, GPS_ERR_CUDA, "no CUDA device available (libgpsurv has no CPU fallback)");
+  }
+  if (device < 0 || device >= count) return fail(nullptr, GPS_ERR_ARG, "gps_create: device index out of range");
+  cudaDeviceProp prop;
+  e = cudaGetDeviceProperties(&prop, device);
+  if (e != cudaSuccess) return fail(nullptr, GPS_ERR_CUDA, cudaGetErrorString(e));
+  if (prop.major != 10) {
+    char b[256];
+    snprintf(b, sizeof b, "device %d is sm_%d%d; libgpsurv is built for sm_100a only", device, prop.major, prop.minor);
+    return fail(nullptr, GPS_ERR_CUDA, b);
+  }
+  H* h = new H();
+  h->device = device;
+  h->batch = batch;
+  if (cudaSetDevice(device) != cudaSuccess || cudaStreamCreateWithFlags(&h->st, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaEventCreate(&h->ev0) != cudaSuccess || cudaEventCreate(&h->ev1) != cudaSuccess ||
+      cudaMallocHost((void**)&h->pin_info, sizeof(int) * batch) != cudaSuccess) {
+    std::string m = cudaGetErrorString(cudaGetLastError());
+    delete h;
+    return fail(nullptr, GPS_ERR_CUDA, "gps_create: " + m);
+  }
+  e = cudaFuncSetAttribute(potf2_inv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LEAF_SMEM);
+  if (e != cudaSuccess) {
+    delete h;
+    return fail(nullptr, GPS_ERR_CUDA, std::string("gps_create: ") + cudaGetErrorString(e));
+  }
+  *out = h;
+  return GPS_OK;
+}
+
+int gps_create(int device, gps_handle* out) { return gps_create_batch(device, 1, out); }
+
+int gps_destroy(gps_handle h) {
+  if (!h) return GPS_OK;
+  cudaSetDevice(h->device);
+  if (h->st) cudaStreamSynchronize(h->st);
+  drop_graphs(h);
+  free_data(h);
+  dfree(h->adj);
+  if (h->pin) cudaFreeHost(h->pin);
+  if (h->pin_info) cudaFreeHost(h->pin_info);
+  if (h->ev0) cudaEventDestroy(h->ev0);
+  if (h->ev1) cudaEventDestroy(h->ev1);
+  if (h->st) cudaStreamDestroy(h->st);
+  delete h;
+  return GPS_OK;
+}
+
+int gps_set_options(gps_handle h, int cov_form, int mean_form, int noise_corr, int ard_mode) {
+  int rc = check_handle(h);
+  if (rc) return rc;
+  if (cov_form != GPS_COV_SQEXP && cov_form != GPS_COV_ARD)
+    return fail(h, GPS_ERR_UNSUPPORTED, "covFuncForm must be SqExp or ARD (Matern/RF/InformedARD are not built)");
+  if (mean_form != GPS_MEAN_ZERO && mean_form != GPS_MEAN_LINEAR) return fail(h, GPS_ERR_ARG, "bad meanFuncForm");
+  if (noise_corr < 0 || noise_corr > 2) return fail(h, GPS_ERR_ARG, "bad noiseCorr");
+  if (ard_mode != GPS_ARD_INTENDED && ard_mode != GPS_ARD_AS_WRITTEN) return fail(h, GPS_ERR_ARG, "bad ard_mode");
+  ModelOpts o{cov_form, mean_form, noise_corr, ard_mode};
+  if (memcmp(&o, &h->o, sizeof o) != 0) {
+    h->o = o;
+    if (h->have_data) {
+      CK(h, cudaStreamSynchronize(h->st));
+      h->p = (cov_form == GPS_COV_ARD) ? h->d : 1;
+      int nrhs = (mean_form == GPS_MEAN_LINEAR) ? 2 : 1;
+      h->nrhs = nrhs;
+      h->naug = h->ne + nrhs;
+    }
+    drop_graphs(h);
+    h->fact_level = 0;
+    h->model_valid = false;
+  }
+  return GPS_OK;
+}
+
+int gps_set_data(gps_handle h, const double* X, int n, int d, const double* y, const double* events) {
+  int rc = check_handle(h);
+  if (rc) return rc;
+  if (!X || !y || n < 1 || d < 1) return fail(h, GPS_ERR_ARG, "gps_set_data: bad arguments");
+  CK(h, cudaStreamSynchronize(h->st));
+  const int B = h->batch;
+  const bool same_shape = h->have_data && h->n == n && h->d == d;   // keep allocations and graphs
+  if (!same_shape) {
+  drop_graphs(h);
+  free_data(h);
+  h->n = n; h->d = d;
+  h->p = (h->o.cov_form == GPS_COV_ARD) ? d : 1;
+  h->ne = round_up(n, 2);
+  h->nrhs = (h->o.mean_form == GPS_MEAN_LINEAR) ? 2 : 1;
+  h->naug = h->ne + h->nrhs;
+  h->ld = round_up(h->ne + 2, 16);
+  h->ldx = round_up(n, 16);
+  h->ldmu = round_up(d + 1, 16);
+  h->ldc = round_up(n, 16);
+  h->strideM = (long long)h->ld * round_up(h->ne, 2);
+  h->strideX = (long long)h->ldx * (d + 1);
+  {
+    int want = ceil_div(24000, n * B);
+    h->rn_ksplit = want < 1 ? 1 : (want > d ? d : (want > 64 ? 64 : want));
+  }
+  h->gram_ksplit = pick_gram_ksplit(h, n, n, d, true);
+  size_t vecB = (size_t)h->ld * B;
+  CK(h, dalloc(&h->Xaug, (size_t)h->strideX * B));
+  CK(h, dalloc(&h->Z, (size_t)h->strideX * B));
+  CK(h, dalloc(&h->mu, (size_t)h->ldmu * B));
+  CK(h, dalloc(&h->y, vecB));
+  CK(h, dalloc(&h->events, vecB));
+  CK(h, dalloc(&h->lsc, (size_t)h->ldc * B));
+  CK(h, dalloc(&h->cens_rank, vecB));
+  CK(h, dalloc(&h->d_ncens, (size_t)B));
+  size_t parmax = (size_t)(2 + d + d + 1 + 1);
+  CK(h, dalloc(&h->par, parmax * B));
+  CK(h, dalloc(&h->d_grad, parmax * B));
+  CK(h, dalloc(&h->hyp, (size_t)4 * B));
+  CK(h, dalloc(&h->ell, (size_t)h->ldmu * B));
+  CK(h, dalloc(&h->meanw, (size_t)h->ldmu * B));
+  CK(h, dalloc(&h->noise_diag, vecB));
+  CK(h, dalloc(&h->rnpart, vecB * h->rn_ksplit));
+  CK(h, dalloc(&h->rnorm, vecB));
+  CK(h, dalloc(&h->meanv, vecB));
+  CK(h, dalloc(&h->zvec, vecB * 2));
+  CK(h, dalloc(&h->alpha, vecB * 2));
+  CK(h, dalloc(&h->wdiag, vecB));
+  CK(h, dalloc(&h->rs, vecB));
+  CK(h, dalloc(&h->colpart, (size_t)h->ldmu * ceil_div(n, 64) * B));
+  CK(h, dalloc(&h->qtu, (size_t)h->ldmu * 3 * B));
+  CK(h, dalloc(&h->d_nlml, (size_t)B));
+  CK(h, dalloc(&h->d_logdet, (size_t)B));
+  CK(h, dalloc(&h->info, (size_t)B));
+  size_t mat = (size_t)h->strideM * B;
+  CK(h, dalloc(&h->K, mat));
+  CK(h, dalloc(&h->Ky, mat));
+  CK(h, dalloc(&h->L, mat));
+  CK(h, dalloc(&h->Linv, mat));
+  CK(h, dalloc(&h->Kinv, mat));
+  CK(h, dalloc(&h->mL, mat));
+  CK(h, dalloc(&h->mLinv, mat));
+  if (h->gram_ksplit > 1) {
+    h->gsplit_elems = mat * h->gram_ksplit;
+    CK(h, dalloc(&h->gsplit, h->gsplit_elems, false));
+  }
+  CK(h, dalloc(&h->m_alpha, vecB * 2));
+  CK(h, dalloc(&h->m_hyp, (size_t)4 * B));
+  CK(h, dalloc(&h->m_ell, (size_t)h->ldmu * B));
+  CK(h, dalloc(&h->m_meanw, (size_t)h->ldmu * B));
+  }
+  h->model_valid = false;
+  h->fact_level = 0;
+  // upload (host arrays are [batch][n x d] column-major, [batch][n])
+  for (int b = 0; b < B; b++) {
+    CK(h, cudaMemcpy2DAsync(h->Xaug + (size_t)b * h->strideX, (size_t)h->ldx * sizeof(double), X + (size_t)b * n * d,
+                            (size_t)n * sizeof(double), (size_t)n * sizeof(double), d, cudaMemcpyHostToDevice, h->st));
+    CK(h, cudaMemcpyAsync(h->y + (size_t)b * h->ld, y + (size_t)b * n, (size_t)n * sizeof(double), cudaMemcpyHostToDevice,
+                          h->st));
+    if (events) {
+      CK(h, cudaMemcpyAsync(h->events + (size_t)b * h->ld, events + (size_t)b * n, (size_t)n * sizeof(double),
+                            cudaMemcpyHostToDevice, h->st));
+    } else {
+      std::vector<double> ones(n, 1.0);
+      CK(h, cudaMemcpyAsync(h->events + (size_t)b * h->ld, ones.data(), (size_t)n * sizeof(double), cudaMemcpyHostToDevice,
+                            h->st));
+      CK(h, cudaStreamSynchronize(h->st));   // `ones` goes out of scope
+    }
+  }
+  colmean_kernel<<<dim3(ceil_div(d, 8), B), 256, 0, h->st>>>(h->Xaug, n, d, h->ldx, h->strideX, h->mu, h->ldmu);
+  center_kernel<<<dim3(ceil_div(n, 256), d + 1, B), 256, 0, h->st>>>(h->Xaug, n, d, h->ldx, h->strideX, h->mu, h->ldmu);
+  cens_rank_kernel<<<ceil_div(B, 64), 64, 0, h->st>>>(h->events, n, h->ld, h->cens_rank, h->d_ncens, B);
+  h->launches += 3;
+  CK(h, cudaGetLastError());
+  h->ncens.assign(B, 0);
+  CK(h, cudaMemcpyAsync(h->ncens.data(), h->d_ncens, sizeof(int) * B, cudaMemcpyDeviceToHost, h->st));
+  CK(h, cudaStreamSynchronize(h->st));
+  h->ncens_max = 0;
+  for (int b = 0; b < B; b++) h->ncens_max = h->ncens[b] > h->ncens_max ? h->ncens[b] : h->ncens_max;
+  h->have_data = true;
+  h->targets_version++;
+  h->nc_version++;
+  return GPS_OK;
+}
+
+int gps_set_targets(gps_handle h, const double* y) {
+  int rc = check_handle(h);
+  if (rc) return rc;
+  if (!h->have_data) return fail(h, GPS_ERR_STATE, "gps_set_data has not been called");
+  if (!y) return fail(h, GPS_ERR_ARG, "y is NULL");
+  rc = ensure_pin(h, (size_t)h->n * h->batch + 4096);
+  if (rc) return rc;
+  CK(h, cudaStreamSynchronize(h->st));
+  memcpy(h->pin, y, (size_t)h->n * h->batch * sizeof(double));
+  CK(h, cudaMemcpy2DAsync(h->y, (size_t)h->ld * sizeof(double), h->pin, (size_t)h->n * sizeof(double),
+                          (size_t)h->n * sizeof(double), h->batch, cudaMemcpyHostToDevice, h->st));
+  CK(h, cudaStreamSynchronize(h->st));
+  h->targets_version++;
+  return GPS_OK;
+}
+
+int gps_set_noise_corr(gps_handle h, const double* log_sc2, int len) {
+  int rc = check_handle(h);
+  if (rc) return rc;
+  if (!h->have_data) return fail(h, GPS_ERR_STATE, "gps_set_data has not been called");
+  if (!log_sc2 || len < 0) return fail(h, GPS_ERR_ARG, "gps_set_noise_corr: bad arguments");
+  for (int b = 0; b < h->batch; b++)
+    if (len != h->ncens[b]) {
+      char buf[256];
+      snprintf(buf, sizeof buf, "noise correction has length %d but fit %d has %d censored rows", len, b, h->ncens[b]);
+      return fail(h, GPS_ERR_ARG, buf);
+    }
+  for (size_t i = 0; i < (size_t)len * h->batch; i++)
+    if (isnan(log_sc2[i])) return fail(h, GPS_ERR_ARG, "noise correction contains NaN");
+  if (len > 0) {
+    rc = ensure_pin(h, (size_t)len * h->batch + 4096);
+    if (rc) return rc;
+    CK(h, cudaStreamSynchronize(h->st));
+    memcpy(h->pin, log_sc2, (size_t)len * h->batch * sizeof(double));
+    CK(h, cudaMemcpy2DAsync(h->lsc, (size_t)h->ldc * sizeof(double), h->pin, (size_t)len * sizeof(double),
+                            (size_t)len * sizeof(double), h->batch, cudaMemcpyHostToDevice, h->st));
+    CK(h, cudaStreamSynchronize(h->st));
+  }
+  h->nc_version++;
+  return GPS_OK;
+}
+
+int gps_nlml(gps_handle h, const double* par, int len, double* nlml_out) {
+  int rc = check_handle(h);
+  if (rc) return rc;
+  if (!nlml_out) return fail(h, GPS_ERR_ARG, "nlml_out is NULL");
+  rc = do_factor(h, par, len, true);
+  if (rc) return rc;
+  CK(h, cudaMemcpyAsync(h->pin, h->d_nlml, sizeof(double) * h->batch, cudaMemcpyDeviceToHost, h->st));
+  rc = fetch_info(h);
+  if (rc) return rc;
+  memcpy(nlml_out, h->pin, sizeof(double) * h->batch);
+  remember_fact(h, par, len, 1);
+  return GPS_OK;
+}
+
+int gps_nlml_grad(gps_handle h, const double* par, int len, double* nlml_out, double* grad_out) {
+  int rc = check_handle(h);
+  if (rc) return rc;
+  if (!grad_out) return fail(h, GPS_ERR_ARG, "grad_out is NULL");
+  if (h->have_data && h->o.cov_form == GPS_COV_ARD && h->o.ard_mode == GPS_ARD_AS_WRITTEN && h->d > 1)
+    return fail(h, GPS_ERR_UNSUPPORTED,
+                "the analytic ARD gradient is defined for ard_mode = INTENDED only (the reference's as-written ARD "
+                "gradient, OptimisationGradientLog.R:58-69, is not the derivative of its likelihood)");
+  rc = do_factor(h, par, len, false);
+  if (rc) return rc;
+  bool had_factor = (h->fact_level >= 1);
+  if (had_factor) CK(h, cudaEventRecord(h->ev0, h->st));
+  if (h->fact_level < 2) {
+    rc = run_inverse(h);
+    if (rc) return rc;
+  }
+  rc = run_grad(h);
+  if (rc) return rc;
+  CK(h, cudaEventRecord(h->ev1, h->st));
+  size_t tot = (size_t)len * h->batch;
+  rc = ensure_pin(h, tot + h->batch + 4096);
+  if (rc) return rc;
+  CK(h, cudaMemcpyAsync(h->pin, h->d_nlml, sizeof(double) * h->batch, cudaMemcpyDeviceToHost, h->st));
+  CK(h, cudaMemcpyAsync(h->pin + h->batch, h->d_grad, sizeof(double) * tot, cudaMemcpyDeviceToHost, h->st));
+  rc = fetch_info(h);
+  if (rc) return rc;
+  if (nlml_out) memcpy(nlml_out, h->pin, sizeof(double) * h->batch);
+  memcpy(grad_out, h->pin + h->batch, sizeof(double) * tot);
+  remember_fact(h, par, len, 2);
+  return GPS_OK;
+}
+
+int gps_regress_finalize(gps_handle h, const double* par, int len, double* K_out, double* L_out, double* alpha_out,
+                         double* mean_out, double* logmarlik_out) {
+  int rc = check_handle(h);
+  if (rc) return rc;
+  rc = do_factor(h, par, len, false);
+  if (rc) return rc;
+  if (h->fact_level < 2) {
+    rc = run_inverse(h);
+    if (rc) return rc;
+  }
+  CK(h, cudaEventRecord(h->ev1, h->st));
+  const int B = h->batch, n = h->n;
+  rc = ensure_pin(h, (size_t)B * (1 + 2 * (size_t)n) + 4096);
+  if (rc) return rc;
+  CK(h, cudaMemcpyAsync(h->pin, h->d_nlml, sizeof(double) * B, cudaMemcpyDeviceToHost, h->st));
+  CK(h, cudaMemcpy2DAsync(h->pin + B, (size_t)n * sizeof(double), h->alpha, (size_t)2 * h->ld * sizeof(double),
+                          (size_t)n * sizeof(double), B, cudaMemcpyDeviceToHost, h->st));
+  CK(h, cudaMemcpy2DAsync(h->pin + B + (size_t)B * n, (size_t)n * sizeof(double), h->meanv, (size_t)h->ld * sizeof(double),
+                          (size_t)n * sizeof(double), B, cudaMemcpyDeviceToHost, h->st));
+  rc = fetch_info(h);
+  if (rc) return rc;
+  if (logmarlik_out)
+    for (int b = 0; b < B; b++) logmarlik_out[b] = -h->pin[b];   // GPRegression.R:71 (positive sign)
+  if (alpha_out) memcpy(alpha_out, h->pin + B, sizeof(double) * B * n);
+  if (mean_out) memcpy(mean_out, h->pin + B + (size_t)B * n, sizeof(double) * B * n);
+  if (K_out) {
+    symmetrize_kernel<<<dim3(ceil_div(n, 32), ceil_div(n, 32), B), dim3(32, 8), 0, h->st>>>(h->K, n, h->ld, h->strideM);
+    h->launches++;
+    for (int b = 0; b < B; b++) {
+      rc = copy_out_matrix(h, K_out + (size_t)b * n * n, h->K + (size_t)b * h->strideM, n, n, h->ld);
+      if (rc) return rc;
+    }
+  }
+  if (L_out)
+    for (int b = 0; b < B; b++) {
+      rc = copy_out_matrix(h, L_out + (size_t)b * n * n, h->L + (size_t)b * h->strideM, n, n, h->ld);
+      if (rc) return rc;
+    }
+  // keep the model resident: copy the factor, its inverse and the small state (graphs stay valid)
+  CK(h, cudaMemcpyAsync(h->m_alpha, h->alpha, sizeof(double) * 2 * h->ld * B, cudaMemcpyDeviceToDevice, h->st));
+  CK(h, cudaMemcpyAsync(h->m_hyp, h->hyp, sizeof(double) * 4 * B, cudaMemcpyDeviceToDevice, h->st));
+  CK(h, cudaMemcpyAsync(h->m_ell, h->ell, sizeof(double) * h->ldmu * B, cudaMemcpyDeviceToDevice, h->st));
+  CK(h, cudaMemcpyAsync(h->m_meanw, h->meanw, sizeof(double) * h->ldmu * B, cudaMemcpyDeviceToDevice, h->st));
+  CK(h, cudaMemcpyAsync(h->mL, h->L, sizeof(double) * (size_t)h->strideM * B, cudaMemcpyDeviceToDevice, h->st));
+  CK(h, cudaMemcpyAsync(h->mLinv, h->Linv, sizeof(double) * (size_t)h->strideM * B, cudaMemcpyDeviceToDevice, h->st));
+  CK(h, cudaStreamSynchronize(h->st));
+  remember_fact(h, par, len, 2);
+  h->model_valid = true;
+  h->model_par.assign(par, par + (size_t)len * B);
+  h->model_tv = h->targets_version;
+  h->model_ncv = h->nc_version;
+  return GPS_OK;
+}
+
+int gps_predict(gps_handle h, const double* par, int len, int reuse_model, const double* Xstar, int m, double* mu_out,
+                double* varf_out, double* vard_out) {
+  int rc = check_handle(h);
+  if (rc) return rc;
+  if (!h->have_data) return fail(h, GPS_ERR_STATE, "gps_set_data has not been called");
+  if (!Xstar || m < 1 || !mu_out) return fail(h, GPS_ERR_ARG, "gps_predict: bad arguments");
+  const int B = h->batch, n = h->n, d = h->d;
+  bool fresh = h->model_valid && par && par_close(h->model_par, par, (size_t)len * B) &&
+               h->model_tv == h->targets_version && h->model_ncv == h->nc_version;
+  if (reuse_model) {
+    if (!h->model_valid) return fail(h, GPS_ERR_STATE, "gps_predict(reuse_model): no resident model (call gps_regress_finalize)");
+  } else if (!fresh) {
+    rc = gps_regress_finalize(h, par, len, nullptr, nullptr, nullptr, nullptr, nullptr);   // GPPredict.R:36-46
+    if (rc) return rc;
+  }
+  // scratch
+  if (m > h->m_cap) {
+    CK(h, cudaStreamSynchronize(h->st));
+    dfree(h->Xs); dfree(h->Zs); dfree(h->snorm); dfree(h->snpart); dfree(h->Ks); dfree(h->V); dfree(h->mstar);
+    dfree(h->pout);
+    h->lds = round_up(m, 16);
+    CK(h, dalloc(&h->Xs, (size_t)h->lds * d * B));
+    CK(h, dalloc(&h->Zs, (size_t)h->lds * d * B));
+    CK(h, dalloc(&h->snorm, (size_t)h->lds * B));
+    CK(h, dalloc(&h->snpart, (size_t)h->lds * B * 64));
+    CK(h, dalloc(&h->Ks, (size_t)h->ld * m * B, false));
+    CK(h, dalloc(&h->V, (size_t)h->ld * m * B, false));
+    CK(h, dalloc(&h->mstar, (size_t)h->lds * B));
+    CK(h, dalloc(&h->pout, (size_t)h->lds * 3 * B));
+    h->m_cap = m;
+  }
+  const int lds = h->lds;
+  const long long sXs = (long long)lds * d, sKs = (long long)h->ld * m;
+  for (int b = 0; b < B; b++)
+    CK(h, cudaMemcpy2DAsync(h->Xs + (size_t)b * sXs, (size_t)lds * sizeof(double), Xstar + (size_t)b * m * d,
+                            (size_t)m * sizeof(double), (size_t)m * sizeof(double), d, cudaMemcpyHostToDevice, h->st));
+  CK(h, cudaEventRecord(h->ev0, h->st));
+  h->cu_err = cudaSuccess;
+  h->seq_launches = 0;
+  center_test_kernel<<<dim3(ceil_div(m, 256), d, B), 256, 0, h->st>>>(h->Xs, m, d, lds, sXs, h->mu, h->ldmu);
+  LAUNCHED(h);
+  // training rows re-scaled with the *model's* length-scales
+  {
+    dim3 grid(ceil_div(n, 128), h->rn_ksplit, B);
+    prescale_kernel<<<grid, 128, 0, h->st>>>(h->Xaug, n, d, h->ldx, h->strideX, h->mu, h->ldmu, h->m_ell, h->ldmu, h->p,
+                                              h->o.ard_mode == 1 && h->p > 1, n, h->Z, h->ldx, h->strideX, h->rnpart,
+                                              h->ld, h->rn_ksplit, 1, 1);
+    LAUNCHED(h);
+    rownorm_finish_kernel<<<dim3(ceil_div(n, 256), B), 256, 0, h->st>>>(h->rnpart, n, h->ld, h->rn_ksplit, h->rnorm);
+    LAUNCHED(h);
+    int ks = ceil_div(24000, m * B);
+    ks = ks < 1 ? 1 : (ks > d ? d : (ks > 64 ? 64 : ks));
+    dim3 grid2(ceil_div(m, 128), ks, B);
+    prescale_kernel<<<grid2, 128, 0, h->st>>>(h->Xs, m, d, lds, sXs, h->mu, h->ldmu, h->m_ell, h->ldmu, h->p,
+                                               h->o.ard_mode == 1 && h->p > 1, m, h->Zs, lds, sXs, h->snpart, lds, ks, 1, 1);
+    LAUNCHED(h);
+    rownorm_finish_kernel<<<dim3(ceil_div(m, 256), B), 256, 0, h->st>>>(h->snpart, m, lds, ks, h->snorm);
+    LAUNCHED(h);
+  }
+  mean_kernel<<<dim3(ceil_div(m, 128), B), 128, 0, h->st>>>(h->Xs, m, d, lds, sXs, h->m_meanw, h->ldmu,
+                                                             h->o.mean_form == 1, h->mstar, lds);
+  LAUNCHED(h);
+  {  // K* = cov(X, X*)  (n x m).  snorm uses leading dimension lds, so the epilogue gets its own ldn
+    GemmParams p = gp(h->Z, h->ldx, h->strideX, h->Zs, lds, sXs, n, m, d);
+    EpiCov e;
+    e.normA = h->rnorm; e.normB = h->snorm; e.hyp = h->m_hyp; e.noise_diag = nullptr; e.Kout = h->Ks; e.Kyout = nullptr;
+    e.ldk = h->ld; e.ldn = h->ld; e.strideK = sKs; e.sym = 0;
+    e.ldnB = lds;
+    gemm<false, false>(h, p, e);
+  }
+  {  // V = Linv * K*  (Linv lower: k <= m)
+    GemmParams p = gp(h->mLinv, h->ld, h->strideM, h->Ks, h->ld, sKs, n, m, n);
+    p.khi_m = 1;
+    gemm<false, true>(h, p, plain(h->V, h->ld, sKs, 1.0, 0.0));
+  }
+  predict_finish_kernel<<<dim3(ceil_div(m, 8), B), 256, 0, h->st>>>(h->Ks, h->V, n, m, h->ld, sKs, h->m_alpha, h->ld,
+                                                                    h->mstar, lds, h->m_hyp, h->pout, h->pout + (size_t)lds * B,
+                                                                    h->pout + (size_t)2 * lds * B);
+  LAUNCHED(h);
+  h->launches += h->seq_launches;
+  if (h->cu_err != cudaSuccess) return fail(h, GPS_ERR_CUDA, h->err);
+  CK(h, cudaEventRecord(h->ev1, h->st));
+  rc = ensure_pin(h, (size_t)3 * m * B + 4096);
+  if (rc) return rc;
+  for (int q = 0; q < 3; q++)
+    CK(h, cudaMemcpy2DAsync(h->pin + (size_t)q * m * B, (size_t)m * sizeof(double), h->pout + (size_t)q * lds * B,
+                            (size_t)lds * sizeof(double), (size_t)m * sizeof(double), B, cudaMemcpyDeviceToHost, h->st));
+  CK(h, cudaStreamSynchronize(h->st));
+  float ms = 0.f;
+  if (cudaEventElapsedTime(&ms, h->ev0, h->ev1) == cudaSuccess) h->last_ms = ms;
+  memcpy(mu_out, h->pin, sizeof(double) * m * B);
+  if (varf_out) memcpy(varf_out, h->pin + (size_t)m * B, sizeof(double) * m * B);
+  if (vard_out) memcpy(vard_out, h->pin + (size_t)2 * m * B, sizeof(double) * m * B);
+  return GPS_OK;
+}
+
+int gps_adjust(gps_handle h, const double* a, const double* mu, const double* s, int c, double* mean_out,
+               double* var_out) {
+  int rc = check_handle(h);
+  if (rc) return rc;
+  if (c < 0 || (c > 0 && (!a || !mu || !s || !mean_out || !var_out))) return fail(h, GPS_ERR_ARG, "gps_adjust: bad arguments");
+  if (c == 0) return GPS_OK;
+  if (c > h->adj_cap) {
+    CK(h, cudaStreamSynchronize(h->st));
+    dfree(h->adj);
+    CK(h, dalloc(&h->adj, (size_t)5 * c));
+    h->adj_cap = c;
+  }
+  rc = ensure_pin(h, (size_t)5 * c + 4096);
+  if (rc) return rc;
+  memcpy(h->pin, a, sizeof(double) * c);
+  memcpy(h->pin + c, mu, sizeof(double) * c);
+  memcpy(h->pin + 2 * (size_t)c, s, sizeof(double) * c);
+  const int cap = h->adj_cap;
+  for (int q = 0; q < 3; q++)
+    CK(h, cudaMemcpyAsync(h->adj + (size_t)q * cap, h->pin + (size_t)q * c, sizeof(double) * c, cudaMemcpyHostToDevice, h->st));
+  adjust_kernel<<<ceil_div(c, 256), 256, 0, h->st>>>(h->adj, h->adj + cap, h->adj + 2 * (size_t)cap, c,
+                                                      h->adj + 3 * (size_t)cap, h->adj + 4 * (size_t)cap);
+  h->launches++;
+  CK(h, cudaGetLastError());
+  CK(h, cudaMemcpyAsync(h->pin + 3 * (size_t)c, h->adj + 3 * (size_t)cap, sizeof(double) * c, cudaMemcpyDeviceToHost, h->st));
+  CK(h, cudaMemcpyAsync(h->pin + 4 * (size_t)c, h->adj + 4 * (size_t)cap, sizeof(double) * c, cudaMemcpyDeviceToHost, h->st));
+  CK(h, cudaStreamSynchronize(h->st));
+  memcpy(mean_out, h->pin + 3 * (size_t)c, sizeof(double) * c);
+  memcpy(var_out, h->pin + 4 * (size_t)c, sizeof(double) * c);
+  return GPS_OK;
+}
+
+int gps_cov(gps_handle h, const double* X1, int n1, const double* X2, int n2, int d, double sf2, const double* ell,
+            int p, int cov_form, int ard_mode, double* K_out) {
+  int rc = check_handle(h);
+  if (rc) return rc;
+  if (!X1 || n1 < 1 || d < 1 || !ell || !K_out) return fail(h, GPS_ERR_ARG, "gps_cov: bad arguments");
+  if (cov_form != GPS_COV_SQEXP && cov_form != GPS_COV_ARD)
+    return fail(h, GPS_ERR_UNSUPPORTED, "gps_cov: covFuncForm must be SqExp or ARD");
+  if (p != 1 && p != d && ard_mode == GPS_ARD_INTENDED) return fail(h, GPS_ERR_ARG, "gps_cov: need 1 or d length-scales");
+  const bool sym = (X2 == nullptr);
+  if (sym) n2 = n1;
+  if (n2 < 1) return fail(h, GPS_ERR_ARG, "gps_cov: bad n2");
+  // temporary single-problem buffers (stateless utility path)
+  const int ld1 = round_up(n1, 16), ld2 = round_up(n2, 16), ldk = round_up(n1 + 2, 16), lde = round_up(d > p ? d : p, 16);
+  const int ldn = ldk > ld2 ? ldk : ld2;
+  double *dX1 = nullptr, *dX2 = nullptr, *dZ1 = nullptr, *dZ2 = nullptr, *dmu = nullptr, *dell = nullptr, *dn1 = nullptr,
+         *dn2 = nullptr, *dpart = nullptr, *dK = nullptr, *dhyp = nullptr, *dsplit = nullptr;
+  int ks1 = ceil_div(24000, n1), ks2 = ceil_div(24000, n2);
+  ks1 = ks1 < 1 ? 1 : (ks1 > d ? d : (ks1 > 64 ? 64 : ks1));
+  ks2 = ks2 < 1 ? 1 : (ks2 > d ? d : (ks2 > 64 ? 64 : ks2));
+  int saved_batch = h->batch, saved_ld = h->ld;
+  double* saved_gsplit = h->gsplit;
+  int result = GPS_OK;
+  auto cleanup = [&]() {
+    cudaStreamSynchronize(h->st);
+    cudaFree(dX1); cudaFree(dX2); cudaFree(dZ1); cudaFree(dZ2); cudaFree(dmu); cudaFree(dell); cudaFree(dn1);
+    cudaFree(dn2); cudaFree(dpart); cudaFree(dK); cudaFree(dhyp); cudaFree(dsplit);
+    h->batch = saved_batch; h->ld = saved_ld; h->gsplit = saved_gsplit;
+  };
+#define CKC(call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) { result = fail(h, GPS_ERR_CUDA, std::string("gps_cov: ") + cudaGetErrorString(e__)); cleanup(); return result; } } while (0)
+  CKC(cudaStreamSynchronize(h->st));
+  CKC(dalloc(&dX1, (size_t)ld1 * d));
+  CKC(dalloc(&dZ1, (size_t)ld1 * d));
+  CKC(dalloc(&dmu, (size_t)lde));
+  CKC(dalloc(&dell, (size_t)lde));
+  CKC(dalloc(&dn1, (size_t)ldn));
+  CKC(dalloc(&dpart, (size_t)ldn * 64));
+  CKC(dalloc(&dK, (size_t)ldk * n2, false));
+  CKC(dalloc(&dhyp, (size_t)4));
+  CKC(cudaMemcpy2DAsync(dX1, (size_t)ld1 * sizeof(double), X1, (size_t)n1 * sizeof(double), (size_t)n1 * sizeof(double), d,
+                        cudaMemcpyHostToDevice, h->st));
+  double hyp4[4] = {0.0, sf2, 0.0, 0.0};
+  CKC(cudaMemcpyAsync(dhyp, hyp4, sizeof hyp4, cudaMemcpyHostToDevice, h->st));
+  CKC(cudaMemcpyAsync(dell, ell, sizeof(double) * p, cudaMemcpyHostToDevice, h->st));
+  h->batch = 1;
+  h->ld = ldn;   // EpiCov / cov_finish index the norm vectors with h->ld
+  const int aw = (ard_mode == GPS_ARD_AS_WRITTEN && p > 1) ? 1 : 0;
+  if (!aw) {   // centre with X1's column means (distance-invariant; both operands share mu)
+    colmean_kernel<<<dim3(ceil_div(d, 8), 1), 256, 0, h->st>>>(dX1, n1, d, ld1, 0, dmu, lde);
+    center_test_kernel<<<dim3(ceil_div(n1, 256), d, 1), 256, 0, h->st>>>(dX1, n1, d, ld1, 0, dmu, lde);
+    h->launches += 2;
+  }
+  prescale_kernel<<<dim3(ceil_div(n1, 128), ks1, 1), 128, 0, h->st>>>(dX1, n1, d, ld1, 0, dmu, lde, dell, lde, p, aw, n1,
+                                                                      dZ1, ld1, 0, dpart, ldn, ks1, 0, 0);
+  rownorm_finish_kernel<<<dim3(ceil_div(n1, 256), 1), 256, 0, h->st>>>(dpart, n1, ldn, ks1, dn1);
+  h->launches += 2;
+  const double *Zb = dZ1, *nb = dn1;
+  int ldb = ld1;
+  if (!sym) {
+    CKC(dalloc(&dX2, (size_t)ld2 * d));
+    CKC(dalloc(&dZ2, (size_t)ld2 * d));
+    CKC(dalloc(&dn2, (size_t)ldn));
+    CKC(cudaMemcpy2DAsync(dX2, (size_t)ld2 * sizeof(double), X2, (size_t)n2 * sizeof(double), (size_t)n2 * sizeof(double), d,
+                          cudaMemcpyHostToDevice, h->st));
+    if (!aw) {
+      center_test_kernel<<<dim3(ceil_div(n2, 256), d, 1), 256, 0, h->st>>>(dX2, n2, d, ld2, 0, dmu, lde);
+      h->launches++;
+    }
+    prescale_kernel<<<dim3(ceil_div(n2, 128), ks2, 1), 128, 0, h->st>>>(dX2, n2, d, ld2, 0, dmu, lde, dell, lde, p, aw,
+                                                                        n2, dZ2, ld2, 0, dpart, ldn, ks2, 0, 0);
+    rownorm_finish_kernel<<<dim3(ceil_div(n2, 256), 1), 256, 0, h->st>>>(dpart, n2, ldn, ks2, dn2);
+    h->launches += 2;
+    Zb = dZ2; nb = dn2; ldb = ld2;
+  }
+  int ksplit = pick_gram_ksplit(h, n1, n2, d, sym);
+  if (ksplit > 1) {
+    CKC(dalloc(&dsplit, (size_t)ldk * n2 * ksplit, false));
+    h->gsplit = dsplit;
+  }
+  h->cu_err = cudaSuccess;
+  h->seq_launches = 0;
+  enqueue_cov(h, dZ1, n1, ld1, 0, dn1, Zb, n2, ldb, 0, nb, d, dhyp, nullptr, dK, nullptr, ldk, (long long)ldk * n2, sym,
+              ksplit);
+  if (sym) {
+    symmetrize_kernel<<<dim3(ceil_div(n1, 32), ceil_div(n1, 32), 1), dim3(32, 8), 0, h->st>>>(dK, n1, ldk, 0);
+    h->seq_launches++;
+  }
+  h->launches += h->seq_launches;
+  if (h->cu_err != cudaSuccess) { result = fail(h, GPS_ERR_CUDA, h->err); cleanup(); return result; }
+  CKC(cudaGetLastError());
+  CKC(cudaMemcpy2DAsync(K_out, (size_t)n1 * sizeof(double), dK, (size_t)ldk * sizeof(double), (size_t)n1 * sizeof(double),
+                        n2, cudaMemcpyDeviceToHost, h->st));
+  CKC(cudaStreamSynchronize(h->st));
+#undef CKC
+  cleanup();
+  return GPS_OK;
+}
+
+long long gps_launch_count(gps_handle h) { return h ? h->launches : 0; }
+double gps_last_device_ms(gps_handle h) { return h ? h->last_ms : 0.0; }
+
+int gps_set_graphs(gps_handle h, int enable) {
+  int rc = check_handle(h);
+  if (rc) return rc;
+  h->graphs_enabled = enable != 0;
+  if (!enable) drop_graphs(h);
+  return GPS_OK;
+}
+
+int gps_time_eval(gps_handle h, int kind, int reps, double* ms_out) {
+  int rc = check_handle(h);
+  if (rc) return rc;
+  if (!h->have_data || h->par_cap == 0) return fail(h, GPS_ERR_STATE, "gps_time_eval: evaluate once first");
+  if (reps < 1 || !ms_out) return fail(h, GPS_ERR_ARG, "gps_time_eval: bad arguments");
+  CK(h, cudaStreamSynchronize(h->st));
+  CK(h, cudaEventRecord(h->ev0, h->st));
+  for (int r = 0; r < reps; r++) {
+    rc = run_factor(h);
+    if (rc) return rc;
+    if (kind == 1) {
+      rc = run_inverse(h);
+      if (rc) return rc;
+      rc = run_grad(h);
+      if (rc) return rc;
+    }
+  }
+  CK(h, cudaEventRecord(h->ev1, h->st));
+  CK(h, cudaStreamSynchronize(h->st));
+  float ms = 0.f;
+  CK(h, cudaEventElapsedTime(&ms, h->ev0, h->ev1));
+  *ms_out = (double)ms / reps;
+  h->fact_level = 0;
+  return GPS_OK;
+}
+
+int gps_time_stages(gps_handle h, double* ms_out) {
+  int rc = check_handle(h);
+  if (rc) return rc;
+  if (!h->have_data || h->par_cap == 0) return fail(h, GPS_ERR_STATE, "gps_time_stages: evaluate once first");
+  if (!ms_out) return fail(h, GPS_ERR_ARG, "gps_time_stages: bad arguments");
+  cudaEvent_t ev[8];
+  for (int i = 0; i < 8; i++) CK(h, cudaEventCreate(&ev[i]));
+  const int n = h->n;
+  h->cu_err = cudaSuccess;
+  h->seq_launches = 0;
+  CK(h, cudaStreamSynchronize(h->st));
+  CK(h, cudaEventRecord(ev[0], h->st));
+  CKV(h, cudaMemsetAsync(h->info, 0, sizeof(int) * h->batch, h->st));
+  hyp_prep_kernel<<<h->batch, 256, 0, h->st>>>(h->par, h->par_cap, h->o, n, h->d, h->p, h->events, h->cens_rank, h->lsc,
+                                                h->ldc, h->ld, h->mu, h->ldmu, h->hyp, h->ell, h->ldmu, h->meanw,
+                                                h->noise_diag);
+  enqueue_prescale_train(h, h->ell, 1);
+  enqueue_cov(h, h->Z, n, h->ldx, h->strideX, h->rnorm, h->Z, n, h->ldx, h->strideX, h->rnorm, h->d, h->hyp,
+              h->noise_diag, h->K, h->Ky, h->ld, h->strideM, true, h->gram_ksplit);
+  fill_aug_kernel<<<dim3(ceil_div(h->ne, 128), h->batch), 128, 0, h->st>>>(
+      h->Xaug, n, h->ne, h->d, h->ldx, h->strideX, h->meanw, h->ldmu, h->o.mean_form == 1, h->y, h->ld, h->meanv, h->Ky,
+      h->ld, h->strideM, h->nrhs);
+  CK(h, cudaEventRecord(ev[1], h->st));
+  potrf_range(h, 0, ceil_div(h->ne, NB));
+  nlml_finish_kernel<<<h->batch, 256, 0, h->st>>>(h->L, n, h->ne, h->ld, h->strideM, h->nrhs, h->zvec, h->ld, h->d_nlml,
+                                                   h->d_logdet);
+  CK(h, cudaEventRecord(ev[2], h->st));
+  enqueue_inverse(h);
+  CK(h, cudaEventRecord(ev[3], h->st));
+  {
+    GemmParams p = gp(h->Linv, h->ld, h->strideM, h->Linv, h->ld, h->strideM, h->ne, h->ne, h->ne);
+    p.lower = 1;
+    p.klo_m = 1;
+    gemm<true, true>(h, p, plain(h->Kinv, h->ld, h->strideM, 1.0, 0.0));
+  }
+  CK(h, cudaEventRecord(ev[4], h->st));
+  enqueue_grad(h);   // includes Kinv again: stage 4 = wk + grad GEMM + finish + (Kinv repeated)
+  CK(h, cudaEventRecord(ev[5], h->st));
+  CK(h, cudaStreamSynchronize(h->st));
+  h->launches += h->seq_launches;
+  if (h->cu_err != cudaSuccess) return fail(h, GPS_ERR_CUDA, h->err);
+  float t[6];
+  for (int i = 0; i < 5; i++) CK(h, cudaEventElapsedTime(&t[i], ev[i], ev[i + 1]));
+  ms_out[0] = t[0];           // hyp + prescale + gram + fill
+  ms_out[1] = t[1];           // cholesky (+ forward solve) + nlml assembly
+  ms_out[2] = t[2];           // triangular inverse + alpha
+  ms_out[3] = t[3];           // Kinv
+  ms_out[4] = t[4] - t[3];    // W o K + gradient GEMM + assembly
+  ms_out[5] = 0.0;
+  ms_out[6] = 0.0;
+  ms_out[7] = t[0] + t[1] + t[2] + t[3] + (t[4] - t[3]);
+  for (int i = 0; i < 8; i++) cudaEventDestroy(ev[i]);
+  h->fact_level = 0;
+  return GPS_OK;
+}
+
+namespace {
+__global__ void fill_pattern_kernel(double* p, size_t n, unsigned seed) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  unsigned x = (unsigned)(i * 2654435761u) ^ seed;
+  x ^= x >> 13; x *= 0x5bd1e995u; x ^= x >> 15;
+  p[i] = ((double)(x & 0xffff) / 65536.0) - 0.5;
+}
+}  // namespace
+
+int gps_bench_gemm(gps_handle h, int M, int N, int K, int reps, double* ms_out) {
+  int rc = check_handle(h);
+  if (rc) return rc;
+  if (M < 1 || N < 1 || K < 1 || reps < 1 || !ms_out) return fail(h, GPS_ERR_ARG, "gps_bench_gemm: bad arguments");
+  const int lda = round_up(M, 16), ldb = round_up(N, 16), ldc = lda;
+  double *A = nullptr, *Bm = nullptr, *C = nullptr;
+  CK(h, dalloc(&A, (size_t)lda * K, false));
+  CK(h, dalloc(&Bm, (size_t)ldb * K, false));
+  CK(h, dalloc(&C, (size_t)ldc * N, false));
+  fill_pattern_kernel<<<(unsigned)(((size_t)lda * K + 255) / 256), 256, 0, h->st>>>(A, (size_t)lda * K, 1u);
+  fill_pattern_kernel<<<(unsigned)(((size_t)ldb * K + 255) / 256), 256, 0, h->st>>>(Bm, (size_t)ldb * K, 2u);
+  int saved_batch = h->batch;
+  h->batch = 1;
+  GemmParams p = gp(A, lda, 0, Bm, ldb, 0, M, N, K);
+  h->cu_err = cudaSuccess;
+  for (int w = 0; w < 2; w++) gemm<false, false>(h, p, plain(C, ldc, 0, 1.0, 0.0));
+  cudaEventRecord(h->ev0, h->st);
+  for (int r = 0; r < reps; r++) gemm<false, false>(h, p, plain(C, ldc, 0, 1.0, 0.0));
+  cudaEventRecord(h->ev1, h->st);
+  cudaError_t e = cudaStreamSynchronize(h->st);
+  h->batch = saved_batch;
+  float ms = 0.f;
+  if (e == cudaSuccess) e = cudaEventElapsedTime(&ms, h->ev0, h->ev1);
+  cudaFree(A); cudaFree(Bm); cudaFree(C);
+  if (e != cudaSuccess || h->cu_err != cudaSuccess) return fail(h, GPS_ERR_CUDA, std::string("gps_bench_gemm: ") + cudaGetErrorString(e));
+  h->launches += reps + 4;
+  *ms_out = (double)ms / reps;
+  return GPS_OK;
+}
+
+}  // extern "C"

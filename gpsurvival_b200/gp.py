@@ -1,0 +1,473 @@
+"""Host-side mirror of the reference's R interface for the GP hot path, over libgpsurv.so.
+
+R is not available in the build image, so this module plays the role of the
+drop-in R files in ``r/``: same function names, argument order, option strings, return
+fields and error behaviour as
+
+    CovFunc.R, MeanFunc.R, ForOptimisationLog.R, OptimisationGradientLog.R, GPRegression.R,
+    GPPredict.R, AdjustTrainingSurvivalMeanVariance.R and ApplyGP.R:77-282
+
+with every formula executed by the CUDA library through the C ABI (include/gpsurv.h).
+Nothing here computes covariances, factorisations, solves, gradients or moments on the
+CPU, and nothing imports ``oracle``.  If libgpsurv.so or a B200 is missing, calls raise.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from ._lib import COV, MEAN, NOISE_CORR, ARD_MODE, GpsError, NotPositiveDefinite, check, dptr, f64
+from . import optim as _optim
+
+
+# =========================================================================================
+# Thin object wrapper over the opaque handle
+# =========================================================================================
+class Fit:
+    """One ``gps_handle``: a fit (or a batch of identically shaped fits) resident on one GPU."""
+
+    def __init__(self, device: int = 0, batch: int = 1):
+        self.lib = _lib.load()
+        self.h = C.c_void_p()
+        self.batch = batch
+        check(self.lib.gps_create_batch(device, batch, C.byref(self.h)))
+        self.n = self.d = 0
+        self.opts = ("SqExp", "Zero", False, "intended")
+
+    def close(self):
+        if getattr(self, "h", None) is not None and self.h:
+            self.lib.gps_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _ck(self, rc):
+        check(rc, self.h)
+
+    # -- configuration -------------------------------------------------------------------
+    def set_options(self, cov_form="SqExp", mean_form="Zero", noise_corr=False, ard_mode="intended"):
+        if cov_form not in COV:
+            raise GpsError(_lib.GPS_ERR_UNSUPPORTED, f"covFuncForm {cov_form!r} is not built (SqExp, ARD)")
+        self._ck(self.lib.gps_set_options(self.h, COV[cov_form], MEAN[mean_form], NOISE_CORR[noise_corr],
+                                          ARD_MODE[ard_mode]))
+        self.opts = (cov_form, mean_form, noise_corr, ard_mode)
+
+    def set_data(self, X, y, events=None):
+        if self.batch == 1:
+            X = f64(X)
+            n, d = X.shape
+        else:   # [batch, n, d] -> each problem column-major
+            X = np.asarray(X, dtype=np.float64)
+            _, n, d = X.shape
+            X = np.ascontiguousarray(np.transpose(X, (0, 2, 1)))
+        y = np.ascontiguousarray(np.asarray(y, dtype=np.float64)).reshape(self.batch, n)
+        ev = None if events is None else np.ascontiguousarray(np.asarray(events, dtype=np.float64)).reshape(self.batch, n)
+        self._ck(self.lib.gps_set_data(self.h, dptr(X), n, d, dptr(y), dptr(ev)))
+        self.n, self.d = n, d
+
+    def set_targets(self, y):
+        y = np.ascontiguousarray(np.asarray(y, dtype=np.float64)).reshape(self.batch, self.n)
+        self._ck(self.lib.gps_set_targets(self.h, dptr(y)))
+
+    def set_noise_corr(self, log_sc2):
+        v = np.ascontiguousarray(np.asarray(log_sc2, dtype=np.float64)).reshape(self.batch, -1)
+        self._ck(self.lib.gps_set_noise_corr(self.h, dptr(v), v.shape[1]))
+
+    # -- evaluations ---------------------------------------------------------------------
+    def _par(self, par):
+        p = np.ascontiguousarray(np.asarray(par, dtype=np.float64)).reshape(self.batch, -1)
+        return p, p.shape[1]
+
+    def nlml(self, par):
+        p, ln = self._par(par)
+        out = np.empty(self.batch)
+        self._ck(self.lib.gps_nlml(self.h, dptr(p), ln, dptr(out)))
+        return out if self.batch > 1 else float(out[0])
+
+    def nlml_grad(self, par):
+        p, ln = self._par(par)
+        out = np.empty(self.batch)
+        g = np.empty((self.batch, ln))
+        self._ck(self.lib.gps_nlml_grad(self.h, dptr(p), ln, dptr(out), dptr(g)))
+        return (out, g) if self.batch > 1 else (float(out[0]), g[0])
+
+    def finalize(self, par, want_K=False, want_L=False):
+        p, ln = self._par(par)
+        B, n = self.batch, self.n
+        K = np.empty((B, n, n)) if want_K else None
+        L = np.empty((B, n, n)) if want_L else None
+        alpha = np.empty((B, n))
+        mean = np.empty((B, n))
+        lml = np.empty(B)
+        self._ck(self.lib.gps_regress_finalize(self.h, dptr(p), ln, dptr(K), dptr(L), dptr(alpha), dptr(mean),
+                                               dptr(lml)))
+        # device matrices are column-major: transpose the [B, col, row] view into [B, row, col]
+        out = {"alpha": alpha, "meanTraining": mean, "logMarLik": lml}
+        if want_K:
+            out["K"] = np.transpose(K, (0, 2, 1))
+        if want_L:
+            out["L"] = np.transpose(L, (0, 2, 1))
+        if B == 1:
+            out = {k: (v[0] if isinstance(v, np.ndarray) and v.ndim >= 1 else v) for k, v in out.items()}
+            out["logMarLik"] = float(lml[0])
+        return out
+
+    def predict(self, par, Xstar, reuse_model=False):
+        p, ln = self._par(par)
+        if self.batch == 1:
+            Xs = f64(Xstar)
+            m = Xs.shape[0]
+        else:
+            Xs = np.asarray(Xstar, dtype=np.float64)
+            m = Xs.shape[1]
+            Xs = np.ascontiguousarray(np.transpose(Xs, (0, 2, 1)))
+        mu, vf, vd = (np.empty((self.batch, m)) for _ in range(3))
+        self._ck(self.lib.gps_predict(self.h, dptr(p), ln, 1 if reuse_model else 0, dptr(Xs), m, dptr(mu), dptr(vf),
+                                      dptr(vd)))
+        if self.batch == 1:
+            return mu[0], vf[0], vd[0]
+        return mu, vf, vd
+
+    def adjust(self, a, mu, s):
+        a, mu, s = (np.ascontiguousarray(np.asarray(v, dtype=np.float64).ravel()) for v in (a, mu, s))
+        em, ev = np.empty_like(a), np.empty_like(a)
+        self._ck(self.lib.gps_adjust(self.h, dptr(a), dptr(mu), dptr(s), a.size, dptr(em), dptr(ev)))
+        return em, ev
+
+    def cov(self, x1, x2, sf2, ell, cov_form="SqExp", ard_mode="intended"):
+        x1 = f64(x1)
+        n1, d = x1.shape
+        ell = np.ascontiguousarray(np.atleast_1d(np.asarray(ell, dtype=np.float64)).ravel())
+        if x2 is None:
+            x2p, n2 = None, n1
+        else:
+            x2a = f64(x2)
+            x2p, n2 = x2a, x2a.shape[0]
+        K = np.empty((n1, n2), order="F")
+        self._ck(self.lib.gps_cov(self.h, dptr(x1), n1, dptr(x2p), n2, d, float(sf2), dptr(ell), ell.size,
+                                  COV[cov_form], ARD_MODE[ard_mode], dptr(K)))
+        return K
+
+    # -- measurement helpers -------------------------------------------------------------
+    def launch_count(self):
+        return int(self.lib.gps_launch_count(self.h))
+
+    def last_device_ms(self):
+        return float(self.lib.gps_last_device_ms(self.h))
+
+    def set_graphs(self, enable=True):
+        self._ck(self.lib.gps_set_graphs(self.h, 1 if enable else 0))
+
+    def time_eval(self, kind=1, reps=10):
+        ms = C.c_double()
+        self._ck(self.lib.gps_time_eval(self.h, kind, reps, C.byref(ms)))
+        return ms.value
+
+    def time_stages(self):
+        ms = np.zeros(8)
+        self._ck(self.lib.gps_time_stages(self.h, dptr(ms)))
+        return ms
+
+    def bench_gemm(self, M, N, K, reps=5):
+        ms = C.c_double()
+        self._ck(self.lib.gps_bench_gemm(self.h, M, N, K, reps, C.byref(ms)))
+        return ms.value
+
+
+# =========================================================================================
+# Session: the device-resident state behind the stateless reference signatures
+# =========================================================================================
+class _Session:
+    """Keeps one handle alive across the stateless calls the reference makes (optim calls
+    ForOptimisationLog / OptimisationGradientLog with the same trainingData thousands of
+    times).  X is re-uploaded only when it changes; targets / noise correction when they do."""
+
+    def __init__(self):
+        self.fit = None
+        self.device = 0
+        self.X = None
+        self.y = None
+        self.events = None
+        self.lnc = None
+        self.ard_mode = "intended"
+
+    def reset(self):
+        if self.fit is not None:
+            self.fit.close()
+        self.__init__()
+
+    def bind(self, X, y, events, cov_form, mean_form, noise_corr, lnc):
+        if self.fit is None:
+            self.fit = Fit(self.device)
+        fit = self.fit
+        nc = noise_corr if noise_corr in ("noiseCorrLearned", "noiseCorrVec") else False
+        opts = (cov_form, mean_form, nc, self.ard_mode)
+        if fit.opts != opts:
+            fit.set_options(*opts)
+        X = np.asarray(X, dtype=np.float64)
+        y = np.asarray(y, dtype=np.float64).ravel()
+        events = np.ones(X.shape[0]) if events is None else np.asarray(events, dtype=np.float64).ravel()
+        same_X = self.X is not None and (X is self.X or (X.shape == self.X.shape and np.array_equal(X, self.X)))
+        same_ev = self.events is not None and np.array_equal(events, self.events)
+        if not (same_X and same_ev):
+            fit.set_data(X, y, events)
+            self.X, self.y, self.events = X, y.copy(), events.copy()
+            self.lnc = None
+        elif not np.array_equal(y, self.y):
+            fit.set_targets(y)
+            self.y = y.copy()
+        if nc == "noiseCorrVec":
+            v = np.asarray(lnc, dtype=np.float64).ravel()
+            ncens = int(np.sum(events == 0))
+            if v.size == 1 and ncens != 1:     # R recycles a scalar over the censored rows
+                v = np.full(ncens, v[0])
+            if self.lnc is None or not np.array_equal(v, self.lnc):
+                fit.set_noise_corr(v)
+                self.lnc = v.copy()
+        return fit
+
+
+SESSION = _Session()
+
+
+def set_device(device: int):
+    SESSION.reset()
+    SESSION.device = device
+
+
+def set_ard_mode(mode: str):
+    """'intended' (default; north_star) or 'as_written' (reproduces the reference's recycled
+    ARD scaling bit for bit in structure — SURVEY.md F3)."""
+    if mode not in ARD_MODE:
+        raise ValueError(mode)
+    SESSION.ard_mode = mode
+
+
+# =========================================================================================
+# Reference-named functions
+# =========================================================================================
+def CovFunc(x1, x2, x, y, extraParam, varFuncSqHyp, lengthHyp, covFuncForm):
+    """CovFunc.R:1 — covariance between the rows of x1 and x2 (x, y, extraParam unused for
+    SqExp / ARD).  'Matern', 'RF', 'InformedARD' raise (GPS_ERR_UNSUPPORTED)."""
+    if covFuncForm not in COV:
+        raise GpsError(_lib.GPS_ERR_UNSUPPORTED, f"covFuncForm {covFuncForm!r} is not built (SqExp, ARD)")
+    if SESSION.fit is None:
+        SESSION.fit = Fit(SESSION.device)
+    x1 = np.asarray(x1, dtype=np.float64)
+    x2 = np.asarray(x2, dtype=np.float64)
+    same = x1 is x2 or (x1.shape == x2.shape and np.array_equal(x1, x2))   # identical(x1, x2), CovFunc.R:24
+    return np.asarray(SESSION.fit.cov(x1, None if same else x2, float(np.ravel(varFuncSqHyp)[0]),
+                                      np.ravel(lengthHyp), covFuncForm, SESSION.ard_mode))
+
+
+def MeanFunc(meanHyp, x, meanFuncForm, n):
+    """MeanFunc.R:1 — host GEMV exactly as in the reference (the device applies the same mean
+    inside the fused evaluation; this standalone copy exists for API completeness)."""
+    x = np.asarray(x, dtype=np.float64)
+    d = x.shape[1]
+    if meanFuncForm == "Zero":
+        return np.zeros((n, 1))
+    if meanFuncForm == "Linear":
+        mh = np.asarray(meanHyp, dtype=np.float64).ravel()
+        return (x @ mh[:d] + mh[d]).reshape(n, 1)
+    raise ValueError(meanFuncForm)
+
+
+def _reject_priors(imposePriors):
+    if imposePriors:
+        raise GpsError(_lib.GPS_ERR_UNSUPPORTED,
+                       "imposePriors=TRUE cannot run in the reference as shipped (LogPriorX arity mismatch, "
+                       "SURVEY.md F6); evaluate with imposePriors=FALSE")
+
+
+def ForOptimisationLog(logHyp, trainingData, trainingTargets, trainingEvents, meanFuncForm, dimension, extraParam,
+                       covFuncForm, nSamples, noiseCorr, logHypNoiseCorrection, imposePriors):
+    """ForOptimisationLog.R:1 — negative log marginal likelihood, returned as a 1x1 matrix (:67).
+    A non-positive-definite Ky raises NotPositiveDefinite (the nearPD fallback, :43-51, stays
+    on the host side of the boundary)."""
+    _reject_priors(imposePriors)
+    fit = SESSION.bind(trainingData, trainingTargets, trainingEvents, covFuncForm, meanFuncForm, noiseCorr,
+                       logHypNoiseCorrection)
+    return np.array([[fit.nlml(np.ravel(logHyp))]])
+
+
+def OptimisationGradientLog(logHyp, trainingData, trainingTargets, trainingEvents, meanFuncForm, dimension,
+                            extraParam, covFuncForm, nSamples, noiseCorr, logHypNoiseCorrection, imposePriors):
+    """OptimisationGradientLog.R:1 — gradient as a k x 1 matrix (:93), same order as logHyp."""
+    _reject_priors(imposePriors)
+    fit = SESSION.bind(trainingData, trainingTargets, trainingEvents, covFuncForm, meanFuncForm, noiseCorr,
+                       logHypNoiseCorrection)
+    _, g = fit.nlml_grad(np.ravel(logHyp))
+    return g.reshape(-1, 1)
+
+
+def _flatten(logHyp, d, meanFuncForm, noiseCorr, lnc):
+    vec = np.concatenate([np.ravel(np.asarray(logHyp["noise"], dtype=np.float64)),
+                          np.ravel(np.asarray(logHyp["func"], dtype=np.float64)),
+                          np.ravel(np.asarray(logHyp["length"], dtype=np.float64)),
+                          np.ravel(np.asarray(logHyp["mean"], dtype=np.float64))])      # GPRegression.R:22
+    if meanFuncForm == "Zero":
+        vec = vec[:vec.size - (d + 1)]                                                  # :23
+    if noiseCorr == "noiseCorrLearned":
+        vec = np.concatenate([vec, np.ravel(np.asarray(lnc, dtype=np.float64))])        # :24
+    return vec
+
+
+def _par_from_chosen(logHypChosen, d, meanFuncForm, noiseCorr, lnc):
+    return _flatten(logHypChosen, d, meanFuncForm, noiseCorr, lnc)
+
+
+def GPRegression(logHyp, parameterStructure, trainingTestStructure, logHypNoiseCorrection, want_matrices=False):
+    """GPRegression.R:1 — optimise the hyper-parameters with stats::optim's algorithm, then
+    rebuild the model at the optimum.  Returns the reference's list (:75-81).  ``K`` and ``L``
+    (8n^2 bytes each) are only copied back when ``want_matrices`` is true; the factor stays
+    resident on the GPU for GPPredict either way."""
+    X = trainingTestStructure["trainingData"]
+    y = np.asarray(trainingTestStructure["trainingTargets"], dtype=np.float64).ravel()
+    events = trainingTestStructure.get("events")
+    d = np.asarray(X).shape[1]
+    ps = parameterStructure
+    noiseCorr = ps["noiseCorr"]
+    maxit = ps["maxitSurvival"] if ps["modelType"] == "survival" else ps["maxit"]        # :16
+    meanFuncForm, covFuncForm = ps["meanFuncForm"], ps["covFuncForm"]
+    _reject_priors(ps.get("imposePriors", False))
+    vec = _flatten(logHyp, d, meanFuncForm, noiseCorr, logHypNoiseCorrection)
+    fit = SESSION.bind(X, y, events, covFuncForm, meanFuncForm, noiseCorr, logHypNoiseCorrection)
+    opt = _optim.optim(vec, fn=lambda p: fit.nlml(p), gr=lambda p: fit.nlml_grad(p)[1],
+                       method=ps["optimType"], maxit=maxit)                              # :28-31
+    vec = opt["par"]
+    fin = fit.finalize(vec, want_K=want_matrices, want_L=want_matrices)                  # :60-71
+    lnc = logHypNoiseCorrection
+    body = vec
+    if noiseCorr == "noiseCorrLearned":                                                  # :35-38
+        lnc = vec[-1:]
+        body = vec[:-1]
+    p = d if covFuncForm == "ARD" else 1
+    mean = body[body.size - d - 1:] if meanFuncForm == "Linear" else np.zeros(d + 1)     # :54-57
+    # the reference stores log(exp(.)) of the optimum (:39-52,73)
+    chosen = {"noise": float(np.log(np.exp(body[0]))), "func": float(np.log(np.exp(body[1]))),
+              "length": np.log(np.exp(body[2:2 + p])), "mean": np.array(mean, dtype=np.float64)}
+    out = {"logHyp": logHyp, "meanTraining": fin["meanTraining"].reshape(-1, 1), "alpha": fin["alpha"].reshape(-1, 1),
+           "logHypChosen": chosen, "logMarLik": fin["logMarLik"], "objective": opt["value"],
+           "K": fin.get("K"), "L": fin.get("L"), "optim": opt, "_par": vec.copy()}
+    if noiseCorr in ("noiseCorrVec", "noiseCorrLearned"):                                # :76-81
+        lnc = np.asarray(lnc, dtype=np.float64).ravel()
+        if lnc[0] == -np.inf:
+            lnc = np.array([-1e10])
+        out["logHypNoiseCorrection"] = lnc
+    return out
+
+
+def GPPredict(regressionStructure, parameterStructure, trainingTestStructure, logHypNoiseCorrection):
+    """GPPredict.R:1 — predictive mean / variances at testData.  For GPS2 / GPS3 the factor is
+    rebuilt from the passed noise correction and the current trainingTargets (:36-46); for
+    GPR / GPS1 the factor and alpha of ``regressionStructure`` (resident on the GPU) are used."""
+    ps = parameterStructure
+    meanFuncForm, covFuncForm, noiseCorr = ps["meanFuncForm"], ps["covFuncForm"], ps["noiseCorr"]
+    X = trainingTestStructure["trainingData"]
+    y = trainingTestStructure["trainingTargets"]
+    events = trainingTestStructure.get("events")
+    Xs = np.asarray(trainingTestStructure["testData"], dtype=np.float64)
+    d = np.asarray(X).shape[1]
+    corr = noiseCorr in ("noiseCorrVec", "noiseCorrLearned")
+    par = _par_from_chosen(regressionStructure["logHypChosen"], d, meanFuncForm, noiseCorr, logHypNoiseCorrection)
+    if corr:
+        fit = SESSION.bind(X, y, events, covFuncForm, meanFuncForm, noiseCorr, logHypNoiseCorrection)
+        mu, vf, vd = fit.predict(par, Xs, reuse_model=False)
+    else:
+        fit = SESSION.fit
+        if fit is None:
+            raise GpsError(_lib.GPS_ERR_STATE, "GPPredict: no resident model; call GPRegression first")
+        mu, vf, vd = fit.predict(par, Xs, reuse_model=True)
+    return {"funcMeanPred": mu.reshape(-1, 1), "varFunction": vf, "varData": vd}
+
+
+def AdjustTrainingSurvivalMeanVariance(a, mu, sigma):
+    """AdjustTrainingSurvivalMeanVariance.R:1 — accepts scalars (as the reference's sapply
+    passes them) or vectors; returns list('mu'=, 'sigma'=)."""
+    if SESSION.fit is None:
+        SESSION.fit = Fit(SESSION.device)
+    scalar = np.ndim(a) == 0
+    em, ev = SESSION.fit.adjust(np.atleast_1d(a), np.atleast_1d(mu), np.atleast_1d(sigma))
+    if scalar:
+        return {"mu": float(em[0]), "sigma": float(ev[0])}
+    return {"mu": em, "sigma": ev}
+
+
+_REAL_SOURCES = ("CuratedOvarian", "TCGA2STAT", "TCGASynapse", "TCGAYuanEtAl")
+
+
+def ApplyGP(trainingTestStructure, dataOptionsStructure, parameterStructure, plotSaveOptions=None):
+    """ApplyGP.R:1, lines 77-282 — target transforms, the GPS outer loop, final predictions.
+    Plotting, saving and the survcomp / survAUC metrics (:287-435) are out of scope."""
+    tts = dict(trainingTestStructure)
+    ps = dict(parameterStructure)
+    modelType, noiseCorr = ps["modelType"], ps["noiseCorr"]
+    if ps.get("burnIn", False):
+        raise GpsError(_lib.GPS_ERR_UNSUPPORTED, "burnIn=TRUE is broken in the reference as shipped (SURVEY.md F6)")
+    source = (dataOptionsStructure or {}).get("dataSource", "Generate")
+    X = np.asarray(tts["trainingData"], dtype=np.float64)
+    events = np.asarray(tts["events"], dtype=np.float64).ravel()
+    y = np.log(np.asarray(tts["trainingTargets"], dtype=np.float64).ravel())            # :79 / :94
+    if modelType == "survival" and source in _REAL_SOURCES:
+        y = y - np.median(y)                                                            # :86-92
+    logHyp = ps["logHypStart"]                                                          # :130,136
+    out = {}
+    if modelType == "survival":
+        cens = events == 0
+        a_start = y[cens].copy()                                                        # :108
+        n_cens = int(cens.sum())
+        learned = y.copy()                                                              # :145
+        if noiseCorr == "noiseCorrLearned":                                             # :146-152
+            lnc = np.atleast_1d(np.asarray(logHyp["noise"], dtype=np.float64))
+        elif noiseCorr == "noiseCorrVec":
+            lnc = np.full(n_cens, float(np.ravel(logHyp["noise"])[0]))
+        else:
+            lnc = None
+        count, change, objective = 0, 1.0, 1.0                                          # :140-143
+        objective_table = [0.0]
+        while (change > ps["tolerance"] and count < ps["maxCount"]) or count <= 5:      # :162
+            learning = {"trainingData": X, "trainingTargets": learned, "testData": X[cens], "events": events}
+            reg = GPRegression(logHyp, ps, learning, lnc)                               # :170
+            pred = GPPredict(reg, ps, learning, reg.get("logHypNoiseCorrection"))       # :171
+            logHyp = reg["logHypChosen"]                                                # :185
+            objective_new = reg["objective"]                                            # :187
+            objective_table.append(objective_new)
+            adj = AdjustTrainingSurvivalMeanVariance(a_start, pred["funcMeanPred"].ravel(), pred["varData"])   # :190
+            change = abs(objective - objective_new)                                     # :195
+            objective = objective_new
+            count += 1
+            learned = learned.copy()
+            learned[cens] = adj["mu"]                                                   # :201
+            if noiseCorr == "noiseCorrVec":                                             # :208-210
+                with np.errstate(divide="ignore"):
+                    lnc = np.log(adj["sigma"])
+                lnc[np.isinf(lnc)] = -1e10
+            elif noiseCorr == "noiseCorrLearned":                                       # :211-212
+                lnc = reg["logHypNoiseCorrection"]
+        out["convergence"] = 0 if count < ps["maxCount"] else 1                         # :216-221
+        out["count"] = count
+        out["objectiveTable"] = np.array(objective_table)
+        out["trainingTargetsLearned"] = learned
+        final_targets = learned
+    else:                                                                               # :224-232
+        ps["noiseCorr"] = False
+        learning = {"trainingData": X, "trainingTargets": y, "events": events}
+        reg = GPRegression(logHyp, ps, learning, None)
+        lnc = None
+        final_targets = y
+    final = {"trainingData": X, "trainingTargets": final_targets, "testData": tts["testData"], "events": events}
+    pred = GPPredict(reg, ps, final, lnc)                                               # :243 / :245
+    train = dict(final, testData=X)
+    pred3 = GPPredict(reg, ps, train, lnc)                                              # :272 / :280
+    out.update({"logHypChosen": reg["logHypChosen"], "funcMeanPred": pred["funcMeanPred"],
+                "varFunction": pred["varFunction"], "varData": pred["varData"],
+                "trainingSetPredictions": pred3["funcMeanPred"], "logMarLik": reg["logMarLik"],
+                "objective": reg["objective"]})
+    return out

@@ -1,0 +1,204 @@
+"""Host-side optimisers used where the reference calls ``stats::optim`` (GPRegression.R:28-31).
+
+In an R deployment ``optim`` itself keeps running in R and calls the drop-in
+``ForOptimisationLog`` / ``OptimisationGradientLog``; this module exists so that the Python
+mirror of the reference interface (gpsurvival_b200/gp.py) can run whole fits without R.
+Both routines follow the algorithms R's optim implements (Nash 1990, "Compact Numerical
+Methods for Computers": Algorithm 19 Nelder-Mead = R's nmmin, Algorithm 21 variable metric
+= R's vmmin) with R's defaults: alpha=1, beta=0.5, gamma=2, abstol=-Inf,
+reltol=sqrt(.Machine$double.eps); ``maxit`` counts function evaluations for Nelder-Mead
+and iterations for BFGS, as in R.
+
+Pure host logic, numpy only.
+"""
+from __future__ import annotations
+
+import math
+
+import numpy as np
+
+BIG = 1.0e35
+RELTOL = math.sqrt(np.finfo(np.float64).eps)
+
+
+def _safe(fn, x):
+    f = float(fn(x))
+    return f if math.isfinite(f) else BIG
+
+
+def nelder_mead(fn, par, maxit=500, abstol=-math.inf, reltol=RELTOL, alpha=1.0, beta=0.5, gamma=2.0):
+    """Nelder-Mead as R's nmmin runs it.  The simplex is an (n+1) x n array of vertices with a
+    parallel array of function values; ``lo``/``hi`` are the best / worst vertex indices."""
+    x0 = np.array(par, dtype=np.float64).ravel()
+    n = x0.size
+    if maxit <= 0:
+        return {"par": x0, "value": float(fn(x0)), "counts": 0, "convergence": 0}
+    f0 = float(fn(x0))
+    if not math.isfinite(f0):
+        raise RuntimeError("function cannot be evaluated at initial parameters")
+    evals = 1
+    convtol = reltol * (abs(f0) + reltol)
+    step = max(0.1 * float(np.max(np.abs(x0))) if n else 0.0, 0.0)
+    if step == 0.0:
+        step = 0.1
+    V = np.tile(x0, (n + 1, 1))          # vertices
+    F = np.full(n + 1, np.nan)
+    F[0] = f0
+    size = 0.0
+    for j in range(1, n + 1):
+        trystep = step
+        while V[j, j - 1] == x0[j - 1]:
+            V[j, j - 1] = x0[j - 1] + trystep
+            trystep *= 10.0
+        size += trystep
+    oldsize = size
+    lo = 0
+    need_vertices = True
+    fail = 0
+    while True:
+        if need_vertices:
+            for j in range(n + 1):
+                if j != lo:
+                    F[j] = _safe(fn, V[j].copy())
+                    evals += 1
+            need_vertices = False
+        # best / worst exactly as nmmin scans them (first strict improvement wins)
+        vl = F[lo]
+        vh = vl
+        hi = lo
+        for j in range(n + 1):
+            if j != lo:
+                if F[j] < vl:
+                    lo, vl = j, F[j]
+                if F[j] > vh:
+                    hi, vh = j, F[j]
+        if vh <= vl + convtol or vl <= abstol:
+            break
+        # centroid of all vertices but the worst, accumulated in nmmin's order
+        cen = -V[hi].copy()
+        for j in range(n + 1):
+            cen = cen + V[j]
+        cen = cen / n
+        xr = (1.0 + alpha) * cen - alpha * V[hi]
+        fr = _safe(fn, xr.copy())
+        evals += 1
+        if fr < vl:
+            xe = gamma * xr + (1.0 - gamma) * cen
+            fe = _safe(fn, xe.copy())
+            evals += 1
+            if fe < fr:
+                V[hi], F[hi] = xe, fe
+            else:
+                V[hi], F[hi] = xr, fr
+        else:
+            if fr < vh:
+                V[hi], F[hi] = xr, fr
+            xc = (1.0 - beta) * V[hi] + beta * cen
+            fc = _safe(fn, xc.copy())
+            evals += 1
+            if fc < F[hi]:
+                V[hi], F[hi] = xc, fc
+            elif fr >= vh:
+                need_vertices = True
+                size = 0.0
+                for j in range(n + 1):
+                    if j != lo:
+                        V[j] = beta * (V[j] - V[lo]) + V[lo]
+                        size += float(np.sum(np.abs(V[j] - V[lo])))
+                if size < oldsize:
+                    oldsize = size
+                else:
+                    fail = 10
+                    break
+        if evals > maxit:
+            break
+    if evals > maxit:
+        fail = 1
+    return {"par": V[lo].copy(), "value": float(F[lo]), "counts": evals, "convergence": fail}
+
+
+def bfgs(fn, gr, par, maxit=100, abstol=-math.inf, reltol=RELTOL):
+    """Variable-metric (BFGS) minimiser as R's vmmin runs it, with the inverse-Hessian
+    approximation kept as a full symmetric matrix."""
+    stepredn, acctol, reltest = 0.2, 1.0e-4, 10.0
+    b = np.array(par, dtype=np.float64).ravel()
+    n = b.size
+    if maxit <= 0:
+        return {"par": b, "value": float(fn(b)), "counts": (0, 0), "convergence": 0}
+    f = float(fn(b))
+    if not math.isfinite(f):
+        raise RuntimeError("initial value in 'vmmin' is not finite")
+    fmin = f
+    nf = ng = 1
+    g = np.array(gr(b), dtype=np.float64).ravel()
+    it = 1
+    ilast = ng
+    Bm = np.eye(n)
+    while True:
+        if ilast == ng:
+            Bm = np.eye(n)
+        x_old = b.copy()
+        g_old = g.copy()
+        t = np.array([-sum(Bm[i, j] * g[j] for j in range(n)) for i in range(n)])
+        gradproj = float(sum(t[i] * g[i] for i in range(n)))
+        if gradproj < 0.0:
+            steplength = 1.0
+            accpoint = False
+            while True:
+                b = x_old + steplength * t
+                count = int(np.sum((reltest + x_old) == (reltest + b)))
+                if count < n:
+                    f = float(fn(b))
+                    nf += 1
+                    accpoint = math.isfinite(f) and f <= fmin + gradproj * steplength * acctol
+                    if not accpoint:
+                        steplength *= stepredn
+                if count == n or accpoint:
+                    break
+            enough = (f > abstol) and abs(f - fmin) > reltol * (abs(fmin) + reltol)
+            if not enough:
+                count = n
+                fmin = f
+            if count < n:
+                fmin = f
+                g = np.array(gr(b), dtype=np.float64).ravel()
+                ng += 1
+                it += 1
+                t = steplength * t
+                c = g - g_old
+                d1 = float(sum(t[i] * c[i] for i in range(n)))
+                if d1 > 0:
+                    xv = np.array([sum(Bm[i, j] * c[j] for j in range(n)) for i in range(n)])
+                    d2 = 1.0 + float(sum(xv[i] * c[i] for i in range(n))) / d1
+                    Bm = Bm + (d2 * np.outer(t, t) - np.outer(xv, t) - np.outer(t, xv)) / d1
+                else:
+                    ilast = ng
+            else:
+                if ilast < ng:
+                    count = 0
+                    ilast = ng
+        else:
+            count = 0
+            if ilast == ng:
+                count = n
+            else:
+                ilast = ng
+        if it >= maxit:
+            break
+        if ng - ilast > 2 * n:
+            ilast = ng
+        if count == n and ilast == ng:
+            break
+    return {"par": b, "value": float(fmin), "counts": (nf, ng), "convergence": 0 if it < maxit else 1}
+
+
+def optim(par, fn, gr=None, method="Nelder-Mead", maxit=None):
+    """``stats::optim(par, fn, gr, method=, control=list(maxit=))`` for the two methods the
+    hot path needs."""
+    if method == "Nelder-Mead":
+        return nelder_mead(fn, par, maxit=500 if maxit is None else maxit)
+    if method == "BFGS":
+        if gr is None:
+            raise ValueError("BFGS needs a gradient")
+        return bfgs(fn, gr, par, maxit=100 if maxit is None else maxit)
+    raise NotImplementedError(f"optim method {method!r} (Nelder-Mead and BFGS are restated)")

@@ -1,0 +1,143 @@
+/*
+ * gpsurv.h — C ABI of libgpsurv.so: the B200 (sm_100a) FP64 implementation of the GP
+ * training / prediction hot path of kllloyd/GPSurvival.
+ *
+ * The reference has no FFI layer (it is 58 plain R scripts); this ABI sits *underneath*
+ * the unchanged R function signatures.  Each entry point names the reference code it
+ * replaces (paths relative to /root/reference/code/).  See INTEGRATION.md for the
+ * `.Call` glue and SURVEY.md §8b for the contract.
+ *
+ * Conventions
+ *   - every function returns a gps_status (0 = GPS_OK); text via gps_last_error().
+ *   - all matrices are FP64, column-major (R layout), leading dimension = rows.
+ *   - host pointers are read during the call only; the library never retains them and
+ *     never allocates memory the caller must free (except the opaque handle).
+ *   - `events` is 0/1 as double (R numeric); 0 = right-censored.
+ *   - hyper-parameter vector `par` (ForOptimisationLog.R:9-31, GPRegression.R:22-25):
+ *       [log sn2, log sf2, log ell_1..log ell_p, (w_1..w_d, b  — Linear mean only),
+ *        (log sc2 — GPS2 'noiseCorrLearned' only, last)]   with p = 1 (SqExp) or d (ARD).
+ *   - no CPU fallback: without an sm_100 device gps_create fails with GPS_ERR_CUDA.
+ *   - a handle is not thread-safe; use one handle per host thread per device.
+ */
+#ifndef GPSURV_H
+#define GPSURV_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct gps_handle_s* gps_handle;
+
+typedef enum {
+  GPS_OK = 0,
+  GPS_ERR_ARG = 1,          /* bad argument (NULL, size, NaN/Inf in par) */
+  GPS_ERR_CUDA = 2,         /* CUDA runtime failure or no sm_100 device */
+  GPS_ERR_NOT_PD = 3,       /* Ky not positive definite; gps_last_pivot() = failing column (1-based) */
+  GPS_ERR_UNSUPPORTED = 4,  /* RF / InformedARD / Matern covariance, as-written ARD gradient */
+  GPS_ERR_STATE = 5         /* call order (e.g. predict before finalize) */
+} gps_status;
+
+typedef enum { GPS_COV_SQEXP = 0, GPS_COV_ARD = 1 } gps_cov_form;          /* covFuncForm */
+typedef enum { GPS_MEAN_ZERO = 0, GPS_MEAN_LINEAR = 1 } gps_mean_form;     /* meanFuncForm */
+typedef enum {
+  GPS_NC_NONE = 0,      /* noiseCorr FALSE / 'none'      (GPR, GPS1) */
+  GPS_NC_LEARNED = 1,   /* 'noiseCorrLearned'            (GPS2)      */
+  GPS_NC_VEC = 2        /* 'noiseCorrVec'                (GPS3)      */
+} gps_noise_corr;
+typedef enum {
+  GPS_ARD_INTENDED = 0,   /* column k divided by ell_k (north_star item 1) */
+  GPS_ARD_AS_WRITTEN = 1  /* R recycling of CovFunc.R:25,27: element (i,j) / ell[(i+j*n) mod p] */
+} gps_ard_mode;
+
+const char* gps_version(void);
+const char* gps_last_error(gps_handle h);      /* h may be NULL: last error of the calling thread's stateless call */
+int gps_last_pivot(gps_handle h);              /* failing pivot of the last GPS_ERR_NOT_PD (1-based), else 0 */
+
+/* ---- lifetime ----------------------------------------------------------------------- */
+/* One handle = one fit (one trainingTestStructure) on one device.  `batch` > 1 makes it a
+ * batch of `batch` independent fits of identical shape evaluated by the same launches
+ * (restarts / CV folds — SURVEY.md §8e); every array argument below then carries the
+ * batch as the slowest dimension. */
+int gps_create(int device, gps_handle* out);
+int gps_create_batch(int device, int batch, gps_handle* out);
+int gps_destroy(gps_handle h);
+
+/* Options that the reference passes as strings in parameterStructure (GPRegression.R:13-20). */
+int gps_set_options(gps_handle h, int cov_form, int mean_form, int noise_corr, int ard_mode);
+
+/* ---- data ---------------------------------------------------------------------------- */
+/* trainingData (n x d), trainingTargets (n), events (n) — GPRegression.R:7-11.  X is constant
+ * over all evaluations of a fit and is uploaded once. */
+int gps_set_data(gps_handle h, const double* X, int n, int d, const double* y, const double* events);
+/* trainingTargetsLearned changes every GPS round (ApplyGP.R:201). */
+int gps_set_targets(gps_handle h, const double* y);
+/* logHypNoiseCorrection for GPS3: one value per censored row, in row order (ApplyGP.R:149,209;
+ * ForOptimisationLog.R:36-39).  len must equal the number of censored rows.  (For GPS2 the
+ * correction travels inside `par`.) */
+int gps_set_noise_corr(gps_handle h, const double* log_sc2, int len);
+
+/* ---- CovFunc.R:1-54 (SqExp / ARD) ------------------------------------------------------ */
+/* K (n1 x n2) = sf2 * exp(-0.5 * ||x1_i/ell - x2_j/ell||^2).  X2 == NULL means X2 = X1
+ * (the identical(x1,x2) branch, CovFunc.R:24-25).  Stateless: `h` only supplies the device
+ * and scratch memory. */
+int gps_cov(gps_handle h, const double* X1, int n1, const double* X2, int n2, int d,
+            double sf2, const double* ell, int p, int cov_form, int ard_mode, double* K_out);
+
+/* ---- ForOptimisationLog.R:1-68 --------------------------------------------------------- */
+/* Negative log marginal likelihood at `par` (imposePriors = FALSE).  nlml_out: `batch` values;
+ * par: batch x len. */
+int gps_nlml(gps_handle h, const double* par, int len, double* nlml_out);
+
+/* ---- OptimisationGradientLog.R:1-94 ---------------------------------------------------- */
+/* Gradient w.r.t. `par`, same order as `par` (:88-89).  Reuses the factorisation of the last
+ * gps_nlml when `par`, targets and noise correction are unchanged (optim calls fn and gr
+ * separately — SURVEY.md §3.3).  nlml_out may be NULL. */
+int gps_nlml_grad(gps_handle h, const double* par, int len, double* nlml_out, double* grad_out);
+
+/* ---- GPRegression.R:60-82 (everything after optim) ------------------------------------- */
+/* Recompute the model at `par` and keep it resident for gps_predict.  Optional outputs
+ * (NULL to skip; K and L are n x n, 8n^2 bytes each): K_out noise-free covariance (:61),
+ * L_out lower Cholesky factor of Ky (:65-69), alpha_out (:70), mean_out meanTraining (:60),
+ * logmarlik_out positive-sign log marginal likelihood (:71). */
+int gps_regress_finalize(gps_handle h, const double* par, int len, double* K_out, double* L_out,
+                         double* alpha_out, double* mean_out, double* logmarlik_out);
+
+/* ---- GPPredict.R:1-60 ------------------------------------------------------------------- */
+/* Predict at testData (m x d) with the hyper-parameters `par`.  If the resident model was
+ * built from the same par / targets / noise correction it is reused; otherwise (GPS2/GPS3 with
+ * a new correction or new targets, GPPredict.R:36-46) it is rebuilt first.  With
+ * `reuse_model` != 0 the resident model is used as is, whatever the current targets are —
+ * that is what the reference does for GPR / GPS1, where L and alpha come from
+ * regressionStructure (GPPredict.R:12-13).  Outputs: funcMeanPred, varFunction, varData (m each). */
+int gps_predict(gps_handle h, const double* par, int len, int reuse_model, const double* Xstar, int m,
+                double* mu_out, double* varf_out, double* vard_out);
+
+/* ---- AdjustTrainingSurvivalMeanVariance.R:1-37 ------------------------------------------ */
+/* Lower-truncated-normal moments for c censored samples: a = censoring time, mu/s = predictive
+ * mean and the value the reference passes as `sigma` (ApplyGP.R:173,190 pass the variance).
+ * `1 - pnorm` is computed exactly as the reference does, including the 1e-12 branch (:28-31). */
+int gps_adjust(gps_handle h, const double* a, const double* mu, const double* s, int c,
+               double* mean_out, double* var_out);
+
+/* ---- introspection used by bench.py / tests ------------------------------------------- */
+/* Number of kernels this handle has launched since creation (bench.py's gpu_launches). */
+long long gps_launch_count(gps_handle h);
+/* Device time in ms of the last gps_nlml / gps_nlml_grad / finalize / predict (CUDA events
+ * around the device work of that call, excluding host<->device copies). */
+double gps_last_device_ms(gps_handle h);
+/* Enable (1) / disable (0) CUDA-graph replay of evaluations (default on). */
+int gps_set_graphs(gps_handle h, int enable);
+/* Time `reps` back-to-back device-only repetitions of the last evaluation kind
+ * (0 = nlml, 1 = nlml+grad) at the last `par`, inputs resident; returns ms per repetition. */
+int gps_time_eval(gps_handle h, int kind, int reps, double* ms_out);
+/* Stage timers: fills ms[0..7] = {prescale+gram, cholesky, inverse, kinv, wk+grad gemm, rest, 0, total}
+ * for one nlml+grad evaluation at the last par, each stage timed with CUDA events. */
+int gps_time_stages(gps_handle h, double* ms_out);
+/* Raw FP64 GEMM through the library's DMMA kernel: C(MxN) = A(MxK) * B(NxK)' — for the
+ * peak-fraction measurement beside cublasDgemm.  Device-resident synthetic operands. */
+int gps_bench_gemm(gps_handle h, int M, int N, int K, int reps, double* ms_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GPSURV_H */

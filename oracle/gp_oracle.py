@@ -651,7 +651,7 @@ def bfgs(fn, gr, par, maxit=100, abstol=-np.inf, reltol=RELTOL):
                     D2 = 1.0 + D2 / D1
                     for i in range(n):
                         for j in range(i + 1):
-                            B[i, j] += (D2 * t[i] * t[j] - X[i] * c[j] - t[i] * X[j]) / D1
+                            B[i, j] += (D2 * t[i] * t[j] - X[i] * t[j] - t[i] * X[j]) / D1
                 else:
                     ilast = gradcount
             else:
