@@ -1,0 +1,320 @@
+#!/usr/bin/env python
+"""bench.py — GP logML + gradient evaluations / s on BASELINE.json configs[1]
+(C2: GPS3, ARD, n=2000, d=20, 50 % censoring), one process per GPU.
+
+    python bench.py --gpus N --steps K --warmup W            # our CUDA path
+    python bench.py --impl reference --steps K --warmup W    # the reference algorithm on host cores
+
+One "step" = one evaluation of ForOptimisationLog + OptimisationGradientLog (NLML and its
+gradient w.r.t. all 22 hyper-parameters); the e2e leg uses a fresh hyper-parameter vector every
+step, the device-resident leg replays the evaluation at the resident vector (nothing is cached
+between replays: every replay recomputes Gram, Cholesky, inverse and gradient).
+
+* value  : evaluations/s, inputs resident in HBM, device-timed with CUDA events on the
+           library's stream (gps_time_eval: K back-to-back graph replays), max over ranks.
+* e2e    : the same metric through the public API with HOST buffers: every step uploads X, y,
+           events, the GPS3 noise-correction vector and par, evaluates, and reads NLML+gradient back.
+* roofline: the evaluation graph (one launch = one evaluation = 3 n^2 d + n^3 algorithmic FP64
+           flops) against the FP64 tensor (DMMA) peak measured in this run with
+           cublasDgemm 8192^3 (MEASURED_PEAKS.json carries no FP64 figure).
+* cpu_baseline: the reference's algorithm restated in numpy (oracle/, as-written operation
+           sequence) on the host cores — R itself is not installed in the image.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+from gpsurvival_b200 import synth   # noqa: E402
+
+METRIC = "gp_logml_grad_evals_per_sec"
+UNIT = "evals/s"
+CFG = synth.CONFIGS["C2"]
+
+
+def workload(rank: int):
+    pb = synth.make_config_problem(CFG, fit_index=rank)
+    X = pb["trainingData"]
+    y = np.log(pb["trainingTargets"])
+    ev = pb["events"]
+    lnc = np.full(int(np.sum(ev == 0)), np.log(0.2))
+    par0 = synth.start_par(CFG, d=X.shape[1])
+    return X, y, ev, lnc, par0
+
+
+def step_pars(par0, count, seed):
+    rng = np.random.default_rng(seed)
+    return par0[None, :] + 0.05 * rng.standard_normal((count, par0.size))
+
+
+def algorithmic_flops(n, d, ard=True):
+    return (3.0 if ard else 1.0) * n * n * d + float(n) ** 3
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region (profiling guide)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.idx = gpu_index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-i", str(self.idx), "-lms", "100"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[1]))
+                mx.append(float(r[2]))
+            except (ValueError, IndexError):
+                continue
+            for k, nm in enumerate(names):
+                if len(r) > 5 + k and r[5 + k].lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": float(max(mx)) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def measure_fp64_peak(device):
+    """cublasDgemm 8192^3 (via torch.matmul, float64): best of 5 — the FP64 tensor-peak denominator."""
+    import torch
+    n = 8192
+    a = torch.randn(n, n, dtype=torch.float64, device=device)
+    b = torch.randn(n, n, dtype=torch.float64, device=device)
+    torch.matmul(a, b)
+    torch.cuda.synchronize(device)
+    best = 1e30
+    for _ in range(5):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        torch.matmul(a, b)
+        e1.record()
+        torch.cuda.synchronize(device)
+        best = min(best, e0.elapsed_time(e1))
+    del a, b
+    torch.cuda.empty_cache()
+    return 2.0 * n ** 3 / (best * 1e-3) / 1e12
+
+
+def cpu_eval(par, X, y, ev, lnc):
+    """One NLML + gradient evaluation the way the reference computes it (numpy restatement)."""
+    from oracle import gp_oracle as orc
+    kw = dict(cov_form=CFG.cov_form, mean_form="Zero", noise_corr=CFG.noise_corr, log_hyp_noise_corr=lnc)
+    f = orc.nlml(par, X, y, ev, as_written_ops=True, **kw)
+    g = orc.nlml_grad(par, X, y, ev, **kw)
+    return f, g
+
+
+def cpu_threads():
+    try:
+        from threadpoolctl import threadpool_info
+        th = [p.get("num_threads", 1) for p in threadpool_info() if p.get("user_api") == "blas"]
+        return max(th) if th else os.cpu_count()
+    except Exception:
+        return os.cpu_count()
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    X, y, ev, lnc, par0 = workload(0)
+    pars = step_pars(par0, args.steps + args.warmup, 7)
+    t_w = time.perf_counter()
+    for w in range(max(args.warmup, 1)):
+        cpu_eval(pars[w], X, y, ev, lnc)
+    per = (time.perf_counter() - t_w) / max(args.warmup, 1)
+    steps = args.steps
+    if steps * per > 180.0:          # keep the whole arm within a few minutes on slow hosts
+        steps = max(3, int(180.0 / per))
+    t0 = time.perf_counter()
+    for s in range(steps):
+        cpu_eval(pars[args.warmup + s], X, y, ev, lnc)
+    dt = time.perf_counter() - t0
+    val = steps / dt
+    cores = cpu_threads()
+    sample = f"{steps} full evaluations of the C2 workload (n={X.shape[0]}, d={X.shape[1]})"
+    line = {
+        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * dt / steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "C2: GPS3 ARD NLML+gradient, n=2000 d=20 c=1000 (BASELINE.json configs[1])",
+                   "n": int(X.shape[0]), "d": int(X.shape[1]), "hyperparameters": int(par0.size)},
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample,
+                         "note": "reference algorithm restated in numpy (as-written op sequence); R unavailable in image"},
+        "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+def run_gpu(args):
+    import torch
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    device = torch.device("cuda", local)
+    torch.cuda.set_device(device)
+
+    from gpsurvival_b200 import gp
+    X, y, ev, lnc, par0 = workload(rank)
+    n, d = X.shape
+    flops = algorithmic_flops(n, d, ard=True)
+
+    fit = gp.Fit(local)
+    fit.set_options(CFG.cov_form, "Zero", CFG.noise_corr, "intended")
+    fit.set_data(X, y, ev)
+    fit.set_noise_corr(lnc)
+    K, W = args.steps, max(args.warmup, 3)
+    pars = step_pars(par0, 2 * (K + W), 11 + rank)
+    for w in range(W):                                   # warm-up: direct run, graph capture, replay
+        fit.nlml_grad(pars[w])
+
+    def barrier():
+        torch.cuda.synchronize(device)
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize(device)
+
+    def max_over_ranks(v):
+        if dist is None:
+            return v
+        t = torch.tensor([v], dtype=torch.float64, device=device)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---- FP64 tensor peak of this GPU (roofline denominator), rank 0 only to keep the run short
+    peak_tf = measure_fp64_peak(device) if rank == 0 else 0.0
+
+    # ---- device-resident throughput: K graph replays, CUDA events on the library's stream --------
+    sampler = ClockSampler(local)
+    barrier()
+    sampler.start()
+    l0 = fit.launch_count()
+    ms_per_eval = fit.time_eval(kind=1, reps=K)
+    launches = fit.launch_count() - l0
+    barrier()
+    dev_ms = max_over_ranks(ms_per_eval * K)
+    clocks = sampler.stop()
+    value = world * K / (dev_ms * 1e-3)
+
+    # ---- end to end through the public API with host buffers --------------------------------------
+    barrier()
+    t0 = time.perf_counter()
+    for s in range(K):
+        fit.set_data(X, y, ev)
+        fit.set_noise_corr(lnc)
+        f, g = fit.nlml_grad(pars[W + s])
+    torch.cuda.synchronize(device)
+    e2e_s = max_over_ranks(time.perf_counter() - t0)
+    barrier()
+    e2e_val = world * K / e2e_s
+    h2d = 8 * (X.size + y.size + ev.size + lnc.size + par0.size)
+    d2h = 8 * (1 + par0.size) + 4
+
+    line = None
+    if rank == 0:
+        stages = fit.time_stages()
+        gemm_ms = fit.bench_gemm(8192, 8192, 8192, 3)
+        achieved = flops / (ms_per_eval * 1e-3) / 1e12
+        # bounded CPU sample of the same workload (about 10-30 s of host work)
+        t0 = time.perf_counter()
+        cnt = 0
+        f_cpu = g_cpu = None
+        while cnt < 3 or (time.perf_counter() - t0 < 12.0 and cnt < 40):
+            f_cpu, g_cpu = cpu_eval(pars[W + K - 1], X, y, ev, lnc)
+            cnt += 1
+        cpu_val = cnt / (time.perf_counter() - t0)
+        parity = {"nlml_rel": abs(f - f_cpu) / abs(f_cpu),
+                  "grad_rel": float(np.max(np.abs(g - g_cpu)) / np.max(np.abs(g_cpu)))}
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": dev_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "C2: GPS3 ARD NLML+gradient, n=2000 d=20 c=1000 (BASELINE.json configs[1])",
+                       "n": int(n), "d": int(d), "hyperparameters": int(par0.size), "partition": f"independent fits x{world}",
+                       "l2": "per-evaluation working set 5 n x n FP64 matrices = 160 MB > 126 MB L2 (no flush needed)"},
+            "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                    "ms_per_step": 1e3 * e2e_s / K},
+            "gpu_launches": int(launches),
+            "clocks": clocks,
+            "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s",
+                         "frac": achieved / peak_tf if peak_tf else None, "traffic": None,
+                         "kernel": "evaluation graph (1 launch = 1 NLML+gradient evaluation, %d kernel nodes)" % (launches // max(K, 1)),
+                         "algorithmic_flops_per_launch": flops,
+                         "peak_source": "cublasDgemm 8192^3 via torch.matmul(float64), best of 5, measured in this run "
+                                        "(MEASURED_PEAKS.json has no FP64 figure)"},
+            "dmma_gemm_8192": {"tflops": 2.0 * 8192 ** 3 / (gemm_ms * 1e-3) / 1e12,
+                               "frac_of_cublas_dgemm": (2.0 * 8192 ** 3 / (gemm_ms * 1e-3) / 1e12) / peak_tf if peak_tf else None},
+            "stages_ms": {"gram": stages[0], "cholesky": stages[1], "tri_inverse": stages[2], "kinv": stages[3],
+                          "wk_grad": stages[4], "total": stages[7]},
+            "cpu_baseline": {"value": cpu_val, "unit": UNIT, "cores": cpu_threads(), "kind": "port",
+                             "sample": f"{cnt} full evaluations of the same C2 workload",
+                             "note": "reference algorithm restated in numpy (as-written op sequence); R unavailable in image"},
+            "parity_vs_oracle": parity,
+        }
+    fit.close()
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+    if line is not None:
+        print(json.dumps(line), flush=True)
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+    return run_gpu(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

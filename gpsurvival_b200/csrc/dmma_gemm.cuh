@@ -45,7 +45,14 @@ struct GemmParams {
   int klo_n;   // k >= n0          (B lower-triangular in (k,n): B[k,n] = 0 for k < n)
   int klo_m;   // k >= m0          (A upper-triangular in (m,k): A[m,k] = 0 for k < m)
   int khi_m;   // k <  m0 + BM     (A lower-triangular in (m,k): A[m,k] = 0 for k > m)
-  int ksplit;  // split-K factor (>= 1); gridDim.z = batch * ksplit
+  int ksplit;  // split-K factor (>= 1); gridDim.z = batch * nodes * ksplit
+  // "nodes": several independent sub-problems of one matrix in a single launch (the merges of
+  // one level of the triangular-inverse tree).  Node i adds i*nodeStride{A,B} to the operand
+  // pointers; its row count is clipped to the matrix edge: M_i = min(M, clip_total - i*clip_step)
+  // (nodes with M_i <= 0 exit) and, with k_eq_m, K_i = M_i.
+  int nodes;
+  long long nodeStrideA, nodeStrideB;
+  int clip_total, clip_step, k_eq_m;
 };
 
 __device__ __forceinline__ void dmma884(double& d0, double& d1, double a_mma, double b_mma) {
@@ -82,7 +89,7 @@ struct AccTile {
   double v[Cfg::FM][Cfg::FN][2];
   int m_base, n_base;      // global (tile + warp + lane) coordinates of v[0][0][0]
   int m0, n0;              // tile origin
-  int batch, split;
+  int batch, split, node;
 };
 
 template <class Cfg, bool A_KC, bool B_KC>
@@ -128,7 +135,8 @@ __device__ __forceinline__ void load_tile(double* __restrict__ s, const double* 
 // called by every thread of the CTA after the main loop (smem is free to reuse after a
 // __syncthreads()).
 template <class Cfg, bool A_KC, bool B_KC, class Epi>
-__global__ void __launch_bounds__(Cfg::NT) dmma_gemm_kernel(GemmParams p, Epi epi) {
+__global__ void __launch_bounds__(Cfg::NT) dmma_gemm_kernel(GemmParams p_in, Epi epi) {
+  GemmParams p = p_in;
   using SL = SmemLayout<Cfg, A_KC, B_KC>;
   constexpr int BM = Cfg::BM, BN = Cfg::BN, BK = Cfg::BK, STAGES = Cfg::STAGES, NT = Cfg::NT;
   constexpr int FM = Cfg::FM, FN = Cfg::FN;
@@ -142,12 +150,18 @@ __global__ void __launch_bounds__(Cfg::NT) dmma_gemm_kernel(GemmParams p, Epi ep
   const int wm0 = (warp % Cfg::WARPS_M) * Cfg::WM;
   const int wn0 = (warp / Cfg::WARPS_M) * Cfg::WN;
   const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
-  const int batch = blockIdx.z / p.ksplit, split = blockIdx.z % p.ksplit;
+  const int zz = blockIdx.z / p.ksplit, split = blockIdx.z % p.ksplit;
+  const int batch = zz / p.nodes, node = zz % p.nodes;
 
+  if (p.clip_step) {
+    p.M = min(p.M, p.clip_total - node * p.clip_step);
+    if (p.k_eq_m) p.K = p.M;
+  }
+  if (m0 >= p.M) return;
   if (p.lower && (m0 + BM - 1 + p.diag_off < n0)) return;
 
-  const double* __restrict__ A = p.A + (size_t)batch * p.strideA;
-  const double* __restrict__ B = p.B + (size_t)batch * p.strideB;
+  const double* __restrict__ A = p.A + (size_t)batch * p.strideA + (size_t)node * p.nodeStrideA;
+  const double* __restrict__ B = p.B + (size_t)batch * p.strideB + (size_t)node * p.nodeStrideB;
 
   int k_lo = 0, k_hi = p.K;
   if (p.klo_n) k_lo = max(k_lo, n0);
@@ -217,6 +231,7 @@ __global__ void __launch_bounds__(Cfg::NT) dmma_gemm_kernel(GemmParams p, Epi ep
   acc.n_base = n0 + wn0 + g;
   acc.batch = batch;
   acc.split = split;
+  acc.node = node;
   epi(p, acc, smem);
 }
 
@@ -231,12 +246,13 @@ struct EpiPlain {
   int ldc;
   long long strideC;       // per batch
   long long strideSplit;   // per split slice (0 if ksplit == 1)
+  long long nodeStrideC;   // per node (0 if nodes == 1)
   double alpha, beta;
   int lower_strict_mask;   // 1: do not write elements with row + diag_off < col (keeps upper triangle untouched)
   int diag_off;
   template <class Cfg>
   __device__ __forceinline__ void operator()(const GemmParams& p, AccTile<Cfg>& a, double*) const {
-    double* __restrict__ Cb = C + (size_t)a.batch * strideC + (size_t)a.split * strideSplit;
+    double* __restrict__ Cb = C + (size_t)a.batch * strideC + (size_t)a.split * strideSplit + (size_t)a.node * nodeStrideC;
 #pragma unroll
     for (int j = 0; j < Cfg::FN; j++) {
       int n = a.n_base + 8 * j;
@@ -391,7 +407,7 @@ cudaError_t launch_gemm(const GemmParams& p, const Epi& epi, int batch, cudaStre
     attr_set[dev & 63] = true;
   }
   if (p.M <= 0 || p.N <= 0) return cudaSuccess;
-  dim3 grid((p.M + Cfg::BM - 1) / Cfg::BM, (p.N + Cfg::BN - 1) / Cfg::BN, batch * p.ksplit);
+  dim3 grid((p.M + Cfg::BM - 1) / Cfg::BM, (p.N + Cfg::BN - 1) / Cfg::BN, batch * p.nodes * p.ksplit);
   kern<<<grid, Cfg::NT, SL::BYTES, st>>>(p, epi);
   return cudaGetLastError();
 }

@@ -194,9 +194,12 @@ template <bool A_KC, bool B_KC, class Epi>
 void gemm(H* h, const GemmParams& p, const Epi& epi) {
   long long tl = (long long)ceil_div(p.M, 128) * ceil_div(p.N, 128);
   if (p.lower) tl = tl / 2 + 1;
-  tl *= (long long)h->batch * p.ksplit;
+  tl *= (long long)h->batch * p.ksplit * p.nodes;
+  // triangular operands make the per-tile K range uneven: a single wave of big tiles is then
+  // gated by its longest tile, so ask for several waves before using the 128 x 128 config
+  const long long need = (p.klo_m || p.klo_n || p.khi_m) ? 600 : 100;
   cudaError_t e;
-  if (tl >= 100 && p.N >= 96)
+  if (tl >= need && p.N >= 96)
     e = launch_gemm<CfgLarge, A_KC, B_KC, Epi>(p, epi, h->batch, h->st);
   else
     e = launch_gemm<CfgSmall, A_KC, B_KC, Epi>(p, epi, h->batch, h->st);
@@ -209,12 +212,13 @@ GemmParams gp(const double* A, int lda, long long sA, const double* B, int ldb, 
   memset(&p, 0, sizeof p);
   p.A = A; p.B = B; p.M = M; p.N = N; p.K = K; p.lda = lda; p.ldb = ldb; p.strideA = sA; p.strideB = sB;
   p.ksplit = 1;
+  p.nodes = 1;
   return p;
 }
 
 EpiPlain plain(double* C, int ldc, long long sC, double alpha, double beta) {
   EpiPlain e;
-  e.C = C; e.ldc = ldc; e.strideC = sC; e.strideSplit = 0; e.alpha = alpha; e.beta = beta;
+  e.C = C; e.ldc = ldc; e.strideC = sC; e.strideSplit = 0; e.nodeStrideC = 0; e.alpha = alpha; e.beta = beta;
   e.lower_strict_mask = 0; e.diag_off = 0;
   return e;
 }
@@ -291,28 +295,36 @@ void potrf_range(H* h, int j0, int j1) {
   potrf_range(h, mid, j1);
 }
 
-// Recursive inverse of the lower-triangular factor: the NB leaves were inverted by
-// potf2_inv_kernel; merge  Linv21 = -Linv22 * (L21 * Linv11)  bottom-up.  Kinv is the temporary.
-void trtri_range(H* h, int j0, int j1) {
-  if (j1 - j0 <= 1) return;
-  const int ld = h->ld;
+// Inverse of the lower-triangular factor.  The NB leaves were inverted by potf2_inv_kernel;
+// merge pairs of blocks bottom-up, one LEVEL per pair of launches: at level s (block size
+// bs = NB * 2^s) node i covers rows/cols [i*2bs, (i+1)*2bs) and computes
+//   Linv21 = -Linv22 * (L21 * Linv11)
+// for its own 2x2 partition; all nodes of a level are independent and share two launches.
+// Kinv is the temporary for T = L21 * Linv11.
+void trtri_levels(H* h) {
+  const int ld = h->ld, ne = h->ne;
   const long long sM = h->strideM;
-  int mid = j0 + (j1 - j0 + 1) / 2;
-  trtri_range(h, j0, mid);
-  trtri_range(h, mid, j1);
-  int c0 = j0 * NB, r0 = mid * NB, r1 = (j1 * NB < h->ne) ? j1 * NB : h->ne;
-  int Mr = r1 - r0, Kc = r0 - c0;
-  if (Mr <= 0) return;
-  double* T = h->Kinv + r0 + (size_t)c0 * ld;
-  {  // T = L21 * Linv11   (Linv11 lower: k >= n)
-    GemmParams p = gp(h->L + r0 + (size_t)c0 * ld, ld, sM, h->Linv + c0 + (size_t)c0 * ld, ld, sM, Mr, Kc, Kc);
-    p.klo_n = 1;
-    gemm<false, true>(h, p, plain(T, ld, sM, 1.0, 0.0));
-  }
-  {  // Linv21 = -Linv22 * T   (Linv22 lower: k <= m)
-    GemmParams p = gp(h->Linv + r0 + (size_t)r0 * ld, ld, sM, T, ld, sM, Mr, Kc, Mr);
-    p.khi_m = 1;
-    gemm<false, true>(h, p, plain(h->Linv + r0 + (size_t)c0 * ld, ld, sM, -1.0, 0.0));
+  for (int bs = NB; bs < ne; bs *= 2) {
+    const int nodes = ceil_div(ne, 2 * bs);
+    const long long nstride = (long long)2 * bs * (1 + (long long)ld);
+    {  // T = L21 * Linv11   (Linv11 lower: k >= n)
+      GemmParams p = gp(h->L + bs, ld, sM, h->Linv, ld, sM, bs, bs, bs);
+      p.klo_n = 1;
+      p.nodes = nodes; p.nodeStrideA = nstride; p.nodeStrideB = nstride;
+      p.clip_total = ne - bs; p.clip_step = 2 * bs; p.k_eq_m = 0;
+      EpiPlain e = plain(h->Kinv + bs, ld, sM, 1.0, 0.0);
+      e.nodeStrideC = nstride;
+      gemm<false, true>(h, p, e);
+    }
+    {  // Linv21 = -Linv22 * T   (Linv22 lower: k <= m; K = rows of the node)
+      GemmParams p = gp(h->Linv + bs + (size_t)bs * ld, ld, sM, h->Kinv + bs, ld, sM, bs, bs, bs);
+      p.khi_m = 1;
+      p.nodes = nodes; p.nodeStrideA = nstride; p.nodeStrideB = nstride;
+      p.clip_total = ne - bs; p.clip_step = 2 * bs; p.k_eq_m = 1;
+      EpiPlain e = plain(h->Linv + bs, ld, sM, -1.0, 0.0);
+      e.nodeStrideC = nstride;
+      gemm<false, true>(h, p, e);
+    }
   }
 }
 
@@ -351,7 +363,7 @@ void enqueue_factor(H* h) {
 }
 
 void enqueue_inverse(H* h) {
-  trtri_range(h, 0, ceil_div(h->ne, NB));
+  trtri_levels(h);
   alpha_kernel<<<dim3(ceil_div(h->n, 8), h->nrhs, h->batch), 256, 0, h->st>>>(h->Linv, h->n, h->ld, h->strideM, h->zvec,
                                                                                h->ld, h->alpha);
   LAUNCHED(h);

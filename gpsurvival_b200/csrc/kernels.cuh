@@ -250,25 +250,31 @@ constexpr int LS = NB + 1;    // row stride of the 64 x 64 shared tiles (odd => 
 constexpr int LT = 33;
 constexpr size_t LEAF_SMEM = (2 * NB * LS + 32 * LT + NB) * sizeof(double);
 
+// The 32x32 warp primitives keep the working row/column in registers but stay COMPACT: the
+// outer loop over the pivot is rolled and the register window rotates (the shift is fused
+// into the FMA destination: a[c-1] = a[c] - l*lc), so indices are static without unrolling
+// 32 x 32 steps.  A fully unrolled version is ~200 KB of straight-line SASS executed once and
+// is instruction-fetch bound (measured: 20 K warp-instructions in 120 K cycles).
+
 // One warp, lane = row.  a[] = row `lane` of a 32x32 SPD block (lower part valid).  On exit
 // sL[r*LS + c] holds the factor (zeros above the diagonal), sInvD[j] = 1 / L_jj.
 // Returns the first non-positive pivot column (1-based) or 0.
 __device__ __forceinline__ int warp_potf2_32(double (&a)[32], double* sL, double* sInvD, int lane) {
   int bad = 0;
-#pragma unroll
+#pragma unroll 1
   for (int j = 0; j < 32; j++) {
-    double d = __shfl_sync(0xffffffffu, a[j], j);
+    double d = __shfl_sync(0xffffffffu, a[0], j);       // pivot: column j of row j
     if (!(d > 0.0) && bad == 0) bad = j + 1;
     double rs = rsqrt(d);
-    double lr = (lane > j) ? a[j] * rs : ((lane == j) ? d * rs : 0.0);
-    if (j + 1 < 32 && lane == j + 1) a[j + 1] -= lr * lr;   // next pivot early: keeps it off the smem round trip
+    double lr = (lane > j) ? a[0] * rs : ((lane == j) ? d * rs : 0.0);
     sL[lane * LS + j] = lr;
     if (lane == j) sInvD[j] = rs;
     __syncwarp();
+    const double* colj = sL + (j + 1) * LS + j;         // L[j+1.., j]: broadcast reads
 #pragma unroll
-    for (int c = j + 1; c < 32; c++) {
-      double lc = sL[c * LS + j];
-      if (c > j + 1 || lane != j + 1) a[c] -= lr * lc;
+    for (int c = 1; c < 32; c++) {
+      double lc = (j + c < 32) ? colj[(c - 1) * LS] : 0.0;
+      a[c - 1] = a[c] - lr * lc;                        // rank-1 update + window shift
     }
   }
   return bad;
@@ -280,15 +286,34 @@ __device__ __forceinline__ void warp_trinv_32(const double* sL, const double* sI
   double x[32];
 #pragma unroll
   for (int r = 0; r < 32; r++) x[r] = (r == lane) ? 1.0 : 0.0;
-#pragma unroll
+#pragma unroll 1
   for (int k = 0; k < 32; k++) {
-    double xk = x[k] * sInvD[k];
-    x[k] = xk;
+    double xk = x[0] * sInvD[k];
+    sX[k * LS + lane] = xk;
+    const double* colk = sL + (k + 1) * LS + k;
 #pragma unroll
-    for (int r = k + 1; r < 32; r++) x[r] -= sL[r * LS + k] * xk;
+    for (int r = 1; r < 32; r++) {
+      double lv = (k + r < 32) ? colk[(r - 1) * LS] : 0.0;
+      x[r - 1] = x[r] - lv * xk;
+    }
   }
+}
+
+// One warp, lane = row of a 32x32 block B: B <- B * L^-T (L lower 32x32 in sL) by forward
+// substitution; result written to sOut[lane*LS + j].
+__device__ __forceinline__ void warp_trsm_32(double (&a)[32], const double* sL, const double* sInvD, double* sOut,
+                                             int lane) {
+#pragma unroll 1
+  for (int j = 0; j < 32; j++) {
+    double x = a[0] * sInvD[j];
+    sOut[lane * LS + j] = x;
+    const double* colj = sL + (j + 1) * LS + j;
 #pragma unroll
-  for (int r = 0; r < 32; r++) sX[r * LS + lane] = x[r];
+    for (int c = 1; c < 32; c++) {
+      double lc = (j + c < 32) ? colj[(c - 1) * LS] : 0.0;
+      a[c - 1] = a[c] - x * lc;
+    }
+  }
 }
 
 __global__ void __launch_bounds__(256) potf2_inv_kernel(const double* __restrict__ A, double* __restrict__ L,
@@ -323,15 +348,7 @@ __global__ void __launch_bounds__(256) potf2_inv_kernel(const double* __restrict
     double a[32];
 #pragma unroll
     for (int c = 0; c < 32; c++) a[c] = S[(32 + lane) * LS + c];
-#pragma unroll
-    for (int j = 0; j < 32; j++) {
-      double x = a[j] * invd[j];
-      a[j] = x;
-#pragma unroll
-      for (int c = j + 1; c < 32; c++) a[c] -= x * S[c * LS + j];
-    }
-#pragma unroll
-    for (int c = 0; c < 32; c++) S[(32 + lane) * LS + c] = a[c];
+    warp_trsm_32(a, S, invd, S + 32 * LS, lane);
   } else if (warp == 0) {
     warp_trinv_32(S, invd, X, lane);      // X11 = L11^-1
   }
@@ -340,7 +357,7 @@ __global__ void __launch_bounds__(256) potf2_inv_kernel(const double* __restrict
     double xr[32];
 #pragma unroll
     for (int k = 0; k < 32; k++) xr[k] = S[(32 + lane) * LS + k];
-#pragma unroll
+#pragma unroll 1
     for (int cc = 0; cc < 8; cc++) {
       int c = warp * 8 + cc;
       double acc = S[(32 + lane) * LS + 32 + c];
@@ -364,7 +381,7 @@ __global__ void __launch_bounds__(256) potf2_inv_kernel(const double* __restrict
     double xr[32];
 #pragma unroll
     for (int k = 0; k < 32; k++) xr[k] = S[(32 + lane) * LS + k];
-#pragma unroll
+#pragma unroll 1
     for (int cc = 0; cc < 4; cc++) {
       int c = warp * 4 + cc;
       double acc = 0.0;
@@ -378,7 +395,7 @@ __global__ void __launch_bounds__(256) potf2_inv_kernel(const double* __restrict
     double xr[32];
 #pragma unroll
     for (int k = 0; k < 32; k++) xr[k] = X[(32 + lane) * LS + 32 + k];
-#pragma unroll
+#pragma unroll 1
     for (int cc = 0; cc < 4; cc++) {
       int c = warp * 4 + cc;
       double acc = 0.0;

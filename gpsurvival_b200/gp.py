@@ -358,7 +358,7 @@ def GPRegression(logHyp, parameterStructure, trainingTestStructure, logHypNoiseC
            "K": fin.get("K"), "L": fin.get("L"), "optim": opt, "_par": vec.copy()}
     if noiseCorr in ("noiseCorrVec", "noiseCorrLearned"):                                # :76-81
         lnc = np.asarray(lnc, dtype=np.float64).ravel()
-        if lnc[0] == -np.inf:
+        if lnc.size and lnc[0] == -np.inf:
             lnc = np.array([-1e10])
         out["logHypNoiseCorrection"] = lnc
     return out

@@ -283,7 +283,7 @@ def regress_finalize(par, X, y, events, cov_form="SqExp", mean_form="Zero", nois
            "logHypChosen": log_hyp_chosen, "logMarLik": log_mar_lik}
     if _has_corr(noise_corr):                                                # :76-81
         lnc = np.asarray(lnc, dtype=np.float64).ravel()
-        if lnc[0] == -np.inf:      # length-c condition: R < 4.2 tests the first element only
+        if lnc.size and lnc[0] == -np.inf:      # length-c condition: R < 4.2 tests the first element only
             lnc = np.array([-1e10])
         out["logHypNoiseCorrection"] = lnc
     return out

@@ -1,0 +1,39 @@
+#-------------------------------------------------------------------------------------------------#
+# gpsurv_session.R — device-resident state behind the reference's stateless signatures.
+# NOT RUN IN THE BUILD IMAGE (no R there — SURVEY.md F1); logic mirrors gpsurvival_b200/gp.py
+# (_Session.bind), which is what the test-suite exercises.
+#
+# optim() calls ForOptimisationLog / OptimisationGradientLog thousands of times with the same
+# trainingData; the session uploads X only when it changes, targets / noise correction when
+# they change, and lets the library reuse fn's factorisation for gr.
+#-------------------------------------------------------------------------------------------------#
+.gps <- new.env()
+.gps$handle <- NULL
+.gps$ardMode <- 0L      # 0 = intended (per-dimension scaling), 1 = as written (recycled, CovFunc.R:25,27)
+
+GpsCovCode  <- function(covFuncForm) switch(covFuncForm, 'SqExp' = 0L, 'ARD' = 1L,
+                 stop(paste0("covFuncForm '", covFuncForm, "' is not built in libgpsurv (SqExp, ARD)")))
+GpsMeanCode <- function(meanFuncForm) switch(meanFuncForm, 'Zero' = 0L, 'Linear' = 1L)
+GpsNcCode   <- function(noiseCorr) if(identical(noiseCorr, 'noiseCorrLearned')) 1L else if(identical(noiseCorr, 'noiseCorrVec')) 2L else 0L
+
+GpsBind <- function(trainingData, trainingTargets, trainingEvents, covFuncForm, meanFuncForm, noiseCorr, logHypNoiseCorrection){
+  if(is.null(.gps$handle)) .gps$handle <- .Call('gps_r_create', 0L)
+  opts <- c(GpsCovCode(covFuncForm), GpsMeanCode(meanFuncForm), GpsNcCode(noiseCorr), .gps$ardMode)
+  if(!identical(opts, .gps$opts)){
+    .Call('gps_r_set_options', .gps$handle, opts[1], opts[2], opts[3], opts[4]); .gps$opts <- opts
+  }
+  X <- as.matrix(trainingData); storage.mode(X) <- 'double'
+  y <- as.double(trainingTargets)
+  e <- if(is.null(trainingEvents)) rep(1, nrow(X)) else as.double(trainingEvents)
+  if(!identical(X, .gps$X) || !identical(e, .gps$events)){
+    .Call('gps_r_set_data', .gps$handle, X, y, e); .gps$X <- X; .gps$y <- y; .gps$events <- e; .gps$lnc <- NULL
+  } else if(!identical(y, .gps$y)){
+    .Call('gps_r_set_targets', .gps$handle, y); .gps$y <- y
+  }
+  if(opts[3] == 2L){
+    v <- as.double(logHypNoiseCorrection)
+    if(length(v) == 1 && sum(e == 0) != 1) v <- rep(v, sum(e == 0))   # R recycling of a scalar (ForOptimisationLog.R:38)
+    if(!identical(v, .gps$lnc)){ .Call('gps_r_set_noise_corr', .gps$handle, v); .gps$lnc <- v }
+  }
+  .gps$handle
+}

@@ -19,10 +19,6 @@ def covcase(n1, n2, d, ks):
     print("   row-max by 8:", np.array2string(E.max(axis=1)[:n1//8*8].reshape(-1, 8).max(axis=1), precision=1), flush=True)
     fit.close()
 
-for (n1, n2, d, ks) in [(64,200,700,1),(64,200,700,5),(64,200,700,2),(64,64,700,5),(128,200,700,5),(72,200,704,5),(200,64,700,5)]:
-    covcase(n1, n2, d, ks)
-os.environ.pop("GPS_KSPLIT")
-
 # first performance numbers
 fit = gp.Fit(0)
 for (M, N, K) in [(4096,4096,4096),(8192,8192,8192),(16384,16384,256),(2048,2048,2048)]:

@@ -1,0 +1,353 @@
+"""GPU parity tests (B200): the CUDA path, called through the C ABI / the reference-named host
+mirror, against (a) the committed mpmath golden fixtures, (b) the numpy oracle on seeded inputs
+at sizes it finishes in seconds, (c) size-independent properties at BASELINE.json's full sizes.
+
+Tolerances are north_star's: NLML and gradients 1e-9 relative, predictions 1e-8."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+from gpsurvival_b200 import gp, synth, _lib          # noqa: E402
+from oracle import gp_oracle as orc                  # noqa: E402
+
+GOLD = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "golden_small.json")))
+TOL_NLML = 1e-9
+TOL_GRAD = 1e-9
+TOL_PRED = 1e-8
+
+
+def relmax(a, b):
+    a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
+    return float(np.max(np.abs(a - b)) / max(float(np.max(np.abs(b))), 1e-300))
+
+
+@pytest.fixture(scope="module")
+def fit0():
+    f = gp.Fit(0)
+    yield f
+    f.close()
+
+
+def _make_fit(X, y, ev, cov_form, mean_form, noise_corr, lnc=None, ard_mode="intended"):
+    fit = gp.Fit(0)
+    fit.set_options(cov_form, mean_form, noise_corr, ard_mode)
+    fit.set_data(X, y, ev)
+    if noise_corr == "noiseCorrVec":
+        fit.set_noise_corr(lnc)
+    return fit
+
+
+# ---- golden fixtures (mpmath, 50 digits) -------------------------------------------------------
+@pytest.mark.parametrize("c", GOLD["cases"], ids=[c["name"] for c in GOLD["cases"]])
+def test_golden_fixture(c):
+    X, y, ev = np.array(c["X"]), np.array(c["y"]), np.array(c["events"])
+    par = np.array(c["par"])
+    fit = _make_fit(X, y, ev, c["cov_form"], c["mean_form"], c["noise_corr"], c["log_sc2_vec"])
+    assert abs(fit.nlml(par) - c["nlml"]) <= TOL_NLML * abs(c["nlml"])
+    f, g = fit.nlml_grad(par)
+    assert abs(f - c["nlml"]) <= TOL_NLML * abs(c["nlml"])
+    assert relmax(g, c["grad"]) <= TOL_GRAD
+    mu, vf, vd = fit.predict(par, np.array(c["Xstar"]))
+    assert relmax(mu, c["pred_mean"]) <= TOL_PRED
+    sf2 = float(np.exp(par[1]))
+    assert np.max(np.abs(vf - np.array(c["pred_varf"]))) <= TOL_PRED * sf2
+    assert np.max(np.abs(vd - np.array(c["pred_vard"]))) <= TOL_PRED * sf2
+    fit.close()
+
+
+# ---- CovFunc ---------------------------------------------------------------------------------
+@pytest.mark.parametrize("n1,n2,d", [(100, 0, 1), (301, 0, 20), (285, 0, 3000), (130, 77, 5), (64, 200, 700),
+                                     (1, 1, 3), (2, 0, 1)])
+@pytest.mark.parametrize("cov_form", ["SqExp", "ARD"])
+@pytest.mark.parametrize("ard_mode", ["intended", "as_written"])
+def test_cov_matches_oracle(fit0, n1, n2, d, cov_form, ard_mode):
+    rng = np.random.default_rng(n1 * 7 + d)
+    x1 = rng.standard_normal((n1, d))
+    x2 = None if n2 == 0 else rng.standard_normal((n2, d))
+    ell = np.array([1.7 * np.sqrt(d)]) if cov_form == "SqExp" else 1.7 * np.sqrt(d) * (1 + 0.3 * rng.random(d))
+    K = fit0.cov(x1, x2, 0.8, ell, cov_form, ard_mode)
+    Ko = orc.cov_func(x1, x1 if x2 is None else x2, 0.8, ell, cov_form, ard_mode)
+    assert np.max(np.abs(K - Ko)) <= 1e-12
+    if x2 is None:
+        assert np.array_equal(K, K.T) and np.all(np.diag(K) == 0.8)      # exact symmetry and diagonal
+
+
+def test_cov_reference_named_entry_point():
+    rng = np.random.default_rng(5)
+    x = rng.standard_normal((50, 3))
+    xs = rng.standard_normal((20, 3))
+    K = gp.CovFunc(x, x, x, None, None, 0.5, 1.3, "SqExp")
+    Ks = gp.CovFunc(x, xs, x, None, None, 0.5, 1.3, "SqExp")
+    assert np.max(np.abs(K - orc.cov_func(x, x, 0.5, [1.3]))) <= 1e-12
+    assert np.max(np.abs(Ks - orc.cov_func(x, xs, 0.5, [1.3]))) <= 1e-12
+    with pytest.raises(gp.GpsError):
+        gp.CovFunc(x, x, x, None, 3, 0.5, 1.3, "Matern")
+
+
+# ---- NLML / gradient / finalize / predict against the oracle -----------------------------------
+CASES = [
+    # name, n, m, d, c, cov, mean, noise_corr, seed
+    ("C1 SqExp GPS1", 100, 50, 1, 40, "SqExp", "Zero", False, 11),
+    ("SqExp GPS2 odd n", 257, 40, 4, 100, "SqExp", "Zero", "noiseCorrLearned", 12),
+    ("C2-shaped ARD GPS3 n=300", 300, 64, 20, 150, "ARD", "Zero", "noiseCorrVec", 13),
+    ("ARD Linear GPS2", 201, 33, 6, 90, "ARD", "Linear", "noiseCorrLearned", 14),
+    ("SqExp Linear GPS1", 150, 20, 3, 60, "SqExp", "Linear", False, 15),
+    ("C3-shaped ARD GPS3 d=1500", 285, 57, 1500, 142, "ARD", "Zero", "noiseCorrVec", 16),
+    ("ARD GPS3 n=700", 700, 120, 20, 350, "ARD", "Zero", "noiseCorrVec", 17),
+    ("tiny n=3", 3, 2, 2, 1, "ARD", "Zero", "noiseCorrVec", 18),
+    ("one leaf n=64", 64, 5, 2, 20, "SqExp", "Zero", False, 19),
+    ("n=65", 65, 5, 2, 20, "SqExp", "Zero", "noiseCorrLearned", 20),
+    ("no censored rows GPS3", 90, 9, 3, 0, "ARD", "Zero", "noiseCorrVec", 21),
+]
+
+
+@pytest.mark.parametrize("case", CASES, ids=[c[0] for c in CASES])
+def test_eval_matches_oracle(case):
+    name, n, m, d, c, cov_form, mean_form, noise_corr, seed = case
+    pb = synth.make_problem(n, m, d, c, seed)
+    X, y, ev, Xs = pb["trainingData"], np.log(pb["trainingTargets"]), pb["events"], pb["testData"]
+    rng = np.random.default_rng(seed)
+    p = d if cov_form == "ARD" else 1
+    par = [np.log(0.2), np.log(0.8)] + list(np.log(1.7 * np.sqrt(d)) + 0.2 * rng.standard_normal(p))
+    if mean_form == "Linear":
+        par += list(0.1 * rng.standard_normal(d + 1))
+    lnc = None
+    if noise_corr == "noiseCorrLearned":
+        par += [np.log(0.3)]
+    if noise_corr == "noiseCorrVec":
+        lnc = np.log(0.2) + 0.5 * rng.standard_normal(int(np.sum(ev == 0)))
+    par = np.array(par)
+    kw = dict(cov_form=cov_form, mean_form=mean_form, noise_corr=noise_corr, log_hyp_noise_corr=lnc)
+    fit = _make_fit(X, y, ev, cov_form, mean_form, noise_corr, lnc)
+    f_o = orc.nlml(par, X, y, ev, **kw)
+    g_o = orc.nlml_grad(par, X, y, ev, **kw)
+    for _ in range(3):                       # direct launch, graph capture, graph replay
+        assert abs(fit.nlml(par) - f_o) <= TOL_NLML * abs(f_o)
+    for _ in range(3):                       # cached factorisation, then graphs
+        f, g = fit.nlml_grad(par)
+        assert abs(f - f_o) <= TOL_NLML * abs(f_o)
+        assert relmax(g, g_o) <= TOL_GRAD
+    f2, g2 = fit.nlml_grad(par + 0.01)       # uncached
+    assert relmax(g2, orc.nlml_grad(par + 0.01, X, y, ev, **kw)) <= TOL_GRAD
+    fin = fit.finalize(par, want_K=True, want_L=True)
+    reg = orc.regress_finalize(par, X, y, ev, cov_form, mean_form, noise_corr, lnc)
+    assert np.max(np.abs(fin["K"] - reg["K"])) <= 1e-12
+    assert relmax(fin["L"], reg["L"]) <= 1e-9
+    assert relmax(fin["alpha"], reg["alpha"]) <= TOL_PRED
+    assert relmax(fin["meanTraining"], reg["meanTraining"]) <= 1e-12 or np.all(reg["meanTraining"] == 0)
+    assert abs(fin["logMarLik"] - reg["logMarLik"]) <= TOL_NLML * abs(reg["logMarLik"])
+    assert np.array_equal(np.triu(fin["L"], 1), np.zeros_like(fin["L"]))
+    mu, vf, vd = fit.predict(par, Xs)
+    reg["logHypChosen"] = {"noise": par[0], "func": par[1], "length": par[2:2 + p],
+                           "mean": par[2 + p:2 + p + d + 1] if mean_form == "Linear" else np.zeros(d + 1)}
+    pr = orc.predict(reg, X, y, ev, Xs, cov_form, mean_form, noise_corr,
+                     par[-1:] if noise_corr == "noiseCorrLearned" else lnc)
+    assert relmax(mu, pr["funcMeanPred"]) <= TOL_PRED
+    assert np.max(np.abs(vf - pr["varFunction"])) <= TOL_PRED * 0.8
+    assert np.max(np.abs(vd - pr["varData"])) <= TOL_PRED * 0.8
+    fit.close()
+
+
+def test_as_written_ard_nlml_matches_oracle():
+    pb = synth.make_problem(120, 10, 7, 50, 33)
+    X, y, ev = pb["trainingData"], np.log(pb["trainingTargets"]), pb["events"]
+    par = np.concatenate([[np.log(0.2), np.log(0.8)], np.log(1.7 * np.sqrt(7)) + 0.1 * np.arange(7)])
+    fit = _make_fit(X, y, ev, "ARD", "Zero", False, ard_mode="as_written")
+    f_o = orc.nlml(par, X, y, ev, cov_form="ARD", ard_mode="as_written")
+    assert abs(fit.nlml(par) - f_o) <= TOL_NLML * abs(f_o)
+    with pytest.raises(gp.GpsError) as e:
+        fit.nlml_grad(par)
+    assert e.value.code == _lib.GPS_ERR_UNSUPPORTED
+    fit.close()
+
+
+# ---- reference-named stateless entry points ------------------------------------------------------
+def test_for_optimisation_log_signature_and_caching():
+    pb = synth.make_problem(80, 10, 2, 30, 5)
+    X, y, ev = pb["trainingData"], np.log(pb["trainingTargets"]), pb["events"]
+    par = np.log([0.2, 0.8, 2.0])
+    args = (X, y, ev, "Zero", 2, None, "SqExp", 80, False, None, False)
+    v = gp.ForOptimisationLog(par, *args)
+    assert v.shape == (1, 1) and abs(v[0, 0] - orc.nlml(par, X, y, ev)) <= TOL_NLML * abs(v[0, 0])
+    g = gp.OptimisationGradientLog(par, *args)
+    assert g.shape == (3, 1) and relmax(g.ravel(), orc.nlml_grad(par, X, y, ev)) <= TOL_GRAD
+    y2 = y + 0.1                                     # new targets: same X stays resident
+    v2 = gp.ForOptimisationLog(par, X, y2, ev, "Zero", 2, None, "SqExp", 80, False, None, False)
+    assert abs(v2[0, 0] - orc.nlml(par, X, y2, ev)) <= TOL_NLML * abs(v2[0, 0])
+    with pytest.raises(gp.GpsError):
+        gp.ForOptimisationLog(par, X, y, ev, "Zero", 2, None, "SqExp", 80, False, None, True)   # imposePriors
+
+
+# ---- Adjust ----------------------------------------------------------------------------------
+def test_adjust_matches_oracle_and_fixture(fit0):
+    rng = np.random.default_rng(3)
+    c = 20000
+    mu = rng.standard_normal(c)
+    s = 0.05 + rng.random(c)
+    alpha = rng.uniform(-8, 7.5, c)
+    a = mu + alpha * s
+    em, ev = fit0.adjust(a, mu, s)
+    eo, vo = orc.adjust(a, mu, s)
+    al = (a - mu) / s
+    lo = al < 5.0                                    # parity bar 1e-8 where 1 - Phi is well conditioned
+    assert np.max(np.abs(em[lo] - eo[lo]) / np.maximum(np.abs(eo[lo]), 1.0)) <= 1e-8
+    assert np.max(np.abs(ev[lo] - vo[lo]) / np.maximum(np.abs(vo[lo]), 1e-3)) <= 1e-8
+    mid = (al >= 5.0) & (al < 6.5)                    # reported separately
+    assert np.max(np.abs(em[mid] - eo[mid]) / np.maximum(np.abs(eo[mid]), 1.0)) <= 1e-5
+    assert np.mean((ev == 0) != (vo == 0)) <= 0.002   # the hard (a, 0) branch may flip within 1 ulp of 1e-12
+    assert np.all(em >= a - 1e-9 * np.maximum(1.0, np.abs(a)))
+    rows = GOLD["adjust"]
+    em, ev = fit0.adjust([r["a"] for r in rows], [r["mu"] for r in rows], [r["s"] for r in rows])
+    for r, m_, v_ in zip(rows, em, ev):
+        if r["alpha"] < 5:
+            assert abs(m_ - r["as_written_mean"]) <= 1e-8 * max(1.0, abs(r["as_written_mean"]))
+            assert abs(v_ - r["as_written_var"]) <= 1e-8 * max(1e-3, abs(r["as_written_var"]))
+    out = gp.AdjustTrainingSurvivalMeanVariance(0.5, 0.0, 1.0)
+    assert set(out) == {"mu", "sigma"} and abs(out["mu"] - orc.adjust_one(0.5, 0.0, 1.0)[0]) < 1e-12
+    assert fit0.adjust([], [], [])[0].size == 0       # empty input
+
+
+# ---- whole fits: GPS loop trajectory ---------------------------------------------------------------
+@pytest.mark.parametrize("model,nc", [("GPS1", False), ("GPS2", "noiseCorrLearned"), ("GPS3", "noiseCorrVec"),
+                                      ("GPR", None)])
+def test_apply_gp_c1_matches_oracle(model, nc):
+    cfg = synth.CONFIGS["C1"]
+    pb = synth.make_config_problem(cfg)
+    params = dict(modelType="survival" if nc is not None else "non-survival", noiseCorr=nc if nc is not None else False,
+                  optimType="Nelder-Mead", maxit=300, maxitSurvival=10, meanFuncForm="Zero", covFuncForm="SqExp",
+                  tolerance=1e-5 * 100 * 0.4, maxCount=20, logHypStart=synth.start_log_hyp(1, "SqExp"),
+                  burnIn=False, imposePriors=False)
+    tts = pb
+    if nc is None:                                    # RemoveCensored (runSyntheticExp1.R:195)
+        keep = pb["events"] == 1
+        tts = dict(pb, trainingData=pb["trainingData"][keep], trainingTargets=pb["trainingTargets"][keep],
+                   events=pb["events"][keep])
+    r = gp.ApplyGP(tts, {"dataSource": "Generate"}, params)
+    ro = orc.apply_gp(tts, params)
+    if "count" in ro:
+        assert r["count"] == ro["count"]
+    # whole-fit agreement is a secondary, looser check (simplex comparisons are 1-ulp sensitive)
+    assert relmax(r["funcMeanPred"].ravel(), ro["funcMeanPred"]) <= 1e-6
+    assert relmax(r["varData"], ro["varData"]) <= 1e-6
+    assert abs(r["objective"] - ro["objective"]) <= 1e-6 * abs(ro["objective"])
+
+
+def test_gp_regression_bfgs_ard():
+    pb = synth.make_problem(150, 20, 4, 60, 8)
+    y = np.log(pb["trainingTargets"])
+    params = dict(modelType="survival", noiseCorr="noiseCorrVec", optimType="BFGS", maxit=50, maxitSurvival=8,
+                  meanFuncForm="Zero", covFuncForm="ARD", imposePriors=False)
+    lh = synth.start_log_hyp(4, "ARD")
+    lnc = np.full(int(np.sum(pb["events"] == 0)), lh["noise"])
+    data = {"trainingData": pb["trainingData"], "trainingTargets": y, "events": pb["events"]}
+    reg = gp.GPRegression(lh, params, data, lnc, want_matrices=True)
+    rego = orc.gp_regression(lh, params, data, lnc)
+    assert abs(reg["objective"] - rego["objective"]) <= 1e-7 * abs(rego["objective"])
+    assert relmax(reg["alpha"].ravel(), rego["alpha"]) <= 1e-5
+    assert reg["objective"] < orc.nlml(orc.flatten_log_hyp(lh, 4, "Zero", "noiseCorrVec", lnc), pb["trainingData"], y,
+                                       pb["events"], cov_form="ARD", noise_corr="noiseCorrVec", log_hyp_noise_corr=lnc)
+    assert set(("logHyp", "meanTraining", "K", "L", "alpha", "logHypChosen", "logMarLik", "objective",
+                "logHypNoiseCorrection")) <= set(reg)
+
+
+# ---- batches -------------------------------------------------------------------------------------
+def test_batched_fits_equal_single_fits():
+    B, n, m, d = 5, 90, 12, 6
+    pbs = [synth.make_problem(n, m, d, 40, 100 + b) for b in range(B)]
+    # the number of censored rows must be equal across a batch for GPS3; use GPS2 here
+    X = np.stack([p["trainingData"] for p in pbs])
+    y = np.stack([np.log(p["trainingTargets"]) for p in pbs])
+    ev = np.stack([p["events"] for p in pbs])
+    Xs = np.stack([p["testData"] for p in pbs])
+    rng = np.random.default_rng(0)
+    par = np.tile(np.concatenate([[np.log(0.2), np.log(0.8)], np.full(d, np.log(1.7 * np.sqrt(d))), [np.log(0.3)]]),
+                  (B, 1)) + 0.2 * rng.standard_normal((B, d + 3))
+    bf = gp.Fit(0, batch=B)
+    bf.set_options("ARD", "Zero", "noiseCorrLearned", "intended")
+    bf.set_data(X, y, ev)
+    f, g = bf.nlml_grad(par)
+    f_again, g_again = bf.nlml_grad(par + 0.0)
+    assert np.array_equal(f, f_again) and np.array_equal(g, g_again)       # run-to-run reproducible
+    mu, vf, vd = bf.predict(par, Xs)
+    for b in range(B):
+        kw = dict(cov_form="ARD", noise_corr="noiseCorrLearned")
+        fo = orc.nlml(par[b], X[b], y[b], ev[b], **kw)
+        assert abs(f[b] - fo) <= TOL_NLML * abs(fo)
+        assert relmax(g[b], orc.nlml_grad(par[b], X[b], y[b], ev[b], **kw)) <= TOL_GRAD
+        reg = orc.regress_finalize(par[b], X[b], y[b], ev[b], "ARD", "Zero", "noiseCorrLearned")
+        reg["logHypChosen"] = {"noise": par[b, 0], "func": par[b, 1], "length": par[b, 2:2 + d], "mean": np.zeros(d + 1)}
+        pr = orc.predict(reg, X[b], y[b], ev[b], Xs[b], "ARD", "Zero", "noiseCorrLearned", par[b, -1:])
+        assert relmax(mu[b], pr["funcMeanPred"]) <= TOL_PRED
+        assert np.max(np.abs(vd[b] - pr["varData"])) <= TOL_PRED
+    bf.close()
+
+
+# ---- error behaviour -------------------------------------------------------------------------------
+def test_error_paths():
+    pb = synth.make_problem(40, 5, 2, 10, 1)
+    X, y, ev = pb["trainingData"], np.log(pb["trainingTargets"]), pb["events"]
+    fit = gp.Fit(0)
+    with pytest.raises(gp.GpsError) as e:
+        fit.nlml(np.zeros(3))                          # no data yet
+    assert e.value.code == _lib.GPS_ERR_STATE
+    fit.set_data(X, y, ev)
+    with pytest.raises(gp.GpsError) as e:
+        fit.nlml(np.zeros(5))                          # wrong length
+    assert e.value.code == _lib.GPS_ERR_ARG
+    with pytest.raises(gp.GpsError) as e:
+        fit.nlml(np.array([0.0, np.nan, 0.0]))
+    assert e.value.code == _lib.GPS_ERR_ARG
+    with pytest.raises(gp.GpsError):
+        fit.set_options("Matern")
+    # duplicate rows + vanishing noise => numerically singular Ky => NOT_PD with a pivot index
+    Xd = np.vstack([X, X])
+    fit.set_data(Xd, np.concatenate([y, y]), np.concatenate([ev, ev]))
+    with pytest.raises(gp.NotPositiveDefinite) as e:
+        fit.nlml(np.array([-800.0, 0.0, 0.0]))
+    assert e.value.code == _lib.GPS_ERR_NOT_PD and 1 <= e.value.pivot <= 80
+    assert abs(fit.nlml(np.log([0.2, 0.8, 2.0])) - orc.nlml(np.log([0.2, 0.8, 2.0]), Xd, np.concatenate([y, y]),
+                                                             np.concatenate([ev, ev]))) < 1e-7   # handle still usable
+    fit.set_options("SqExp", "Zero", "noiseCorrVec")
+    with pytest.raises(gp.GpsError):
+        fit.set_noise_corr(np.zeros(3))                # wrong number of censored rows
+    fit.close()
+
+
+# ---- size-independent properties at BASELINE.json's full sizes ---------------------------------------
+@pytest.mark.parametrize("name", ["C2", "C3"])
+def test_full_size_properties(name):
+    cfg = synth.CONFIGS[name]
+    pb = synth.make_config_problem(cfg)
+    X, y, ev, Xs = pb["trainingData"], np.log(pb["trainingTargets"]), pb["events"], pb["testData"]
+    n, d = X.shape
+    lnc = np.full(int(np.sum(ev == 0)), np.log(0.2))
+    fit = _make_fit(X, y, ev, cfg.cov_form, "Zero", cfg.noise_corr, lnc)
+    par = synth.start_par(cfg, d=d)
+    f, g = fit.nlml_grad(par)
+    fin = fit.finalize(par, want_K=True, want_L=True)
+    K, L, alpha = fin["K"], fin["L"], fin["alpha"]
+    noise = np.full(n, 0.2)
+    noise[ev == 0] += np.exp(lnc)
+    Ky = K + np.diag(noise)
+    assert np.max(np.abs(L @ L.T - Ky)) <= 1e-12 * n                   # L L' = Ky
+    assert np.max(np.abs(Ky @ alpha - y)) <= 1e-9 * np.max(np.abs(y)) * n   # Ky alpha = y
+    assert abs(-fin["logMarLik"] - f) <= 1e-12 * abs(f)
+    logdet = 2 * np.sum(np.log(np.diag(L)))
+    assert abs(f - (0.5 * y @ alpha + 0.5 * logdet + 0.5 * n * np.log(2 * np.pi))) <= 1e-10 * abs(f)
+    # directional derivative of the GPU NLML along a random direction vs the analytic gradient
+    rng = np.random.default_rng(0)
+    v = rng.standard_normal(par.size)
+    v /= np.linalg.norm(v)
+    h = 1e-4
+    fd = (fit.nlml(par + h * v) - fit.nlml(par - h * v)) / (2 * h)
+    assert abs(fd - g @ v) <= 1e-6 * max(1.0, abs(g @ v))
+    mu, vf, vd = fit.predict(par, Xs)
+    assert np.all(vf >= -1e-9) and np.all(vf <= 0.8 + 1e-9) and np.allclose(vd - vf, 0.2, atol=1e-12)
+    # against the oracle's K-space formulas evaluated from the GPU's own K (cheap at any size)
+    Ks = gp.CovFunc(X, Xs, X, None, None, 0.8, np.exp(par[2:2 + d]), cfg.cov_form)
+    assert relmax(mu, Ks.T @ alpha) <= TOL_PRED
+    fit.close()

@@ -1,0 +1,79 @@
+"""CPU tests of the boundary: the C-ABI library builds, loads and exports every symbol that
+include/gpsurv.h declares; without a GPU it fails loudly instead of falling back; the product
+package never imports the oracle."""
+import ast
+import ctypes as C
+import os
+import re
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared_symbols():
+    src = open(os.path.join(ROOT, "include", "gpsurv.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(gps_[a-z_0-9]+)\s*\(", src)))
+
+
+def test_header_symbols_all_exported(lib):
+    from gpsurvival_b200 import _lib
+    names = _declared_symbols()
+    assert len(names) >= 20
+    for name in names:
+        assert hasattr(lib, name), f"{name} declared in gpsurv.h but not exported by libgpsurv.so"
+        assert name in _lib.PROTOTYPES, f"{name} has no ctypes prototype"
+    assert sorted(_lib.PROTOTYPES) == names
+
+
+def test_version_and_loud_failure_without_gpu(lib):
+    assert b"sm_100a" in lib.gps_version()
+    import torch
+    if torch.cuda.is_available():
+        return
+    h = C.c_void_p()
+    rc = lib.gps_create(0, C.byref(h))
+    assert rc == 2 and not h                       # GPS_ERR_CUDA, no handle, no CPU fallback
+    assert b"no CPU fallback" in lib.gps_last_error(None)
+    from gpsurvival_b200 import gp
+    import pytest
+    with pytest.raises(gp.GpsError):
+        gp.ForOptimisationLog(np.zeros(3), np.zeros((4, 1)), np.zeros(4), np.ones(4), "Zero", 1, None, "SqExp", 4,
+                              False, None, False)
+
+
+def test_null_handle_is_an_argument_error(lib):
+    assert lib.gps_nlml(None, None, 0, None) == 1
+    assert lib.gps_destroy(None) == 0
+    assert lib.gps_launch_count(None) == 0
+
+
+def test_product_never_imports_oracle():
+    pkg = os.path.join(ROOT, "gpsurvival_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith(".py"):
+                tree = ast.parse(open(os.path.join(dirpath, f)).read())
+                for node in ast.walk(tree):
+                    mods = []
+                    if isinstance(node, ast.Import):
+                        mods = [a.name for a in node.names]
+                    elif isinstance(node, ast.ImportFrom):
+                        mods = [node.module or ""]
+                    assert not any(m.split(".")[0] == "oracle" for m in mods), f"{f} imports the oracle"
+            if f.endswith((".cu", ".cuh", ".h")):
+                assert "oracle" not in open(os.path.join(dirpath, f)).read()
+
+
+def test_host_logic_flatten_and_options():
+    from gpsurvival_b200 import gp, synth
+    lh = synth.start_log_hyp(3, "ARD")
+    assert gp._flatten(lh, 3, "Zero", False, None).size == 5
+    assert gp._flatten(lh, 3, "Linear", False, None).size == 9
+    assert gp._flatten(lh, 3, "Zero", "noiseCorrLearned", [0.1]).size == 6
+    cfg = synth.CONFIGS["C2"]
+    assert cfg.n_hyp == 22 and synth.start_par(cfg).size == 22
+    pb = synth.make_config_problem(cfg, scale=0.05)
+    assert pb["trainingData"].shape == (100, 20) and int(np.sum(pb["events"] == 0)) == 50
+    assert abs(pb["trainingData"].mean()) < 1e-12 and np.allclose(pb["trainingData"].std(axis=0, ddof=1), 1.0)

@@ -155,10 +155,10 @@ def test_cody_pnorm_and_dnorm_accuracy():
     for x in np.linspace(-37, 8.2, 1500):
         ref = float(mp.erfc(-mp.mpf(float(x)) / mp.sqrt(2)) / 2)
         # exp() of a large argument amplifies its own rounding in the far tail
-        assert abs(orc.pnorm_std(float(x)) - ref) <= (4e-16 if abs(x) < 6 else 1e-13) * ref
-    for x in np.linspace(-38, 38, 1500):
+        assert abs(orc.pnorm_std(float(x)) - ref) <= (1e-15 if abs(x) < 6 else 1e-13) * ref
+    for x in np.linspace(-37, 37, 1500):           # beyond |x| ~ 37.5 the density is denormal
         ref = float(mp.npdf(mp.mpf(float(x))))
-        assert abs(orc.dnorm_std(float(x)) - ref) <= 5e-15 * ref
+        assert abs(orc.dnorm_std(float(x)) - ref) <= (1e-15 if abs(x) < 6 else 1e-13) * ref
     assert orc.pnorm_std(0.0) == 0.5 and orc.pnorm_std(9.0) == 1.0 and orc.pnorm_std(-40.0) == 0.0
 
 
