@@ -393,6 +393,7 @@ struct EpiColDot {
 // ---------------------------------------------------------------------------------------
 using CfgLarge = TileCfg<128, 128, 16, 2, 4, 4>;
 using CfgSmall = TileCfg<64, 64, 16, 2, 2, 4>;
+using CfgMid = TileCfg<64, 64, 16, 4, 2, 4>;     // same tile, 8 warps: two warps per scheduler even at 1 CTA/SM
 
 template <class Cfg, bool A_KC, bool B_KC, class Epi>
 cudaError_t launch_gemm(const GemmParams& p, const Epi& epi, int batch, cudaStream_t st) {

@@ -100,6 +100,7 @@ struct gps_handle_s {
   long long seq_launches = 0;   // launches issued by the sequence being recorded
   double last_ms = 0.0;
   int last_pivot = 0;
+  int force_tile = -1;          // developer override of the GEMM tile config (GPS_TILE=0|1|2)
   std::string err;
   cudaError_t cu_err = cudaSuccess;
 };
@@ -199,8 +200,12 @@ void gemm(H* h, const GemmParams& p, const Epi& epi) {
   // gated by its longest tile, so ask for several waves before using the 128 x 128 config
   const long long need = (p.klo_m || p.klo_n || p.khi_m) ? 600 : 100;
   cudaError_t e;
-  if (tl >= need && p.N >= 96)
+  int choice = (tl >= need && p.N >= 96) ? 2 : 0;
+  if (h->force_tile >= 0) choice = h->force_tile;
+  if (choice == 2)
     e = launch_gemm<CfgLarge, A_KC, B_KC, Epi>(p, epi, h->batch, h->st);
+  else if (choice == 1)
+    e = launch_gemm<CfgMid, A_KC, B_KC, Epi>(p, epi, h->batch, h->st);
   else
     e = launch_gemm<CfgSmall, A_KC, B_KC, Epi>(p, epi, h->batch, h->st);
   h->seq_launches++;
@@ -264,6 +269,25 @@ void enqueue_cov(H* h, const double* Za, int n1, int lda, long long sA, const do
   }
 }
 
+// Panel launch: every CTA redoes the 64 x 64 chain, so the row tiling trades redundancy against
+// latency.  A lone fit gets many 32-row CTAs (the GPU is otherwise idle); a batch gets 128-row
+// tiles and, once the grid is full, several tiles per CTA.  +1 CTA publishes L11 / X11.
+void launch_panel(H* h, int e0, int nb, int M, long long* dbg) {
+  const int B = h->batch;
+  const long long small_ctas = (long long)ceil_div(M > 0 ? M : 1, 32) * B;
+  if (small_ctas <= 2 * 148) {
+    dim3 grid(ceil_div(M > 0 ? M : 1, 32) + 1, B);
+    panel_kernel<32><<<grid, 256, PANEL_SMEM, h->st>>>(h->Ky, h->L, h->Linv, h->ld, h->strideM, e0, nb, M, 1, h->info, dbg);
+  } else {
+    int tiles = ceil_div(M > 0 ? M : 1, 128);
+    int T = 1;
+    while ((long long)ceil_div(tiles, T) * B > 4 * 148 && T < tiles) T++;
+    dim3 grid(ceil_div(tiles, T) + 1, B);
+    panel_kernel<128><<<grid, 256, PANEL_SMEM, h->st>>>(h->Ky, h->L, h->Linv, h->ld, h->strideM, e0, nb, M, T, h->info, dbg);
+  }
+  LAUNCHED(h);
+}
+
 // ---------------------------------------------------------------------------------------
 // Recursive blocked Cholesky over block columns [j0, j1) (units of NB).  Precondition: all
 // updates from columns < j0*NB are already applied to Ky[:, j0*NB : j1*NB].  Rows run to
@@ -274,14 +298,9 @@ void potrf_range(H* h, int j0, int j1) {
   const long long sM = h->strideM;
   if (j1 - j0 == 1) {
     int e0 = j0 * NB, nb = (h->ne - e0 < NB) ? h->ne - e0 : NB;
-    potf2_inv_kernel<<<h->batch, 256, LEAF_SMEM, h->st>>>(h->Ky, h->L, h->Linv, ld, sM, e0, nb, h->info);
-    LAUNCHED(h);
+    // fused: L11 = chol(A11), X11 = L11^-1, L[e1:, e0:e1] = Ky[e1:, e0:e1] * X11'
     int e1 = e0 + nb, M = h->naug - e1;
-    if (M > 0) {
-      // L[e1:, e0:e1] = Ky[e1:, e0:e1] * Linv11'   (TRSM as a GEMM with the inverted leaf)
-      GemmParams p = gp(h->Ky + e1 + (size_t)e0 * ld, ld, sM, h->Linv + e0 + (size_t)e0 * ld, ld, sM, M, nb, nb);
-      gemm<false, false>(h, p, plain(h->L + e1 + (size_t)e0 * ld, ld, sM, 1.0, 0.0));
-    }
+    launch_panel(h, e0, nb, M, nullptr);
     return;
   }
   int mid = j0 + (j1 - j0 + 1) / 2;
@@ -295,7 +314,7 @@ void potrf_range(H* h, int j0, int j1) {
   potrf_range(h, mid, j1);
 }
 
-// Inverse of the lower-triangular factor.  The NB leaves were inverted by potf2_inv_kernel;
+// Inverse of the lower-triangular factor.  The NB x NB diagonal blocks were inverted by panel_kernel;
 // merge pairs of blocks bottom-up, one LEVEL per pair of launches: at level s (block size
 // bs = NB * 2^s) node i covers rows/cols [i*2bs, (i+1)*2bs) and computes
 //   Linv21 = -Linv22 * (L21 * Linv11)
@@ -582,6 +601,7 @@ int gps_create_batch(int device, int batch, gps_handle* out) {
     return fail(nullptr, GPS_ERR_CUDA, b);
   }
   H* h = new H();
+  if (const char* ev = getenv("GPS_TILE")) h->force_tile = atoi(ev);
   h->device = device;
   h->batch = batch;
   if (cudaSetDevice(device) != cudaSuccess || cudaStreamCreateWithFlags(&h->st, cudaStreamNonBlocking) != cudaSuccess ||
@@ -591,7 +611,9 @@ int gps_create_batch(int device, int batch, gps_handle* out) {
     delete h;
     return fail(nullptr, GPS_ERR_CUDA, "gps_create: " + m);
   }
-  e = cudaFuncSetAttribute(potf2_inv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LEAF_SMEM);
+  e = cudaFuncSetAttribute(panel_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PANEL_SMEM);
+  if (e == cudaSuccess)
+    e = cudaFuncSetAttribute(panel_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PANEL_SMEM);
   if (e != cudaSuccess) {
     delete h;
     return fail(nullptr, GPS_ERR_CUDA, std::string("gps_create: ") + cudaGetErrorString(e));
@@ -1217,6 +1239,27 @@ __global__ void fill_pattern_kernel(double* p, size_t n, unsigned seed) {
   p[i] = ((double)(x & 0xffff) / 65536.0) - 0.5;
 }
 }  // namespace
+
+// Developer probe: run the panel kernel once on block column 0 of the current Ky with
+// clock64() stamps at its phase boundaries (cycles since kernel start in out[0..n)).
+int gps_debug_panel_clocks(gps_handle h, long long* out, int n_out) {
+  int rc = check_handle(h);
+  if (rc) return rc;
+  if (!h->have_data || !out || n_out < 16) return fail(h, GPS_ERR_ARG, "gps_debug_panel_clocks: bad arguments");
+  long long* d = nullptr;
+  CK(h, dalloc(&d, 32));
+  int nb = h->ne < NB ? h->ne : NB;
+  int M = h->naug - nb;
+  h->cu_err = cudaSuccess;
+  for (int rep = 0; rep < 3; rep++) launch_panel(h, 0, nb, M, d);
+  long long host[32];
+  CK(h, cudaMemcpyAsync(host, d, sizeof host, cudaMemcpyDeviceToHost, h->st));
+  CK(h, cudaStreamSynchronize(h->st));
+  cudaFree(d);
+  for (int i = 0; i < n_out; i++) out[i] = (i < 32 && host[i]) ? host[i] - host[0] : 0;
+  h->fact_level = 0;
+  return GPS_OK;
+}
 
 int gps_bench_gemm(gps_handle h, int M, int N, int K, int reps, double* ms_out) {
   int rc = check_handle(h);

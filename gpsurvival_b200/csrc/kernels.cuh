@@ -231,190 +231,310 @@ __global__ void fill_aug_kernel(const double* __restrict__ X, int n, int ne, int
 }
 
 // ---------------------------------------------------------------------------------------
-// Leaf of the recursive Cholesky: factor one NB x NB (64 x 64) diagonal block and invert the
-// factor (chol(): ForOptimisationLog.R:41-42).  Reads the lower triangle of A[e0.., e0..],
-// writes L (lower, zeros above) and Linv (lower, zeros above) at the same coordinates.
+// Fused panel kernel of the blocked Cholesky (chol(): ForOptimisationLog.R:41-42): for the
+// block column [e0, e0+nb) it
+//   (1) factors the NB x NB diagonal block          L11 = chol(A11)
+//   (2) inverts the factor                          X11 = L11^-1          (kept for the panel
+//       solve here, for the triangular inverse of the gradient and for prediction)
+//   (3) solves the panel below                      L21 = A21 * X11'      (M rows, incl. the
+//       appended right-hand-side rows)
+// in ONE launch.  Every CTA redoes (1)+(2) for itself — redundant work, but no extra launch
+// and no inter-CTA dependency — and owns 128 rows of (3).
 //
-// The pivot chain (n sequential sqrt/scale steps) is the latency floor of the whole
-// factorisation, so the leaf is built from warp-synchronous 32 x 32 primitives whose working
-// row lives in REGISTERS (fully unrolled, static indices): per column the critical path is
-// shuffle(pivot) -> rsqrt -> scale -> one FMA on the next pivot (~90 cycles), with the rest of
-// the rank-1 update fed by shared-memory broadcasts off the critical path.
-//   64x64 = [A11 0; A21 A22]:  potf2(A11) | trsm(A21) + inv(L11) | syrk(A22) | potf2(A22) |
-//   inv(L22) | T = L21*X11 | X21 = -X22*T.
-// A non-positive pivot records info[b] = failing column (1-based, first wins) and the block
-// is completed with NaNs (the host turns info into GPS_ERR_NOT_PD).
-// grid (batch), block 256, dynamic smem LEAF_SMEM.
+// (1) is the sequential pivot chain that bounds the whole factorisation at n <~ 4k, so it is
+// organised for latency (measured history in DESIGN.md):
+//   * blocked: four 16-column sub-panels.  Inside a sub-panel ONE warp (lane = rows lane and
+//     lane+32) keeps the 16 live columns of its rows in a rotating register window
+//     (p[i-1] = p[i] - l*lc: static indices, rolled loop, compact code, no predicates);
+//     the pivot and the next pivot travel by warp shuffle, so the per-column critical path is
+//     rsqrt -> mul -> shfl -> fma (~115 cycles) and the 15-element rank-1 update runs in its
+//     shadow from shared-memory broadcasts.
+//   * after each sub-panel the rank-16 update of the trailing block runs on DMMA from shared
+//     memory on all 8 warps.
+// (2) is a blocked inverse: four 16 x 16 diagonal blocks inverted in registers (lane = column),
+//     then two merge levels  X21 = -X22 (L21 X11)  on DMMA.
+// (3) is a 128 x 64 x 64 DMMA GEMM from shared memory (8 warps, 32 x 32 per warp).
+// A non-positive pivot records info[b] = failing column (1-based, first wins); the block is
+// completed with NaNs and the host turns info into GPS_ERR_NOT_PD.
+// grid (max(1, ceil(M/128)), batch), block 256, dynamic smem PANEL_SMEM.
 // ---------------------------------------------------------------------------------------
-constexpr int LS = NB + 1;    // row stride of the 64 x 64 shared tiles (odd => conflict-free rows)
-constexpr int LT = 33;
-constexpr size_t LEAF_SMEM = (2 * NB * LS + 32 * LT + NB) * sizeof(double);
+constexpr int PS = NB + 4;     // S  column-major: S[c*PS + r] = A11/L11[r][c]   (== 4 mod 16, even)
+constexpr int PX = NB + 4;     // sX row-major:    sX[k*PX + c] = X11[k][c]
+constexpr int PA = 128 + 4;    // sA: sA[k*PA + m] = A21[m][k]
+constexpr int PT = 32 + 4;     // sT column-major: sT[n*PT + m]
+constexpr size_t PANEL_SMEM = (size_t)(NB * PS + NB * PX + NB * PA + 32 * PT + NB) * sizeof(double);
 
-// The 32x32 warp primitives keep the working row/column in registers but stay COMPACT: the
-// outer loop over the pivot is rolled and the register window rotates (the shift is fused
-// into the FMA destination: a[c-1] = a[c] - l*lc), so indices are static without unrolling
-// 32 x 32 steps.  A fully unrolled version is ~200 KB of straight-line SASS executed once and
-// is instruction-fetch bound (measured: 20 K warp-instructions in 120 K cycles).
+__device__ __forceinline__ void dmma_acc(double& d0, double& d1, double a_mma, double b_mma) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+               : "+d"(d0), "+d"(d1)
+               : "d"(a_mma), "d"(b_mma));
+}
 
-// One warp, lane = row.  a[] = row `lane` of a 32x32 SPD block (lower part valid).  On exit
-// sL[r*LS + c] holds the factor (zeros above the diagonal), sInvD[j] = 1 / L_jj.
-// Returns the first non-positive pivot column (1-based) or 0.
-__device__ __forceinline__ int warp_potf2_32(double (&a)[32], double* sL, double* sInvD, int lane) {
-  int bad = 0;
+// Sub-panel Q (columns 16Q..16Q+15) of the 64 x 64 block in S, executed by warp 0.
+// SLOTS = 2: rows lane and lane+32 are both live (Q < 2); SLOTS = 1: only rows lane+32 (Q >= 2).
+template <int Q>
+__device__ __forceinline__ void potf2_subpanel(double* S, double* invd, int lane, int& bad) {
+  constexpr int S0 = (Q < 2) ? 0 : 1;            // first live slot; the pivot row is in slot Q/2
+  constexpr int PSLOT = Q / 2;
+  double p[2][16];
+#pragma unroll
+  for (int s = S0; s < 2; s++)
+#pragma unroll
+    for (int i = 0; i < 16; i++) p[s][i] = S[(16 * Q + i) * PS + lane + 32 * s];
+  double d = __shfl_sync(0xffffffffu, p[PSLOT][0], (16 * Q) & 31);
 #pragma unroll 1
-  for (int j = 0; j < 32; j++) {
-    double d = __shfl_sync(0xffffffffu, a[0], j);       // pivot: column j of row j
+  for (int jj = 0; jj < 16; jj++) {
+    const int j = 16 * Q + jj;
     if (!(d > 0.0) && bad == 0) bad = j + 1;
-    double rs = rsqrt(d);
-    double lr = (lane > j) ? a[0] * rs : ((lane == j) ? d * rs : 0.0);
-    sL[lane * LS + j] = lr;
-    if (lane == j) sInvD[j] = rs;
+    const double rs = rsqrt(d);
+    double lr[2];
+#pragma unroll
+    for (int s = S0; s < 2; s++) {
+      const int r = lane + 32 * s;
+      lr[s] = (r > j) ? p[s][0] * rs : ((r == j) ? d * rs : 0.0);
+      S[j * PS + r] = lr[s];
+    }
+    if (Q >= 2) S[j * PS + lane] = 0.0;          // rows above the sub-panel: zeros above the diagonal
+    if (lane == 0) invd[j] = rs;
+    // next pivot = a_{j+1,j+1} - l_{j+1,j}^2, straight from the owner's registers
+    {
+      const int o = (j + 1) & 31;
+      double a11 = __shfl_sync(0xffffffffu, p[PSLOT][1], o);
+      double l10 = __shfl_sync(0xffffffffu, lr[PSLOT], o);
+      d = a11 - l10 * l10;
+    }
     __syncwarp();
-    const double* colj = sL + (j + 1) * LS + j;         // L[j+1.., j]: broadcast reads
+    const double* col = S + j * PS + j;
 #pragma unroll
-    for (int c = 1; c < 32; c++) {
-      double lc = (j + c < 32) ? colj[(c - 1) * LS] : 0.0;
-      a[c - 1] = a[c] - lr * lc;                        // rank-1 update + window shift
-    }
-  }
-  return bad;
-}
-
-// One warp, lane = column c of X = L^-1 for a 32x32 lower-triangular L in sL (inverse
-// diagonal in sInvD).  Writes sX[r*LS + c] (zeros above the diagonal).
-__device__ __forceinline__ void warp_trinv_32(const double* sL, const double* sInvD, double* sX, int lane) {
-  double x[32];
+    for (int i = 1; i < 16; i++) {
+      const double lc = col[i];
 #pragma unroll
-  for (int r = 0; r < 32; r++) x[r] = (r == lane) ? 1.0 : 0.0;
-#pragma unroll 1
-  for (int k = 0; k < 32; k++) {
-    double xk = x[0] * sInvD[k];
-    sX[k * LS + lane] = xk;
-    const double* colk = sL + (k + 1) * LS + k;
-#pragma unroll
-    for (int r = 1; r < 32; r++) {
-      double lv = (k + r < 32) ? colk[(r - 1) * LS] : 0.0;
-      x[r - 1] = x[r] - lv * xk;
+      for (int s = S0; s < 2; s++) p[s][i - 1] = p[s][i] - lr[s] * lc;
     }
   }
 }
 
-// One warp, lane = row of a 32x32 block B: B <- B * L^-T (L lower 32x32 in sL) by forward
-// substitution; result written to sOut[lane*LS + j].
-__device__ __forceinline__ void warp_trsm_32(double (&a)[32], const double* sL, const double* sInvD, double* sOut,
-                                             int lane) {
+// Trailing update after sub-panel Q:  S[R.., R..] -= L[R.., 16Q..16Q+15] * L[R.., 16Q..16Q+15]',
+// R = 16(Q+1); lower 8x8 tiles distributed over the 8 warps.
+template <int Q>
+__device__ __forceinline__ void potf2_trailing(double* S, int warp, int g, int t) {
+  constexpr int R = 16 * (Q + 1), NT8 = (NB - R) / 8;
+  int tile = 0;
 #pragma unroll 1
-  for (int j = 0; j < 32; j++) {
-    double x = a[0] * sInvD[j];
-    sOut[lane * LS + j] = x;
-    const double* colj = sL + (j + 1) * LS + j;
+  for (int mi = 0; mi < NT8; mi++)
+#pragma unroll 1
+    for (int ni = 0; ni <= mi; ni++, tile++) {
+      if ((tile & 7) != warp) continue;
+      const int m0 = R + 8 * mi, n0 = R + 8 * ni;
+      double2 c = *reinterpret_cast<double2*>(S + (n0 + g) * PS + m0 + 2 * t);
 #pragma unroll
-    for (int c = 1; c < 32; c++) {
-      double lc = (j + c < 32) ? colj[(c - 1) * LS] : 0.0;
-      a[c - 1] = a[c] - x * lc;
+      for (int ks = 0; ks < 4; ks++) {
+        const int k = 16 * Q + 4 * ks + t;
+        dmma_acc(c.x, c.y, -S[k * PS + n0 + g], S[k * PS + m0 + g]);
+      }
+      *reinterpret_cast<double2*>(S + (n0 + g) * PS + m0 + 2 * t) = c;
+    }
+}
+
+// One merge of the blocked inverse: rows [R1, R1+SZ), cols [C0, C0+SZ) of X:
+//   pass 0:  T   = L21 * X11      (T in sT, column-major)
+//   pass 1:  X21 = -X22 * T
+// 8x8 output tiles are dealt round-robin to `nw` warps (this warp has index `w`).
+template <int SZ>
+__device__ __forceinline__ void trinv_merge(const double* S, double* sX, double* sT, int R1, int C0, int pass, int w,
+                                            int nw, int g, int t) {
+  constexpr int NT8 = SZ / 8;
+#pragma unroll 1
+  for (int tile = w; tile < NT8 * NT8; tile += nw) {
+    const int m0 = 8 * (tile % NT8), n0 = 8 * (tile / NT8);
+    double c0 = 0.0, c1 = 0.0;
+    if (pass == 0) {
+#pragma unroll
+      for (int ks = 0; ks < SZ / 4; ks++) {
+        const int k = 4 * ks + t;
+        dmma_acc(c0, c1, sX[(C0 + k) * PX + C0 + n0 + g], S[(C0 + k) * PS + R1 + m0 + g]);
+      }
+      *reinterpret_cast<double2*>(sT + (n0 + g) * PT + m0 + 2 * t) = make_double2(c0, c1);
+    } else {
+#pragma unroll
+      for (int ks = 0; ks < SZ / 4; ks++) {
+        const int k = 4 * ks + t;
+        dmma_acc(c0, c1, -sT[(n0 + g) * PT + k], sX[(R1 + m0 + g) * PX + R1 + k]);
+      }
+      sX[(R1 + m0 + 2 * t) * PX + C0 + n0 + g] = c0;
+      sX[(R1 + m0 + 2 * t + 1) * PX + C0 + n0 + g] = c1;
     }
   }
 }
 
-__global__ void __launch_bounds__(256) potf2_inv_kernel(const double* __restrict__ A, double* __restrict__ L,
-                                                        double* __restrict__ Linv, int ld, long long stride,
-                                                        int e0, int nb, int* __restrict__ info) {
-  extern __shared__ __align__(16) double leaf_smem[];
-  double* S = leaf_smem;                 // 64 x LS : A, then L
-  double* X = leaf_smem + NB * LS;       // 64 x LS : L^-1
-  double* T = leaf_smem + 2 * NB * LS;   // 32 x LT
-  double* invd = T + 32 * LT;            // 64
-  __shared__ int sbad;
-  const int b = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const double* Ab = A + (size_t)b * stride + (size_t)e0 + (size_t)e0 * ld;
-  for (int idx = tid; idx < NB * NB; idx += 256) {
-    int r = idx & 63, c = idx >> 6;
-    double v = (r == c) ? 1.0 : 0.0;     // identity padding for a partial block
-    if (r < nb && c < nb) v = (r >= c) ? Ab[(size_t)r + (size_t)c * ld] : 0.0;
-    S[r * LS + c] = v;
-    X[r * LS + c] = 0.0;
+// RT = rows of one panel tile (32: many small CTAs for a lone fit; 128: throughput for batches),
+// T = consecutive tiles per CTA.  The LAST CTA along x only publishes L11 / X11.
+template <int RT>
+__global__ void __launch_bounds__(256) panel_kernel(const double* __restrict__ A, double* __restrict__ L,
+                                                    double* __restrict__ Linv, int ld, long long stride, int e0,
+                                                    int nb, int M, int T, int* __restrict__ info,
+                                                    long long* __restrict__ dbg) {
+  extern __shared__ __align__(16) double panel_smem[];
+  int dbg_i = 0;
+#define PANEL_STAMP() do { if (dbg && threadIdx.x == 0 && blockIdx.x == 0 && blockIdx.y == 0) dbg[dbg_i++] = clock64(); } while (0)
+  PANEL_STAMP();
+  double* S = panel_smem;
+  double* sX = S + NB * PS;
+  double* sA = sX + NB * PX;
+  double* sT = sA + NB * PA;
+  double* invd = sT + 32 * PT;
+  const int tid = threadIdx.x, cta = blockIdx.x, b = blockIdx.y;
+  const int warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
+  const double* Ab = A + (size_t)b * stride;
+  const int e1 = e0 + nb;
+  const bool publisher = (cta == (int)gridDim.x - 1);
+  int row0 = e1 + cta * T * RT;                 // first panel row of this CTA
+  int rows = publisher ? 0 : min(RT, e1 + M - row0);
+
+  // stage A11 (zero-filled to 64 x 64) and the A21 tile with coalesced 16-byte async copies
+  for (int c = tid; c < NB * 32; c += 256) {
+    int col = c >> 5, rc = (c & 31) * 2;
+    int valid = (col < nb) ? min(max(nb - rc, 0), 2) : 0;
+    const double* src = valid ? (Ab + (size_t)(e0 + rc) + (size_t)(e0 + col) * ld) : Ab;
+    unsigned dst = (unsigned)__cvta_generic_to_shared(S + col * PS + rc);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(dst), "l"(src), "r"(valid * 8));
   }
-  if (tid == 0) sbad = 0;
+  asm volatile("cp.async.commit_group;\n" ::);
+  auto load_a21 = [&]() {
+    for (int c = tid; c < NB * (RT / 2); c += 256) {
+      int k = c / (RT / 2), mc = (c % (RT / 2)) * 2;
+      int valid = (k < nb) ? min(max(rows - mc, 0), 2) : 0;
+      const double* src = valid ? (Ab + (size_t)(row0 + mc) + (size_t)(e0 + k) * ld) : Ab;
+      unsigned dst = (unsigned)__cvta_generic_to_shared(sA + k * PA + mc);
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(dst), "l"(src), "r"(valid * 8));
+    }
+    asm volatile("cp.async.commit_group;\n" ::);
+  };
+  load_a21();
+  for (int i = tid; i < NB * PX; i += 256) sX[i] = 0.0;
+  asm volatile("cp.async.wait_group 1;\n" ::);     // A11 has landed (A21 may still be in flight)
   __syncthreads();
-  if (warp == 0) {                        // potf2(A11)
-    double a[32];
-#pragma unroll
-    for (int c = 0; c < 32; c++) a[c] = S[lane * LS + c];
-    int bad = warp_potf2_32(a, S, invd, lane);
-    if (bad && lane == 0) sbad = bad;
-  }
+  if (tid >= nb && tid < NB) S[tid * PS + tid] = 1.0;   // identity padding of a partial block
   __syncthreads();
-  if (warp == 1) {                        // L21 = A21 * L11^-T by substitution, lane = row
-    double a[32];
-#pragma unroll
-    for (int c = 0; c < 32; c++) a[c] = S[(32 + lane) * LS + c];
-    warp_trsm_32(a, S, invd, S + 32 * LS, lane);
-  } else if (warp == 0) {
-    warp_trinv_32(S, invd, X, lane);      // X11 = L11^-1
-  }
+  PANEL_STAMP();
+
+  // ---- (1) blocked factorisation -----------------------------------------------------------
+  int bad = 0;
+  if (warp == 0) potf2_subpanel<0>(S, invd, lane, bad);
   __syncthreads();
-  if (warp < 4) {                         // A22 -= L21 * L21'  (warp w: columns 8w..8w+7; lane = row)
-    double xr[32];
+  PANEL_STAMP();
+  potf2_trailing<0>(S, warp, g, t);
+  __syncthreads();
+  PANEL_STAMP();
+  if (warp == 0) potf2_subpanel<1>(S, invd, lane, bad);
+  __syncthreads();
+  PANEL_STAMP();
+  potf2_trailing<1>(S, warp, g, t);
+  __syncthreads();
+  PANEL_STAMP();
+  if (warp == 0) potf2_subpanel<2>(S, invd, lane, bad);
+  __syncthreads();
+  PANEL_STAMP();
+  potf2_trailing<2>(S, warp, g, t);
+  __syncthreads();
+  PANEL_STAMP();
+  if (warp == 0) potf2_subpanel<3>(S, invd, lane, bad);
+  __syncthreads();
+  PANEL_STAMP();
+
+  // ---- (2) blocked inverse ------------------------------------------------------------------
+  if (warp < 4 && lane < 16) {                  // 16 x 16 diagonal blocks: lane = column
+    const int o = 16 * warp, c = lane;
+    double x[16];
 #pragma unroll
-    for (int k = 0; k < 32; k++) xr[k] = S[(32 + lane) * LS + k];
+    for (int i = 0; i < 16; i++) x[i] = (i == c) ? 1.0 : 0.0;
 #pragma unroll 1
-    for (int cc = 0; cc < 8; cc++) {
-      int c = warp * 8 + cc;
-      double acc = S[(32 + lane) * LS + 32 + c];
+    for (int k = 0; k < 16; k++) {
+      const double xk = x[0] * invd[o + k];
+      sX[(o + k) * PX + o + c] = xk;
+      const double* col = S + (o + k) * PS + o + k;
 #pragma unroll
-      for (int k = 0; k < 32; k++) acc -= xr[k] * S[(32 + c) * LS + k];
-      S[(32 + lane) * LS + 32 + c] = acc;
+      for (int i = 1; i < 16; i++) x[i - 1] = x[i] - col[i] * xk;
     }
   }
   __syncthreads();
-  if (warp == 0) {                        // potf2(A22), then X22 = L22^-1
-    double a[32];
-#pragma unroll
-    for (int c = 0; c < 32; c++) a[c] = S[(32 + lane) * LS + 32 + c];
-    int bad = warp_potf2_32(a, S + 32 * LS + 32, invd + 32, lane);
-    if (bad && lane == 0 && sbad == 0) sbad = 32 + bad;
-    __syncwarp();
-    warp_trinv_32(S + 32 * LS + 32, invd + 32, X + 32 * LS + 32, lane);
-  }
+  PANEL_STAMP();
+  trinv_merge<16>(S, sX, sT + (warp >> 2) * 16 * PT, (warp >> 2) * 32 + 16, (warp >> 2) * 32, 0, warp & 3, 4, g, t);
   __syncthreads();
-  {                                       // T = L21 * X11   (warp w: columns 4w..4w+3; lane = row)
-    double xr[32];
-#pragma unroll
-    for (int k = 0; k < 32; k++) xr[k] = S[(32 + lane) * LS + k];
+  trinv_merge<16>(S, sX, sT + (warp >> 2) * 16 * PT, (warp >> 2) * 32 + 16, (warp >> 2) * 32, 1, warp & 3, 4, g, t);
+  __syncthreads();
+  trinv_merge<32>(S, sX, sT, 32, 0, 0, warp, 8, g, t);
+  __syncthreads();
+  trinv_merge<32>(S, sX, sT, 32, 0, 1, warp, 8, g, t);
+  asm volatile("cp.async.wait_group 0;\n" ::);
+  __syncthreads();
+  PANEL_STAMP();
+
+  if (publisher) {                              // publish L11 and X11 (lower, zeros above)
+    if (tid == 0 && bad != 0 && bad <= nb) atomicCAS(&info[b], 0, e0 + bad);
+    double* Lb = L + (size_t)b * stride + (size_t)e0 + (size_t)e0 * ld;
+    double* Ib = Linv + (size_t)b * stride + (size_t)e0 + (size_t)e0 * ld;
+    for (int idx = tid; idx < NB * NB; idx += 256) {
+      int r = idx & 63, c = idx >> 6;
+      if (r < nb && c < nb) {
+        Lb[(size_t)r + (size_t)c * ld] = (r >= c) ? S[c * PS + r] : 0.0;
+        Ib[(size_t)r + (size_t)c * ld] = (r >= c) ? sX[r * PX + c] : 0.0;
+      }
+    }
+    PANEL_STAMP();
+    return;
+  }
+  PANEL_STAMP();
+
+  // ---- (3) L21 = A21 * X11'  : C[m][n] = sum_k A21[m][k] * X[n][k]   (DMMA; warps 4 (m) x 2 (n))
+  constexpr int FMT = RT / 32;                   // 8-row fragments per warp along m
+  const int wm0 = (warp & 3) * (RT / 4), wn0 = (warp >> 2) * 32;
 #pragma unroll 1
-    for (int cc = 0; cc < 4; cc++) {
-      int c = warp * 4 + cc;
-      double acc = 0.0;
+  for (int tile = 0; tile < T; tile++) {
+    if (tile > 0) {
+      row0 += RT;
+      rows = min(RT, e1 + M - row0);
+      if (rows <= 0) break;
+      __syncthreads();                           // everyone is done reading the previous tile
+      load_a21();
+      asm volatile("cp.async.wait_group 0;\n" ::);
+      __syncthreads();
+    } else if (rows <= 0) {
+      break;
+    }
+    double acc[FMT][4][2];
 #pragma unroll
-      for (int k = 0; k < 32; k++) acc += xr[k] * X[k * LS + c];
-      T[lane * LT + c] = acc;
+    for (int i = 0; i < FMT; i++)
+#pragma unroll
+      for (int j = 0; j < 4; j++) acc[i][j][0] = acc[i][j][1] = 0.0;
+#pragma unroll 4
+    for (int ks = 0; ks < NB / 4; ks++) {
+      double af[FMT], bf[4];
+#pragma unroll
+      for (int i = 0; i < FMT; i++) af[i] = sA[(4 * ks + t) * PA + wm0 + 8 * i + g];
+#pragma unroll
+      for (int j = 0; j < 4; j++) bf[j] = sX[(wn0 + 8 * j + g) * PX + 4 * ks + t];
+#pragma unroll
+      for (int i = 0; i < FMT; i++)
+#pragma unroll
+        for (int j = 0; j < 4; j++) dmma_acc(acc[i][j][0], acc[i][j][1], bf[j], af[i]);
+    }
+    double* Lp = L + (size_t)b * stride + (size_t)row0 + (size_t)e0 * ld;
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+      int n = wn0 + 8 * j + g;
+      if (n >= nb) continue;
+#pragma unroll
+      for (int i = 0; i < FMT; i++) {
+        int m = wm0 + 8 * i + 2 * t;
+        double* c = Lp + (size_t)m + (size_t)n * ld;
+        if (m + 1 < rows) *reinterpret_cast<double2*>(c) = make_double2(acc[i][j][0], acc[i][j][1]);
+        else if (m < rows) c[0] = acc[i][j][0];
+      }
     }
   }
-  __syncthreads();
-  {                                       // X21 = -X22 * T
-    double xr[32];
-#pragma unroll
-    for (int k = 0; k < 32; k++) xr[k] = X[(32 + lane) * LS + 32 + k];
-#pragma unroll 1
-    for (int cc = 0; cc < 4; cc++) {
-      int c = warp * 4 + cc;
-      double acc = 0.0;
-#pragma unroll
-      for (int k = 0; k < 32; k++) acc -= xr[k] * T[k * LT + c];
-      X[(32 + lane) * LS + c] = acc;
-    }
-  }
-  __syncthreads();
-  if (tid == 0 && sbad != 0 && sbad <= nb) atomicCAS(&info[b], 0, e0 + sbad);
-  double* Lb = L + (size_t)b * stride + (size_t)e0 + (size_t)e0 * ld;
-  double* Ib = Linv + (size_t)b * stride + (size_t)e0 + (size_t)e0 * ld;
-  for (int idx = tid; idx < NB * NB; idx += 256) {
-    int r = idx & 63, c = idx >> 6;
-    if (r < nb && c < nb) {
-      Lb[(size_t)r + (size_t)c * ld] = (r >= c) ? S[r * LS + c] : 0.0;
-      Ib[(size_t)r + (size_t)c * ld] = (r >= c) ? X[r * LS + c] : 0.0;
-    }
-  }
+  PANEL_STAMP();
+#undef PANEL_STAMP
 }
 
 // ---------------------------------------------------------------------------------------

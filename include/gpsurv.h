@@ -136,6 +136,9 @@ int gps_time_stages(gps_handle h, double* ms_out);
 /* Raw FP64 GEMM through the library's DMMA kernel: C(MxN) = A(MxK) * B(NxK)' — for the
  * peak-fraction measurement beside cublasDgemm.  Device-resident synthetic operands. */
 int gps_bench_gemm(gps_handle h, int M, int N, int K, int reps, double* ms_out);
+/* Developer probe: clock64() stamps (cycles since kernel start) at the phase boundaries of the fused
+ * Cholesky panel kernel, run once on block column 0 of the current Ky. */
+int gps_debug_panel_clocks(gps_handle h, long long* out, int n_out);
 
 #ifdef __cplusplus
 }
