@@ -5,18 +5,22 @@
     python bench.py --gpus N --steps K --warmup W            # our CUDA path
     python bench.py --impl reference --steps K --warmup W    # the reference algorithm on host cores
 
-One "step" = one evaluation of ForOptimisationLog + OptimisationGradientLog (NLML and its
-gradient w.r.t. all 22 hyper-parameters); the e2e leg uses a fresh hyper-parameter vector every
-step, the device-resident leg replays the evaluation at the resident vector (nothing is cached
-between replays: every replay recomputes Gram, Cholesky, inverse and gradient).
+One "step" = one pass of the hot path over one BATCH of independent fits: `--batch` (default 32)
+C2-shaped GPS3/ARD fits (distinct synthetic data sets and start hyper-parameters — restarts /
+CV folds / repetitions, which north_star batches per GPU) each get one evaluation of
+ForOptimisationLog + OptimisationGradientLog (NLML and its gradient w.r.t. all 22
+hyper-parameters).  The unit of the metric stays the single evaluation: value = batch * K / time.
+A lone fit is latency-bound by the sequential pivot chain of its Cholesky; `single_fit` reports it.
 
 * value  : evaluations/s, inputs resident in HBM, device-timed with CUDA events on the
-           library's stream (gps_time_eval: K back-to-back graph replays), max over ranks.
+           library's stream (gps_time_eval: K back-to-back graph replays; nothing is cached
+           between replays: each recomputes Gram, Cholesky, inverse and gradient), max over ranks.
 * e2e    : the same metric through the public API with HOST buffers: every step uploads X, y,
-           events, the GPS3 noise-correction vector and par, evaluates, and reads NLML+gradient back.
-* roofline: the evaluation graph (one launch = one evaluation = 3 n^2 d + n^3 algorithmic FP64
-           flops) against the FP64 tensor (DMMA) peak measured in this run with
-           cublasDgemm 8192^3 (MEASURED_PEAKS.json carries no FP64 figure).
+           events, the GPS3 noise-correction vectors and par for the whole batch, evaluates, and
+           reads all NLMLs and gradients back.
+* roofline: the evaluation graph (one launch = `batch` evaluations, each 3 n^2 d + n^3
+           algorithmic FP64 flops) against the FP64 tensor (DMMA) peak measured in
+           this run with cublasDgemm 8192^3 (MEASURED_PEAKS.json carries no FP64 figure).
 * cpu_baseline: the reference's algorithm restated in numpy (oracle/, as-written operation
            sequence) on the host cores — R itself is not installed in the image.
 """
@@ -42,8 +46,8 @@ UNIT = "evals/s"
 CFG = synth.CONFIGS["C2"]
 
 
-def workload(rank: int):
-    pb = synth.make_config_problem(CFG, fit_index=rank)
+def workload(rank: int, fit: int = 0):
+    pb = synth.make_config_problem(CFG, fit_index=1000 * rank + fit)
     X = pb["trainingData"]
     y = np.log(pb["trainingTargets"])
     ev = pb["events"]
@@ -52,9 +56,29 @@ def workload(rank: int):
     return X, y, ev, lnc, par0
 
 
+def batch_workload(rank: int, batch: int, distinct: int = 4):
+    """`batch` independent fits; `distinct` different synthetic data sets are generated (host time)
+    and cycled, every fit gets its own hyper-parameter vector."""
+    sets = [workload(rank, f) for f in range(min(distinct, batch))]
+    X = np.stack([sets[i % len(sets)][0] for i in range(batch)])
+    y = np.stack([sets[i % len(sets)][1] for i in range(batch)])
+    ev = np.stack([sets[i % len(sets)][2] for i in range(batch)])
+    lnc = np.stack([sets[i % len(sets)][3] for i in range(batch)])
+    return X, y, ev, lnc, sets[0][4]
+
+
 def step_pars(par0, count, seed):
     rng = np.random.default_rng(seed)
     return par0[None, :] + 0.05 * rng.standard_normal((count, par0.size))
+
+
+def config_dict(B, world, n, d, nhyp):
+    return {"workload": "C2: GPS3 ARD NLML+gradient, n=2000 d=20 c=1000 (BASELINE.json configs[1]); one step = "
+                        "one evaluation of each of %d independent fits batched per GPU" % B,
+            "n": int(n), "d": int(d), "hyperparameters": int(nhyp), "fits_per_gpu": int(B),
+            "partition": f"independent fits, {B} per GPU x {world} GPUs, no collective",
+            "l2": "per-step working set %d fits x 5 n x n FP64 matrices = %.1f GB >> 126 MB L2 (no flush needed)"
+                  % (B, B * 5 * n * n * 8 / 1e9)}
 
 
 def algorithmic_flops(n, d, ard=True):
@@ -173,8 +197,9 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * dt / steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "C2: GPS3 ARD NLML+gradient, n=2000 d=20 c=1000 (BASELINE.json configs[1])",
-                   "n": int(X.shape[0]), "d": int(X.shape[1]), "hyperparameters": int(par0.size)},
+        "config": dict(config_dict(args.batch, args.gpus, X.shape[0], X.shape[1], par0.size),
+                       reference_step="the host evaluates the fits of a batch one after another; a timed step here is ONE "
+                                      "evaluation of one fit (a bounded sample of the batch), value is evaluations/s"),
         "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample,
                          "note": "reference algorithm restated in numpy (as-written op sequence); R unavailable in image"},
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -199,16 +224,18 @@ def run_gpu(args):
     torch.cuda.set_device(device)
 
     from gpsurvival_b200 import gp
-    X, y, ev, lnc, par0 = workload(rank)
-    n, d = X.shape
+    B = args.batch
+    X, y, ev, lnc, par0 = batch_workload(rank, B)
+    n, d = X.shape[1], X.shape[2]
     flops = algorithmic_flops(n, d, ard=True)
 
-    fit = gp.Fit(local)
+    fit = gp.Fit(local, batch=B)
     fit.set_options(CFG.cov_form, "Zero", CFG.noise_corr, "intended")
     fit.set_data(X, y, ev)
     fit.set_noise_corr(lnc)
     K, W = args.steps, max(args.warmup, 3)
-    pars = step_pars(par0, 2 * (K + W), 11 + rank)
+    rng = np.random.default_rng(11 + rank)
+    pars = par0[None, None, :] + 0.05 * rng.standard_normal((K + W, B, par0.size))
     for w in range(W):                                   # warm-up: direct run, graph capture, replay
         fit.nlml_grad(pars[w])
 
@@ -233,12 +260,12 @@ def run_gpu(args):
     barrier()
     sampler.start()
     l0 = fit.launch_count()
-    ms_per_eval = fit.time_eval(kind=1, reps=K)
+    ms_per_step = fit.time_eval(kind=1, reps=K)
     launches = fit.launch_count() - l0
     barrier()
-    dev_ms = max_over_ranks(ms_per_eval * K)
+    dev_ms = max_over_ranks(ms_per_step * K)
     clocks = sampler.stop()
-    value = world * K / (dev_ms * 1e-3)
+    value = world * B * K / (dev_ms * 1e-3)
 
     # ---- end to end through the public API with host buffers --------------------------------------
     barrier()
@@ -250,48 +277,59 @@ def run_gpu(args):
     torch.cuda.synchronize(device)
     e2e_s = max_over_ranks(time.perf_counter() - t0)
     barrier()
-    e2e_val = world * K / e2e_s
-    h2d = 8 * (X.size + y.size + ev.size + lnc.size + par0.size)
-    d2h = 8 * (1 + par0.size) + 4
+    e2e_val = world * B * K / e2e_s
+    h2d = 8 * (X.size + y.size + ev.size + lnc.size + B * par0.size)
+    d2h = 8 * B * (1 + par0.size) + 4 * B
 
     line = None
     if rank == 0:
         stages = fit.time_stages()
         gemm_ms = fit.bench_gemm(8192, 8192, 8192, 3)
-        achieved = flops / (ms_per_eval * 1e-3) / 1e12
+        achieved = B * flops / (ms_per_step * 1e-3) / 1e12
+        # a lone fit (latency-bound): same workload, batch of one
+        one = gp.Fit(local)
+        one.set_options(CFG.cov_form, "Zero", CFG.noise_corr, "intended")
+        one.set_data(X[0], y[0], ev[0])
+        one.set_noise_corr(lnc[0])
+        for w in range(3):
+            f1, g1 = one.nlml_grad(pars[w, 0])
+        single_ms = one.time_eval(kind=1, reps=20)
+        single_nlml_ms = one.time_eval(kind=0, reps=20)
+        one.close()
         # bounded CPU sample of the same workload (about 10-30 s of host work)
         t0 = time.perf_counter()
         cnt = 0
         f_cpu = g_cpu = None
         while cnt < 3 or (time.perf_counter() - t0 < 12.0 and cnt < 40):
-            f_cpu, g_cpu = cpu_eval(pars[W + K - 1], X, y, ev, lnc)
+            f_cpu, g_cpu = cpu_eval(pars[W + K - 1, 0], X[0], y[0], ev[0], lnc[0])
             cnt += 1
         cpu_val = cnt / (time.perf_counter() - t0)
-        parity = {"nlml_rel": abs(f - f_cpu) / abs(f_cpu),
-                  "grad_rel": float(np.max(np.abs(g - g_cpu)) / np.max(np.abs(g_cpu)))}
+        parity = {"nlml_rel": abs(f[0] - f_cpu) / abs(f_cpu),
+                  "grad_rel": float(np.max(np.abs(g[0] - g_cpu)) / np.max(np.abs(g_cpu)))}
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": dev_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
-            "config": {"workload": "C2: GPS3 ARD NLML+gradient, n=2000 d=20 c=1000 (BASELINE.json configs[1])",
-                       "n": int(n), "d": int(d), "hyperparameters": int(par0.size), "partition": f"independent fits x{world}",
-                       "l2": "per-evaluation working set 5 n x n FP64 matrices = 160 MB > 126 MB L2 (no flush needed)"},
+            "config": config_dict(B, world, n, d, par0.size),
             "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                     "ms_per_step": 1e3 * e2e_s / K},
             "gpu_launches": int(launches),
             "clocks": clocks,
             "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s",
                          "frac": achieved / peak_tf if peak_tf else None, "traffic": None,
-                         "kernel": "evaluation graph (1 launch = 1 NLML+gradient evaluation, %d kernel nodes)" % (launches // max(K, 1)),
-                         "algorithmic_flops_per_launch": flops,
+                         "kernel": "evaluation graph (1 launch = %d NLML+gradient evaluations, %d kernel nodes)"
+                                   % (B, launches // max(K, 1)),
+                         "algorithmic_flops_per_launch": B * flops,
                          "peak_source": "cublasDgemm 8192^3 via torch.matmul(float64), best of 5, measured in this run "
                                         "(MEASURED_PEAKS.json has no FP64 figure)"},
             "dmma_gemm_8192": {"tflops": 2.0 * 8192 ** 3 / (gemm_ms * 1e-3) / 1e12,
                                "frac_of_cublas_dgemm": (2.0 * 8192 ** 3 / (gemm_ms * 1e-3) / 1e12) / peak_tf if peak_tf else None},
             "stages_ms": {"gram": stages[0], "cholesky": stages[1], "tri_inverse": stages[2], "kinv": stages[3],
                           "wk_grad": stages[4], "total": stages[7]},
+            "single_fit": {"nlml_grad_ms": single_ms, "nlml_ms": single_nlml_ms, "evals_per_sec": 1e3 / single_ms,
+                           "tflops": flops / (single_ms * 1e-3) / 1e12},
             "cpu_baseline": {"value": cpu_val, "unit": UNIT, "cores": cpu_threads(), "kind": "port",
-                             "sample": f"{cnt} full evaluations of the same C2 workload",
+                             "sample": f"{cnt} full evaluations of one fit of the same C2 workload",
                              "note": "reference algorithm restated in numpy (as-written op sequence); R unavailable in image"},
             "parity_vs_oracle": parity,
         }
@@ -307,9 +345,10 @@ def run_gpu(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--steps", type=int, default=30)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=32, help="independent fits evaluated per step on each GPU")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)

@@ -101,6 +101,8 @@ struct gps_handle_s {
   double last_ms = 0.0;
   int last_pivot = 0;
   int force_tile = -1;          // developer override of the GEMM tile config (GPS_TILE=0|1|2)
+  int large_min_dim = 1 << 30;  // 128 x 128 tiles only when both M and N reach this (GPS_LARGE_MIN_DIM); measured:
+                                // the 4-warp 64 x 64 tile (3 CTAs/SM) wins at every size up to 8192^3, alone and batched
   std::string err;
   cudaError_t cu_err = cudaSuccess;
 };
@@ -200,7 +202,7 @@ void gemm(H* h, const GemmParams& p, const Epi& epi) {
   // gated by its longest tile, so ask for several waves before using the 128 x 128 config
   const long long need = (p.klo_m || p.klo_n || p.khi_m) ? 600 : 100;
   cudaError_t e;
-  int choice = (tl >= need && p.N >= 96) ? 2 : 0;
+  int choice = (tl >= need && p.N >= 96 && p.M >= h->large_min_dim && p.N >= h->large_min_dim) ? 2 : 0;
   if (h->force_tile >= 0) choice = h->force_tile;
   if (choice == 2)
     e = launch_gemm<CfgLarge, A_KC, B_KC, Epi>(p, epi, h->batch, h->st);
@@ -270,21 +272,29 @@ void enqueue_cov(H* h, const double* Za, int n1, int lda, long long sA, const do
 }
 
 // Panel launch: every CTA redoes the 64 x 64 chain, so the row tiling trades redundancy against
-// latency.  A lone fit gets many 32-row CTAs (the GPU is otherwise idle); a batch gets 128-row
-// tiles and, once the grid is full, several tiles per CTA.  +1 CTA publishes L11 / X11.
+// latency.  A small cost model (measured: chain ~17 us, panel solve ~1.4 us per 32-row tile and
+// ~5.2 us per 128-row tile, one CTA per SM) picks the tile height RT and the tiles per CTA T that
+// minimise  waves * (chain + T * tile).  +1 CTA per fit publishes L11 / X11.
 void launch_panel(H* h, int e0, int nb, int M, long long* dbg) {
   const int B = h->batch;
-  const long long small_ctas = (long long)ceil_div(M > 0 ? M : 1, 32) * B;
-  if (small_ctas <= 2 * 148) {
-    dim3 grid(ceil_div(M > 0 ? M : 1, 32) + 1, B);
-    panel_kernel<32><<<grid, 256, PANEL_SMEM, h->st>>>(h->Ky, h->L, h->Linv, h->ld, h->strideM, e0, nb, M, 1, h->info, dbg);
-  } else {
-    int tiles = ceil_div(M > 0 ? M : 1, 128);
-    int T = 1;
-    while ((long long)ceil_div(tiles, T) * B > 4 * 148 && T < tiles) T++;
-    dim3 grid(ceil_div(tiles, T) + 1, B);
-    panel_kernel<128><<<grid, 256, PANEL_SMEM, h->st>>>(h->Ky, h->L, h->Linv, h->ld, h->strideM, e0, nb, M, T, h->info, dbg);
+  const int Mr = M > 0 ? M : 1;
+  double best = 1e300;
+  int best_rt = 32, best_T = 1;
+  for (int rt = 32; rt <= 128; rt += 96) {
+    const int tiles = ceil_div(Mr, rt);
+    const double t_tile = (rt == 32) ? 1.4 : 5.2;
+    for (int T = 1; T <= tiles; T++) {
+      const long long ctas = (long long)(ceil_div(tiles, T) + 1) * B;
+      const double cost = (double)ceil_div((int)ctas, 148) * (17.0 + T * t_tile);
+      if (cost < best - 1e-9) { best = cost; best_rt = rt; best_T = T; }
+    }
   }
+  const int tiles = ceil_div(Mr, best_rt);
+  dim3 grid(ceil_div(tiles, best_T) + 1, B);
+  if (best_rt == 32)
+    panel_kernel<32><<<grid, 256, PANEL_SMEM, h->st>>>(h->Ky, h->L, h->Linv, h->ld, h->strideM, e0, nb, M, best_T, h->info, dbg);
+  else
+    panel_kernel<128><<<grid, 256, PANEL_SMEM, h->st>>>(h->Ky, h->L, h->Linv, h->ld, h->strideM, e0, nb, M, best_T, h->info, dbg);
   LAUNCHED(h);
 }
 
@@ -409,7 +419,8 @@ void enqueue_grad(H* h) {
     e.rs = h->rs; e.ldn = h->ld;
     // the tile config decides the number of m tiles: mirror gemm()'s choice
     long long tl = (long long)ceil_div(n, 128) * ceil_div(h->d + 1, 128) * h->batch;
-    bool large = (tl >= 100 && h->d + 1 >= 96);
+    bool large = (tl >= 100 && h->d + 1 >= 96 && n >= h->large_min_dim && h->d + 1 >= h->large_min_dim);
+    if (h->force_tile >= 0) large = (h->force_tile == 2);
     e.mtiles = ceil_div(n, large ? 128 : 64);
     h->mtiles_grad = e.mtiles;
     gemm<false, true>(h, p, e);
@@ -602,6 +613,7 @@ int gps_create_batch(int device, int batch, gps_handle* out) {
   }
   H* h = new H();
   if (const char* ev = getenv("GPS_TILE")) h->force_tile = atoi(ev);
+  if (const char* ev = getenv("GPS_LARGE_MIN_DIM")) h->large_min_dim = atoi(ev);
   h->device = device;
   h->batch = batch;
   if (cudaSetDevice(device) != cudaSuccess || cudaStreamCreateWithFlags(&h->st, cudaStreamNonBlocking) != cudaSuccess ||

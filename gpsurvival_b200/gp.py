@@ -59,7 +59,7 @@ class Fit:
         self.opts = (cov_form, mean_form, noise_corr, ard_mode)
 
     def set_data(self, X, y, events=None):
-        if self.batch == 1:
+        if np.ndim(X) == 2:
             X = f64(X)
             n, d = X.shape
         else:   # [batch, n, d] -> each problem column-major
@@ -120,7 +120,7 @@ class Fit:
 
     def predict(self, par, Xstar, reuse_model=False):
         p, ln = self._par(par)
-        if self.batch == 1:
+        if np.ndim(Xstar) == 2:
             Xs = f64(Xstar)
             m = Xs.shape[0]
         else:
