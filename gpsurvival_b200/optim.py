@@ -21,19 +21,27 @@ BIG = 1.0e35
 RELTOL = math.sqrt(np.finfo(np.float64).eps)
 
 
-def _safe(fn, x):
-    f = float(fn(x))
+def _fin(f):
+    f = float(f)
     return f if math.isfinite(f) else BIG
 
 
-def nelder_mead(fn, par, maxit=500, abstol=-math.inf, reltol=RELTOL, alpha=1.0, beta=0.5, gamma=2.0):
+# The optimisers are written as GENERATORS that yield the point they want evaluated and receive
+# (value, gradient-or-None) back.  A sequential driver (nelder_mead / bfgs below) feeds them from
+# fn / gr; the batched driver (gpsurvival_b200/batchfit.py) advances many of them in lock-step
+# and serves all their requests with ONE batched GPU evaluation per tick — each fit still follows
+# exactly the trajectory the sequential optimiser would.
+def nelder_mead_steps(par, maxit=500, abstol=-math.inf, reltol=RELTOL, alpha=1.0, beta=0.5, gamma=2.0):
     """Nelder-Mead as R's nmmin runs it.  The simplex is an (n+1) x n array of vertices with a
-    parallel array of function values; ``lo``/``hi`` are the best / worst vertex indices."""
+    parallel array of function values; ``lo``/``hi`` are the best / worst vertex indices.
+    Yields ("f", x); expects (f, _) via send(); returns the optim() result dict."""
     x0 = np.array(par, dtype=np.float64).ravel()
     n = x0.size
     if maxit <= 0:
-        return {"par": x0, "value": float(fn(x0)), "counts": 0, "convergence": 0}
-    f0 = float(fn(x0))
+        f0, _ = yield ("f", x0.copy())
+        return {"par": x0, "value": float(f0), "counts": 0, "convergence": 0}
+    f0, _ = yield ("f", x0.copy())
+    f0 = float(f0)
     if not math.isfinite(f0):
         raise RuntimeError("function cannot be evaluated at initial parameters")
     evals = 1
@@ -59,7 +67,8 @@ def nelder_mead(fn, par, maxit=500, abstol=-math.inf, reltol=RELTOL, alpha=1.0, 
         if need_vertices:
             for j in range(n + 1):
                 if j != lo:
-                    F[j] = _safe(fn, V[j].copy())
+                    fv, _ = yield ("f", V[j].copy())
+                    F[j] = _fin(fv)
                     evals += 1
             need_vertices = False
         # best / worst exactly as nmmin scans them (first strict improvement wins)
@@ -80,11 +89,13 @@ def nelder_mead(fn, par, maxit=500, abstol=-math.inf, reltol=RELTOL, alpha=1.0, 
             cen = cen + V[j]
         cen = cen / n
         xr = (1.0 + alpha) * cen - alpha * V[hi]
-        fr = _safe(fn, xr.copy())
+        fv, _ = yield ("f", xr.copy())
+        fr = _fin(fv)
         evals += 1
         if fr < vl:
             xe = gamma * xr + (1.0 - gamma) * cen
-            fe = _safe(fn, xe.copy())
+            fv, _ = yield ("f", xe.copy())
+            fe = _fin(fv)
             evals += 1
             if fe < fr:
                 V[hi], F[hi] = xe, fe
@@ -94,7 +105,8 @@ def nelder_mead(fn, par, maxit=500, abstol=-math.inf, reltol=RELTOL, alpha=1.0, 
             if fr < vh:
                 V[hi], F[hi] = xr, fr
             xc = (1.0 - beta) * V[hi] + beta * cen
-            fc = _safe(fn, xc.copy())
+            fv, _ = yield ("f", xc.copy())
+            fc = _fin(fv)
             evals += 1
             if fc < F[hi]:
                 V[hi], F[hi] = xc, fc
@@ -117,20 +129,26 @@ def nelder_mead(fn, par, maxit=500, abstol=-math.inf, reltol=RELTOL, alpha=1.0, 
     return {"par": V[lo].copy(), "value": float(F[lo]), "counts": evals, "convergence": fail}
 
 
-def bfgs(fn, gr, par, maxit=100, abstol=-math.inf, reltol=RELTOL):
+def bfgs_steps(par, maxit=100, abstol=-math.inf, reltol=RELTOL):
     """Variable-metric (BFGS) minimiser as R's vmmin runs it, with the inverse-Hessian
-    approximation kept as a full symmetric matrix."""
+    approximation kept as a full symmetric matrix.  Yields ("f", x) for line-search values and
+    ("g", x) for gradients; expects (f, g) via send() — when the driver already returned a
+    gradient with the accepted line-search value it is reused and no ("g", x) request is made."""
     stepredn, acctol, reltest = 0.2, 1.0e-4, 10.0
     b = np.array(par, dtype=np.float64).ravel()
     n = b.size
     if maxit <= 0:
-        return {"par": b, "value": float(fn(b)), "counts": (0, 0), "convergence": 0}
-    f = float(fn(b))
+        f, _ = yield ("f", b.copy())
+        return {"par": b, "value": float(f), "counts": (0, 0), "convergence": 0}
+    f, g_with_f = yield ("f", b.copy())
+    f = float(f)
     if not math.isfinite(f):
         raise RuntimeError("initial value in 'vmmin' is not finite")
     fmin = f
     nf = ng = 1
-    g = np.array(gr(b), dtype=np.float64).ravel()
+    if g_with_f is None:
+        _, g_with_f = yield ("g", b.copy())
+    g = np.array(g_with_f, dtype=np.float64).ravel()
     it = 1
     ilast = ng
     Bm = np.eye(n)
@@ -148,7 +166,8 @@ def bfgs(fn, gr, par, maxit=100, abstol=-math.inf, reltol=RELTOL):
                 b = x_old + steplength * t
                 count = int(np.sum((reltest + x_old) == (reltest + b)))
                 if count < n:
-                    f = float(fn(b))
+                    f, g_with_f = yield ("f", b.copy())
+                    f = float(f)
                     nf += 1
                     accpoint = math.isfinite(f) and f <= fmin + gradproj * steplength * acctol
                     if not accpoint:
@@ -161,7 +180,9 @@ def bfgs(fn, gr, par, maxit=100, abstol=-math.inf, reltol=RELTOL):
                 fmin = f
             if count < n:
                 fmin = f
-                g = np.array(gr(b), dtype=np.float64).ravel()
+                if g_with_f is None:
+                    _, g_with_f = yield ("g", b.copy())
+                g = np.array(g_with_f, dtype=np.float64).ravel()
                 ng += 1
                 it += 1
                 t = steplength * t
@@ -190,6 +211,36 @@ def bfgs(fn, gr, par, maxit=100, abstol=-math.inf, reltol=RELTOL):
         if count == n and ilast == ng:
             break
     return {"par": b, "value": float(fmin), "counts": (nf, ng), "convergence": 0 if it < maxit else 1}
+
+
+def _drive(gen, fn, gr):
+    """Run an optimiser generator to completion with plain callables."""
+    try:
+        kind, x = next(gen)
+        while True:
+            if kind == "f":
+                kind, x = gen.send((fn(x), None))
+            else:
+                kind, x = gen.send((None, gr(x)))
+    except StopIteration as stop:
+        return stop.value
+
+
+def nelder_mead(fn, par, maxit=500, **kw):
+    return _drive(nelder_mead_steps(par, maxit=maxit, **kw), fn, None)
+
+
+def bfgs(fn, gr, par, maxit=100, **kw):
+    return _drive(bfgs_steps(par, maxit=maxit, **kw), fn, gr)
+
+
+def optim_steps(par, method="Nelder-Mead", maxit=None):
+    """Generator form of optim() for the batched driver."""
+    if method == "Nelder-Mead":
+        return nelder_mead_steps(par, maxit=500 if maxit is None else maxit)
+    if method == "BFGS":
+        return bfgs_steps(par, maxit=100 if maxit is None else maxit)
+    raise NotImplementedError(f"optim method {method!r} (Nelder-Mead and BFGS are restated)")
 
 
 def optim(par, fn, gr=None, method="Nelder-Mead", maxit=None):

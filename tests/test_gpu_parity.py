@@ -351,3 +351,27 @@ def test_full_size_properties(name):
     Ks = gp.CovFunc(X, Xs, X, None, None, 0.8, np.exp(par[2:2 + d]), cfg.cov_form)
     assert relmax(mu, Ks.T @ alpha) <= TOL_PRED
     fit.close()
+
+
+# ---- batched whole fits (restarts / folds in lock-step on one GPU) -------------------------------------
+@pytest.mark.parametrize("model,nc,method", [("GPS1", False, "Nelder-Mead"), ("GPS2", "noiseCorrLearned", "Nelder-Mead"),
+                                             ("GPS3", "noiseCorrVec", "Nelder-Mead"), ("GPS3", "noiseCorrVec", "BFGS")])
+def test_batched_fits_follow_sequential_apply_gp(model, nc, method):
+    from gpsurvival_b200 import batchfit
+    B = 4
+    pbs = [synth.make_problem(70, 15, 2, 28, 900 + b) for b in range(B)]
+    params = dict(modelType="survival", noiseCorr=nc, optimType=method, maxit=100, maxitSurvival=10 if method == "Nelder-Mead" else 4,
+                  meanFuncForm="Zero", covFuncForm="ARD" if method == "BFGS" else "SqExp", tolerance=0.02, maxCount=9,
+                  logHypStart=synth.start_log_hyp(2, "ARD" if method == "BFGS" else "SqExp"), burnIn=False, imposePriors=False)
+    res = batchfit.apply_gp_batch(pbs, params)
+    counts = set()
+    for b in range(B):
+        gp.SESSION.reset()
+        ref = gp.ApplyGP(pbs[b], {"dataSource": "Generate"}, params)
+        counts.add(ref["count"])
+        assert res[b]["count"] == ref["count"]
+        assert relmax(res[b]["objectiveTable"], ref["objectiveTable"]) <= 1e-7
+        assert relmax(res[b]["funcMeanPred"], ref["funcMeanPred"]) <= 1e-6
+        assert relmax(res[b]["varData"], ref["varData"]) <= 1e-6
+        assert relmax(res[b]["trainingSetPredictions"], ref["trainingSetPredictions"]) <= 1e-6
+    gp.SESSION.reset()
