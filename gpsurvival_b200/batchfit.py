@@ -40,9 +40,9 @@ def _run_optimisers(fit, starts, method, maxit, active):
     while any(r is not None for r in req):
         want_grad = (method == "BFGS") or any(r is not None and r[0] == "g" for r in req)
         if want_grad:
-            f, g = fit.nlml_grad(point)
+            f, g = fit.nlml_grad(point, not_pd="inf")
         else:
-            f, g = fit.nlml(point), None
+            f, g = fit.nlml(point, not_pd="inf"), None
         f = np.atleast_1d(f)
         ticks += 1
         for b in range(B):

@@ -100,6 +100,7 @@ struct gps_handle_s {
   long long seq_launches = 0;   // launches issued by the sequence being recorded
   double last_ms = 0.0;
   int last_pivot = 0;
+  std::vector<int> pivots;      // per-fit failing pivot of the last evaluation (0 = factorised)
   int force_tile = -1;          // developer override of the GEMM tile config (GPS_TILE=0|1|2)
   int large_min_dim = 1 << 30;  // 128 x 128 tiles only when both M and N reach this (GPS_LARGE_MIN_DIM); measured:
                                 // the 4-warp 64 x 64 tile (3 CTAs/SM) wins at every size up to 8192^3, alone and batched
@@ -546,6 +547,7 @@ int fetch_info(H* h) {
   float ms = 0.f;
   if (cudaEventElapsedTime(&ms, h->ev0, h->ev1) == cudaSuccess) h->last_ms = ms;
   else (void)cudaGetLastError();
+  h->pivots.assign(h->pin_info, h->pin_info + h->batch);
   for (int b = 0; b < h->batch; b++)
     if (h->pin_info[b] != 0) {
       h->last_pivot = h->pin_info[b];
@@ -832,8 +834,13 @@ int gps_nlml(gps_handle h, const double* par, int len, double* nlml_out) {
   if (rc) return rc;
   CK(h, cudaMemcpyAsync(h->pin, h->d_nlml, sizeof(double) * h->batch, cudaMemcpyDeviceToHost, h->st));
   rc = fetch_info(h);
-  if (rc) return rc;
+  if (rc && rc != GPS_ERR_NOT_PD) return rc;
   memcpy(nlml_out, h->pin, sizeof(double) * h->batch);
+  if (rc == GPS_ERR_NOT_PD) {   // outputs stay usable: +Inf marks the fits that failed to factorise
+    for (int b = 0; b < h->batch; b++)
+      if (h->pivots[b] != 0) nlml_out[b] = INFINITY;
+    return rc;
+  }
   remember_fact(h, par, len, 1);
   return GPS_OK;
 }
@@ -863,9 +870,17 @@ int gps_nlml_grad(gps_handle h, const double* par, int len, double* nlml_out, do
   CK(h, cudaMemcpyAsync(h->pin, h->d_nlml, sizeof(double) * h->batch, cudaMemcpyDeviceToHost, h->st));
   CK(h, cudaMemcpyAsync(h->pin + h->batch, h->d_grad, sizeof(double) * tot, cudaMemcpyDeviceToHost, h->st));
   rc = fetch_info(h);
-  if (rc) return rc;
+  if (rc && rc != GPS_ERR_NOT_PD) return rc;
   if (nlml_out) memcpy(nlml_out, h->pin, sizeof(double) * h->batch);
   memcpy(grad_out, h->pin + h->batch, sizeof(double) * tot);
+  if (rc == GPS_ERR_NOT_PD) {
+    for (int b = 0; b < h->batch; b++)
+      if (h->pivots[b] != 0) {
+        if (nlml_out) nlml_out[b] = INFINITY;
+        for (int k = 0; k < len; k++) grad_out[(size_t)b * len + k] = NAN;
+      }
+    return rc;
+  }
   remember_fact(h, par, len, 2);
   return GPS_OK;
 }
@@ -1146,6 +1161,12 @@ int gps_cov(gps_handle h, const double* X1, int n1, const double* X2, int n2, in
   CKC(cudaStreamSynchronize(h->st));
 #undef CKC
   cleanup();
+  return GPS_OK;
+}
+
+int gps_batch_pivots(gps_handle h, int* pivots_out) {
+  if (!h || !pivots_out) return fail(h, GPS_ERR_ARG, "gps_batch_pivots: bad arguments");
+  for (int b = 0; b < h->batch; b++) pivots_out[b] = (b < (int)h->pivots.size()) ? h->pivots[b] : 0;
   return GPS_OK;
 }
 

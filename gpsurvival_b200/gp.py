@@ -84,18 +84,29 @@ class Fit:
         p = np.ascontiguousarray(np.asarray(par, dtype=np.float64)).reshape(self.batch, -1)
         return p, p.shape[1]
 
-    def nlml(self, par):
+    def nlml(self, par, not_pd="raise"):
+        """``not_pd='inf'``: a fit whose Ky is not positive definite returns +Inf instead of raising
+        (what an optimiser wants: nmmin / vmmin treat a non-finite value as a rejected point)."""
         p, ln = self._par(par)
         out = np.empty(self.batch)
-        self._ck(self.lib.gps_nlml(self.h, dptr(p), ln, dptr(out)))
+        rc = self.lib.gps_nlml(self.h, dptr(p), ln, dptr(out))
+        if not (rc == _lib.GPS_ERR_NOT_PD and not_pd == "inf"):
+            self._ck(rc)
         return out if self.batch > 1 else float(out[0])
 
-    def nlml_grad(self, par):
+    def nlml_grad(self, par, not_pd="raise"):
         p, ln = self._par(par)
         out = np.empty(self.batch)
         g = np.empty((self.batch, ln))
-        self._ck(self.lib.gps_nlml_grad(self.h, dptr(p), ln, dptr(out), dptr(g)))
+        rc = self.lib.gps_nlml_grad(self.h, dptr(p), ln, dptr(out), dptr(g))
+        if not (rc == _lib.GPS_ERR_NOT_PD and not_pd == "inf"):
+            self._ck(rc)
         return (out, g) if self.batch > 1 else (float(out[0]), g[0])
+
+    def pivots(self):
+        out = (C.c_int * self.batch)()
+        self._ck(self.lib.gps_batch_pivots(self.h, out))
+        return list(out)
 
     def finalize(self, par, want_K=False, want_L=False):
         p, ln = self._par(par)
@@ -339,7 +350,9 @@ def GPRegression(logHyp, parameterStructure, trainingTestStructure, logHypNoiseC
     _reject_priors(ps.get("imposePriors", False))
     vec = _flatten(logHyp, d, meanFuncForm, noiseCorr, logHypNoiseCorrection)
     fit = SESSION.bind(X, y, events, covFuncForm, meanFuncForm, noiseCorr, logHypNoiseCorrection)
-    opt = _optim.optim(vec, fn=lambda p: fit.nlml(p), gr=lambda p: fit.nlml_grad(p)[1],
+    # a non-positive-definite Ky inside optim is reported to the optimiser as +Inf (the reference
+    # would try Matrix::nearPD there, ForOptimisationLog.R:43-51 — out of scope)
+    opt = _optim.optim(vec, fn=lambda p: fit.nlml(p, not_pd="inf"), gr=lambda p: fit.nlml_grad(p, not_pd="inf")[1],
                        method=ps["optimType"], maxit=maxit)                              # :28-31
     vec = opt["par"]
     fin = fit.finalize(vec, want_K=want_matrices, want_L=want_matrices)                  # :60-71

@@ -157,8 +157,8 @@ def bfgs_steps(par, maxit=100, abstol=-math.inf, reltol=RELTOL):
             Bm = np.eye(n)
         x_old = b.copy()
         g_old = g.copy()
-        t = np.array([-sum(Bm[i, j] * g[j] for j in range(n)) for i in range(n)])
-        gradproj = float(sum(t[i] * g[i] for i in range(n)))
+        t = -(Bm @ g)            # numpy BLAS: same maths as vmmin's loops, O(n^2) without Python overhead
+        gradproj = float(t @ g)
         if gradproj < 0.0:
             steplength = 1.0
             accpoint = False
@@ -187,10 +187,10 @@ def bfgs_steps(par, maxit=100, abstol=-math.inf, reltol=RELTOL):
                 it += 1
                 t = steplength * t
                 c = g - g_old
-                d1 = float(sum(t[i] * c[i] for i in range(n)))
+                d1 = float(t @ c)
                 if d1 > 0:
-                    xv = np.array([sum(Bm[i, j] * c[j] for j in range(n)) for i in range(n)])
-                    d2 = 1.0 + float(sum(xv[i] * c[i] for i in range(n))) / d1
+                    xv = Bm @ c
+                    d2 = 1.0 + float(xv @ c) / d1
                     Bm = Bm + (d2 * np.outer(t, t) - np.outer(xv, t) - np.outer(t, xv)) / d1
                 else:
                     ilast = ng

@@ -52,6 +52,11 @@ typedef enum {
 const char* gps_version(void);
 const char* gps_last_error(gps_handle h);      /* h may be NULL: last error of the calling thread's stateless call */
 int gps_last_pivot(gps_handle h);              /* failing pivot of the last GPS_ERR_NOT_PD (1-based), else 0 */
+/* Per-fit failing pivot of the last evaluation (0 = factorised), `batch` ints.  When gps_nlml /
+ * gps_nlml_grad return GPS_ERR_NOT_PD their outputs are still filled: +Inf (NaN gradient) for the
+ * fits that failed, valid values for the others — so an optimiser can reject just that point, where
+ * the reference would fall back to Matrix::nearPD (ForOptimisationLog.R:43-51). */
+int gps_batch_pivots(gps_handle h, int* pivots_out);
 
 /* ---- lifetime ----------------------------------------------------------------------- */
 /* One handle = one fit (one trainingTestStructure) on one device.  `batch` > 1 makes it a

@@ -375,3 +375,22 @@ def test_batched_fits_follow_sequential_apply_gp(model, nc, method):
         assert relmax(res[b]["varData"], ref["varData"]) <= 1e-6
         assert relmax(res[b]["trainingSetPredictions"], ref["trainingSetPredictions"]) <= 1e-6
     gp.SESSION.reset()
+
+
+def test_not_pd_is_per_fit_and_non_fatal_for_optimisers():
+    pb = synth.make_problem(40, 5, 2, 10, 1)
+    X, y, ev = pb["trainingData"], np.log(pb["trainingTargets"]), pb["events"]
+    Xd = np.vstack([X, X])                       # duplicate rows: singular without noise
+    yd, evd = np.concatenate([y, y]), np.concatenate([ev, ev])
+    bf = gp.Fit(0, batch=2)
+    bf.set_data(np.stack([Xd, Xd]), np.stack([yd, yd]), np.stack([evd, evd]))
+    par = np.array([[-800.0, 0.0, 0.0], np.log([0.2, 0.8, 2.0])])
+    with pytest.raises(gp.NotPositiveDefinite):
+        bf.nlml(par)
+    f = bf.nlml(par, not_pd="inf")
+    assert np.isinf(f[0]) and abs(f[1] - orc.nlml(par[1], Xd, yd, evd)) <= 1e-9 * abs(f[1])
+    piv = bf.pivots()
+    assert piv[0] >= 1 and piv[1] == 0
+    f2, g2 = bf.nlml_grad(par, not_pd="inf")
+    assert np.isinf(f2[0]) and np.all(np.isnan(g2[0])) and relmax(g2[1], orc.nlml_grad(par[1], Xd, yd, evd)) <= 1e-9
+    bf.close()
