@@ -28,6 +28,15 @@ def _run_optimisers(fit, starts, method, maxit, active):
     """Advance one optimiser per fit to completion.  Returns list of optim() result dicts (None
     for inactive fits).  Evaluations per tick: one batched call."""
     B = starts.shape[0]
+    if method == "BFGS":
+        # dense inverse-Hessian state of all fits in one GPU tensor, vmmin's control flow as masks
+        from .batch_bfgs import batch_bfgs
+
+        def evaluate(P):
+            f, g = fit.nlml_grad(P, not_pd="inf")
+            return np.atleast_1d(f), np.atleast_2d(g)
+
+        return batch_bfgs(evaluate, starts, maxit=maxit, active=active, device=f"cuda:{fit.device}")
     gens = [(_optim.optim_steps(starts[b], method, maxit) if active[b] else None) for b in range(B)]
     req = [None] * B
     results = [None] * B

@@ -32,6 +32,7 @@ class Fit:
         self.lib = _lib.load()
         self.h = C.c_void_p()
         self.batch = batch
+        self.device = device
         check(self.lib.gps_create_batch(device, batch, C.byref(self.h)))
         self.n = self.d = 0
         self.opts = ("SqExp", "Zero", False, "intended")

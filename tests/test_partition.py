@@ -95,3 +95,36 @@ def test_two_rank_gloo_sharded_sweep():
         pb = synth.make_problem(n, 4, d, n // 3, 500 + i)
         ref = orc.nlml(np.log([0.2, 0.8, 1.7 * np.sqrt(d)]), pb["trainingData"], np.log(pb["trainingTargets"]), pb["events"])
         assert got[0][i][1] == ref
+
+
+def test_batch_bfgs_follows_sequential_vmmin():
+    """The lock-step batched BFGS reproduces, fit by fit, the sequential restatement of R's vmmin
+    (itself pinned on R's documented example in test_oracle.py)."""
+    from scipy.optimize import rosen, rosen_der
+    from gpsurvival_b200 import optim
+    from gpsurvival_b200.batch_bfgs import batch_bfgs
+    rng = np.random.default_rng(3)
+    for n in (2, 6):
+        x0 = np.vstack([np.r_[-1.2, 1.0, np.zeros(n - 2)]] + [rng.uniform(-1.5, 1.5, n) for _ in range(5)])
+        calls = {"n": 0}
+
+        def evaluate(P):
+            calls["n"] += 1
+            return np.array([rosen(p) for p in P]), np.array([rosen_der(p) for p in P])
+
+        for maxit in (7, 200):
+            res, ticks = batch_bfgs(evaluate, x0, maxit=maxit, device="cpu")
+            for i in range(x0.shape[0]):
+                ref = optim.bfgs(rosen, rosen_der, x0[i], maxit=maxit)
+                assert tuple(res[i]["counts"]) == tuple(ref["counts"]), (n, maxit, i)
+                assert res[i]["convergence"] == ref["convergence"]
+                assert abs(res[i]["value"] - ref["value"]) <= 1e-9 * max(1.0, abs(ref["value"]))
+                assert np.allclose(res[i]["par"], ref["par"], rtol=1e-8, atol=1e-10)
+    r, _ = batch_bfgs(evaluate, np.array([[-1.2, 1.0]]), maxit=100, device="cpu")
+    assert tuple(r[0]["counts"]) == (110, 43) and abs(r[0]["value"] - 9.594956e-18) < 5e-24    # R's example(optim)
+    # inactive fits are left alone; non-finite values are rejected points, not errors
+    def ev2(P):
+        f = np.array([rosen(p) if p[0] < 1.05 else np.inf for p in P])
+        return f, np.array([rosen_der(p) for p in P])
+    r2, _ = batch_bfgs(ev2, x0[:3, :2] if x0.shape[1] >= 2 else x0, maxit=30, active=[True, False, True], device="cpu")
+    assert r2[1] is None and r2[0] is not None and np.isfinite(r2[0]["value"])
