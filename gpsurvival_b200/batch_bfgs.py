@@ -81,7 +81,9 @@ def batch_bfgs(evaluate, x0, maxit=100, abstol=-math.inf, reltol=RELTOL, active=
             ti = T(idx).long()
             X[ti] = b[ti]
             c[ti] = g[ti]
-            t[ti] = -torch.bmm(Bm[ti], g[ti].unsqueeze(2)).squeeze(2)
+            # matvec over the whole batch in place of gathering Bm[ti] (a multi-GB copy at large n)
+            t_all = -torch.bmm(Bm, g.unsqueeze(2)).squeeze(2)
+            t[ti] = t_all[ti]
             gp_ = (t[ti] * g[ti]).sum(dim=1).cpu().numpy()
             gradproj[idx] = gp_
             down = idx[gp_ < 0.0]
@@ -149,15 +151,21 @@ def batch_bfgs(evaluate, x0, maxit=100, abstol=-math.inf, reltol=RELTOL, active=
             D1_np = D1.cpu().numpy()
             pos = D1_np > 0
             if np.any(pos):
+                # B += (D2 t t' - X t' - t X') / D1 as ONE in-place rank-3 update of the whole state
+                # tensor; fits that do not update this tick get zero coefficients.
+                w = torch.zeros(B, dtype=torch.float64, device=dev)
                 pi = ui[torch.as_tensor(pos, device=dev)]
-                xv = torch.bmm(Bm[pi], c[pi].unsqueeze(2)).squeeze(2)
-                d1 = (t[pi] * c[pi]).sum(dim=1)
-                d2 = 1.0 + (xv * c[pi]).sum(dim=1) / d1
-                tt = t[pi]
-                upd_m = (d2.view(-1, 1, 1) * tt.unsqueeze(2) * tt.unsqueeze(1)
-                         - xv.unsqueeze(2) * tt.unsqueeze(1) - tt.unsqueeze(2) * xv.unsqueeze(1)) / d1.view(-1, 1, 1)
-                Bm[pi] = Bm[pi] + upd_m
-                X[pi] = xv
+                w[pi] = 1.0
+                xv_all = torch.bmm(Bm, c.unsqueeze(2)).squeeze(2)
+                d1_all = (t * c).sum(dim=1)
+                d1_safe = torch.where(w > 0, d1_all, torch.ones_like(d1_all))
+                d2_all = 1.0 + (xv_all * c).sum(dim=1) / d1_safe
+                s1 = (w * d2_all / d1_safe).unsqueeze(1)
+                s2 = (w / d1_safe).unsqueeze(1)
+                U = torch.stack([s1 * t, -s2 * xv_all, -s2 * t], dim=2)      # [B, n, 3]
+                V = torch.stack([t, t, xv_all], dim=1)                       # [B, 3, n]
+                Bm.baddbmm_(U, V)
+                X[pi] = xv_all[pi]
             for k, i in enumerate(upd):
                 if not pos[k]:
                     ilast[i] = ng[i]
