@@ -78,7 +78,7 @@ struct TileCfg {
   static constexpr int WM = BM / WARPS_M, WN = BN / WARPS_N;
   static constexpr int FM = WM / 8, FN = WN / 8;
   static_assert(BM % (8 * WARPS_M) == 0 && BN % (8 * WARPS_N) == 0, "warp tiling");
-  static_assert(BK % 4 == 0 && BM % BK == 0, "k tiling");
+  static_assert(BK % 4 == 0 && BM % BK == 0 && BK % 16 == 0, "k tiling");
 };
 
 // Accumulator view handed to epilogues: acc[mi][ni][0..1] <-> element
@@ -393,7 +393,9 @@ struct EpiColDot {
 // ---------------------------------------------------------------------------------------
 using CfgLarge = TileCfg<128, 128, 16, 2, 4, 4>;
 using CfgSmall = TileCfg<64, 64, 16, 2, 2, 4>;
-using CfgMid = TileCfg<64, 64, 16, 4, 2, 4>;     // same tile, 8 warps: two warps per scheduler even at 1 CTA/SM
+using CfgMid = TileCfg<64, 64, 16, 4, 2, 4>;
+using CfgS3 = TileCfg<64, 64, 16, 2, 2, 3>;      // experiments: shallower pipeline => more CTAs per SM
+using CfgK32 = TileCfg<64, 64, 32, 2, 2, 3>;     // experiments: half as many barriers per k     // same tile, 8 warps: two warps per scheduler even at 1 CTA/SM
 
 template <class Cfg, bool A_KC, bool B_KC, class Epi>
 cudaError_t launch_gemm(const GemmParams& p, const Epi& epi, int batch, cudaStream_t st) {

@@ -203,12 +203,17 @@ void gemm(H* h, const GemmParams& p, const Epi& epi) {
   // gated by its longest tile, so ask for several waves before using the 128 x 128 config
   const long long need = (p.klo_m || p.klo_n || p.khi_m) ? 600 : 100;
   cudaError_t e;
-  int choice = (tl >= need && p.N >= 96 && p.M >= h->large_min_dim && p.N >= h->large_min_dim) ? 2 : 0;
+  // default: 64 x 64 x 16 tile, 4 warps, 3-stage cp.async pipeline (4 CTAs/SM) — measured best at every size
+  int choice = (tl >= need && p.N >= 96 && p.M >= h->large_min_dim && p.N >= h->large_min_dim) ? 2 : 3;
   if (h->force_tile >= 0) choice = h->force_tile;
   if (choice == 2)
     e = launch_gemm<CfgLarge, A_KC, B_KC, Epi>(p, epi, h->batch, h->st);
   else if (choice == 1)
     e = launch_gemm<CfgMid, A_KC, B_KC, Epi>(p, epi, h->batch, h->st);
+  else if (choice == 3)
+    e = launch_gemm<CfgS3, A_KC, B_KC, Epi>(p, epi, h->batch, h->st);
+  else if (choice == 4)
+    e = launch_gemm<CfgK32, A_KC, B_KC, Epi>(p, epi, h->batch, h->st);
   else
     e = launch_gemm<CfgSmall, A_KC, B_KC, Epi>(p, epi, h->batch, h->st);
   h->seq_launches++;
