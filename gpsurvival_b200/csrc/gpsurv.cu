@@ -433,7 +433,8 @@ void enqueue_grad(H* h) {
   }
   grad_cols_kernel<<<dim3(ceil_div(h->d + 1, 8), h->batch), 256, 0, h->st>>>(h->Xaug, n, h->d, h->ldx, h->strideX,
                                                                              h->colpart, h->ldmu, h->mtiles_grad, h->rs,
-                                                                             h->alpha, h->ld, h->qtu);
+                                                                             h->alpha, h->ld, h->qtu, h->ell, h->ldmu,
+                                                                             h->o.cov_form == 1 ? 1 : 0, h->par_cap, h->d_grad);
   LAUNCHED(h);
   grad_finish_kernel<<<h->batch, 256, 0, h->st>>>(h->qtu, h->ldmu, n, h->d, h->p, h->o, h->wdiag, h->cens_rank, h->ld,
                                                    h->hyp, h->ell, h->ldmu, h->mu, h->ldmu, h->par_cap, h->d_grad);
@@ -706,8 +707,10 @@ int gps_set_data(gps_handle h, const double* X, int n, int d, const double* y, c
   h->strideM = (long long)h->ld * round_up(h->ne, 2);
   h->strideX = (long long)h->ldx * (d + 1);
   {
-    int want = ceil_div(24000, n * B);
-    h->rn_ksplit = want < 1 ? 1 : (want > d ? d : (want > 64 ? 64 : want));
+    int want = ceil_div(160000, n * B);     // ~160 K threads in flight: the pre-scale is pure streaming
+    int cap = d / 8 > 1 ? d / 8 : 1;        // at least 8 columns per thread
+    if (cap > 256) cap = 256;
+    h->rn_ksplit = want < 1 ? 1 : (want > cap ? cap : want);
   }
   h->gram_ksplit = pick_gram_ksplit(h, n, n, d, true);
   size_t vecB = (size_t)h->ld * B;
@@ -994,8 +997,12 @@ int gps_predict(gps_handle h, const double* par, int len, int reuse_model, const
     LAUNCHED(h);
     rownorm_finish_kernel<<<dim3(ceil_div(n, 256), B), 256, 0, h->st>>>(h->rnpart, n, h->ld, h->rn_ksplit, h->rnorm);
     LAUNCHED(h);
-    int ks = ceil_div(24000, m * B);
-    ks = ks < 1 ? 1 : (ks > d ? d : (ks > 64 ? 64 : ks));
+    int ks = ceil_div(160000, m * B);
+    {
+      int cap = d / 8 > 1 ? d / 8 : 1;
+      if (cap > 64) cap = 64;               // snpart holds 64 slices
+      ks = ks < 1 ? 1 : (ks > cap ? cap : ks);
+    }
     dim3 grid2(ceil_div(m, 128), ks, B);
     prescale_kernel<<<grid2, 128, 0, h->st>>>(h->Xs, m, d, lds, sXs, h->mu, h->ldmu, h->m_ell, h->ldmu, h->p,
                                                h->o.ard_mode == 1 && h->p > 1, m, h->Zs, lds, sXs, h->snpart, lds, ks, 1, 1);

@@ -630,7 +630,8 @@ __global__ void wk_kernel(const double* __restrict__ Kinv, const double* __restr
 __global__ void grad_cols_kernel(const double* __restrict__ X, int n, int d, int ldx, long long strideX,
                                  const double* __restrict__ colpart, int ldp, int mtiles,
                                  const double* __restrict__ rs, const double* __restrict__ alpha, int ldn,
-                                 double* __restrict__ qtu) {
+                                 double* __restrict__ qtu, const double* __restrict__ ell, int ldell, int ard,
+                                 int len, double* __restrict__ grad) {
   int k = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31, b = blockIdx.y;
   if (k > d) return;
   const double* x = X + (size_t)b * strideX + (size_t)k * ldx;
@@ -651,6 +652,10 @@ __global__ void grad_cols_kernel(const double* __restrict__ X, int n, int d, int
     o[k] = q;
     o[ldp + k] = t;
     o[2 * ldp + k] = u;
+    if (ard && k < d) {       // d/dlog ell_k = -(t_k - q_k) / ell_k^2, one length-scale per column
+      double e = ell[(size_t)b * ldell + k];
+      grad[(size_t)b * len + 2 + k] = -(t - q) / (e * e);
+    }
   }
 }
 
@@ -676,7 +681,7 @@ __global__ void grad_finish_kernel(const double* __restrict__ qtu, int ldp, int 
   trc = block_sum(trc, sh);
   const double* el = ell + (size_t)b * ldell;
   if (o.cov_form == 1) {
-    for (int k = tid; k < d; k += blockDim.x) g[2 + k] = -(t[k] - q[k]) / (el[k] * el[k]);
+    // ARD length-scale gradients were written by grad_cols_kernel (one warp per column)
   } else {
     double s = 0.0;
     for (int k = tid; k < d; k += blockDim.x) s += t[k] - q[k];
