@@ -11,7 +11,19 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libgpsurv.so")
 
 GPS_OK, GPS_ERR_ARG, GPS_ERR_CUDA, GPS_ERR_NOT_PD, GPS_ERR_UNSUPPORTED, GPS_ERR_STATE = range(6)
-COV = {"SqExp": 0, "ARD": 1}
+COV = {"SqExp": 0, "ARD": 1, "Matern1": 2, "Matern3": 3, "Matern5": 4}
+
+
+def cov_code(cov_form, extra_param=None):
+    """covFuncForm (+ extraParam = maternParam for 'Matern', CovFunc.R:31) -> gps_cov_form."""
+    if cov_form == "Matern":
+        key = "Matern" + str(int(extra_param)) if extra_param is not None else "Matern?"
+        if key not in COV:
+            raise GpsError(GPS_ERR_ARG, f"Matern needs extraParam (maternParam) 1, 3 or 5, got {extra_param!r}")
+        return COV[key]
+    if cov_form not in COV:
+        raise GpsError(GPS_ERR_UNSUPPORTED, f"covFuncForm {cov_form!r} is not built (SqExp, ARD, Matern)")
+    return COV[cov_form]
 MEAN = {"Zero": 0, "Linear": 1}
 NOISE_CORR = {False: 0, None: 0, "none": 0, "noiseCorrLearned": 1, "noiseCorrVec": 2}
 ARD_MODE = {"intended": 0, "as_written": 1}

@@ -95,7 +95,7 @@ def apply_gp_batch(problems, parameterStructure, data_source="Generate", device=
     if own:
         fit = gp.Fit(device, batch=B)
     nc_opt = noise_corr if noise_corr in ("noiseCorrLearned", "noiseCorrVec") else False
-    fit.set_options(cov_form, mean_form, nc_opt, gp.SESSION.ard_mode)
+    fit.set_options(cov_form, mean_form, nc_opt, gp.SESSION.ard_mode, ps.get("extraParam", ps.get("maternParam")))
     fit.set_data(X, y, ev)
     starts = ps["logHypStart"]
     log_hyps = list(starts) if isinstance(starts, (list, tuple)) else [starts] * B      # per-fit restarts allowed

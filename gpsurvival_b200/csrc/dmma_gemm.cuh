@@ -278,7 +278,21 @@ struct EpiPlain {
   }
 };
 
-// Squared-exponential covariance epilogue (CovFunc.R:38-39 on the Gram form):
+// Covariance as a function of the scaled squared distance (CovFunc.R:33-39).  kind: 0 = SqExp / ARD
+// sf2 exp(-r2/2); 1, 3, 5 = Matern nu = 1/2, 3/2, 5/2 in r = sqrt(r2) (extraParam of the reference).
+__device__ __forceinline__ double cov_kernel_fn(int kind, double r2, double s2) {
+  if (kind == 0) return s2 * exp(-0.5 * r2);
+  const double r = sqrt(r2);
+  if (kind == 1) return s2 * exp(-r);
+  if (kind == 3) {
+    const double a = 1.7320508075688772 * r;
+    return s2 * (1.0 + a) * exp(-a);
+  }
+  const double a = 2.23606797749979 * r;
+  return s2 * (1.0 + a + (5.0 * (r * r)) / 3.0) * exp(-a);
+}
+
+// Covariance epilogue (CovFunc.R:33-39 on the Gram form):
 //   r2 = max(0, sA[m] + sB[n] - 2*G[m,n]);  K = sf2 * exp(-r2/2);
 // symmetric case (sym != 0): the diagonal is written as exactly sf2 and Ky additionally gets
 // noise_diag[m] on the diagonal (ForOptimisationLog.R:35-40).  Hyper-parameters are read
@@ -293,6 +307,7 @@ struct EpiCov {
   int ldk, ldn, ldnB;      // ldn / ldnB: per-batch strides of normA (and noise_diag) / normB
   long long strideK;
   int sym;
+  int kind;                // cov_kernel_fn selector
   template <class Cfg>
   __device__ __forceinline__ void operator()(const GemmParams& p, AccTile<Cfg>& a, double*) const {
     const double s2 = hyp[a.batch * 4 + 1];
@@ -314,7 +329,7 @@ struct EpiCov {
           int mm = m + e;
           if (mm >= p.M) continue;
           double r2 = fmax(0.0, nA[mm] + sn - 2.0 * a.v[i][j][e]);
-          double k = s2 * exp(-0.5 * r2);
+          double k = cov_kernel_fn(kind, r2, s2);
           double ky = k;
           if (sym && mm == n) {
             k = s2;

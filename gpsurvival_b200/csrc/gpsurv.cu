@@ -255,15 +255,21 @@ int pick_gram_ksplit(const H* h, int n1, int n2, int d, bool sym) {
   return ks < 1 ? 1 : ks;
 }
 
+inline int cov_kind(int cov_form) {   // ModelOpts.cov_form -> cov_kernel_fn selector
+  return cov_form == GPS_COV_MATERN1 ? 1 : cov_form == GPS_COV_MATERN3 ? 3 : cov_form == GPS_COV_MATERN5 ? 5 : 0;
+}
+inline bool cov_form_ok(int f) { return f >= GPS_COV_SQEXP && f <= GPS_COV_MATERN5; }
+
 void enqueue_cov(H* h, const double* Za, int n1, int lda, long long sA, const double* normA, const double* Zb,
                  int n2, int ldb, long long sB, const double* normB, int d, const double* hyp,
-                 const double* noise_diag, double* Kout, double* Kyout, int ldk, long long sK, bool sym, int ksplit) {
+                 const double* noise_diag, double* Kout, double* Kyout, int ldk, long long sK, bool sym, int ksplit,
+                 int kind) {
   GemmParams p = gp(Za, lda, sA, Zb, ldb, sB, n1, n2, d);
   p.lower = sym ? 1 : 0;
   if (ksplit <= 1) {
     EpiCov e;
     e.normA = normA; e.normB = normB; e.hyp = hyp; e.noise_diag = noise_diag; e.Kout = Kout; e.Kyout = Kyout;
-    e.ldk = ldk; e.ldn = h->ld; e.ldnB = h->ld; e.strideK = sK; e.sym = sym ? 1 : 0;
+    e.ldk = ldk; e.ldn = h->ld; e.ldnB = h->ld; e.strideK = sK; e.sym = sym ? 1 : 0; e.kind = kind;
     gemm<false, false>(h, p, e);
   } else {
     p.ksplit = ksplit;
@@ -272,7 +278,7 @@ void enqueue_cov(H* h, const double* Za, int n1, int lda, long long sA, const do
     gemm<false, false>(h, p, e);
     dim3 grid(ceil_div(n1, 32), ceil_div(n2, 8), h->batch), block(32, 8);
     cov_finish_kernel<<<grid, block, 0, h->st>>>(h->gsplit, n1, n2, ldk, sK, (long long)ksplit * sK, ksplit, normA,
-                                                  normB, h->ld, hyp, noise_diag, Kout, Kyout, ldk, sK, sym ? 1 : 0);
+                                                  normB, h->ld, hyp, noise_diag, Kout, Kyout, ldk, sK, sym ? 1 : 0, kind);
     LAUNCHED(h);
   }
 }
@@ -386,7 +392,7 @@ void enqueue_factor(H* h) {
   LAUNCHED(h);
   enqueue_prescale_train(h, h->ell, 1);
   enqueue_cov(h, h->Z, n, h->ldx, h->strideX, h->rnorm, h->Z, n, h->ldx, h->strideX, h->rnorm, h->d, h->hyp,
-              h->noise_diag, h->K, h->Ky, h->ld, h->strideM, true, h->gram_ksplit);
+              h->noise_diag, h->K, h->Ky, h->ld, h->strideM, true, h->gram_ksplit, cov_kind(h->o.cov_form));
   fill_aug_kernel<<<dim3(ceil_div(h->ne, 128), h->batch), 128, 0, h->st>>>(
       h->Xaug, n, h->ne, h->d, h->ldx, h->strideX, h->meanw, h->ldmu, h->o.mean_form == 1, h->y, h->ld, h->meanv, h->Ky,
       h->ld, h->strideM, h->nrhs);
@@ -663,8 +669,8 @@ int gps_destroy(gps_handle h) {
 int gps_set_options(gps_handle h, int cov_form, int mean_form, int noise_corr, int ard_mode) {
   int rc = check_handle(h);
   if (rc) return rc;
-  if (cov_form != GPS_COV_SQEXP && cov_form != GPS_COV_ARD)
-    return fail(h, GPS_ERR_UNSUPPORTED, "covFuncForm must be SqExp or ARD (Matern/RF/InformedARD are not built)");
+  if (!cov_form_ok(cov_form))
+    return fail(h, GPS_ERR_UNSUPPORTED, "covFuncForm must be SqExp, ARD or Matern (RF / InformedARD are not built)");
   if (mean_form != GPS_MEAN_ZERO && mean_form != GPS_MEAN_LINEAR) return fail(h, GPS_ERR_ARG, "bad meanFuncForm");
   if (noise_corr < 0 || noise_corr > 2) return fail(h, GPS_ERR_ARG, "bad noiseCorr");
   if (ard_mode != GPS_ARD_INTENDED && ard_mode != GPS_ARD_AS_WRITTEN) return fail(h, GPS_ERR_ARG, "bad ard_mode");
@@ -857,6 +863,10 @@ int gps_nlml_grad(gps_handle h, const double* par, int len, double* nlml_out, do
   int rc = check_handle(h);
   if (rc) return rc;
   if (!grad_out) return fail(h, GPS_ERR_ARG, "grad_out is NULL");
+  if (h->o.cov_form >= GPS_COV_MATERN1)
+    return fail(h, GPS_ERR_UNSUPPORTED,
+                "no gradient for the Matern covariances: the reference has none either "
+                "(OptimisationGradientLog.R:6 'NOT YET WORKING FOR Matern'); use optimType = 'Nelder-Mead'");
   if (h->have_data && h->o.cov_form == GPS_COV_ARD && h->o.ard_mode == GPS_ARD_AS_WRITTEN && h->d > 1)
     return fail(h, GPS_ERR_UNSUPPORTED,
                 "the analytic ARD gradient is defined for ard_mode = INTENDED only (the reference's as-written ARD "
@@ -1017,7 +1027,7 @@ int gps_predict(gps_handle h, const double* par, int len, int reuse_model, const
     GemmParams p = gp(h->Z, h->ldx, h->strideX, h->Zs, lds, sXs, n, m, d);
     EpiCov e;
     e.normA = h->rnorm; e.normB = h->snorm; e.hyp = h->m_hyp; e.noise_diag = nullptr; e.Kout = h->Ks; e.Kyout = nullptr;
-    e.ldk = h->ld; e.ldn = h->ld; e.strideK = sKs; e.sym = 0;
+    e.ldk = h->ld; e.ldn = h->ld; e.strideK = sKs; e.sym = 0; e.kind = cov_kind(h->o.cov_form);
     e.ldnB = lds;
     gemm<false, false>(h, p, e);
   }
@@ -1084,8 +1094,7 @@ int gps_cov(gps_handle h, const double* X1, int n1, const double* X2, int n2, in
   int rc = check_handle(h);
   if (rc) return rc;
   if (!X1 || n1 < 1 || d < 1 || !ell || !K_out) return fail(h, GPS_ERR_ARG, "gps_cov: bad arguments");
-  if (cov_form != GPS_COV_SQEXP && cov_form != GPS_COV_ARD)
-    return fail(h, GPS_ERR_UNSUPPORTED, "gps_cov: covFuncForm must be SqExp or ARD");
+  if (!cov_form_ok(cov_form)) return fail(h, GPS_ERR_UNSUPPORTED, "gps_cov: covFuncForm must be SqExp, ARD or Matern");
   if (p != 1 && p != d && ard_mode == GPS_ARD_INTENDED) return fail(h, GPS_ERR_ARG, "gps_cov: need 1 or d length-scales");
   const bool sym = (X2 == nullptr);
   if (sym) n2 = n1;
@@ -1160,7 +1169,7 @@ int gps_cov(gps_handle h, const double* X1, int n1, const double* X2, int n2, in
   h->cu_err = cudaSuccess;
   h->seq_launches = 0;
   enqueue_cov(h, dZ1, n1, ld1, 0, dn1, Zb, n2, ldb, 0, nb, d, dhyp, nullptr, dK, nullptr, ldk, (long long)ldk * n2, sym,
-              ksplit);
+              ksplit, cov_kind(cov_form));
   if (sym) {
     symmetrize_kernel<<<dim3(ceil_div(n1, 32), ceil_div(n1, 32), 1), dim3(32, 8), 0, h->st>>>(dK, n1, ldk, 0);
     h->seq_launches++;
@@ -1237,7 +1246,7 @@ int gps_time_stages(gps_handle h, double* ms_out) {
                                                 h->noise_diag);
   enqueue_prescale_train(h, h->ell, 1);
   enqueue_cov(h, h->Z, n, h->ldx, h->strideX, h->rnorm, h->Z, n, h->ldx, h->strideX, h->rnorm, h->d, h->hyp,
-              h->noise_diag, h->K, h->Ky, h->ld, h->strideM, true, h->gram_ksplit);
+              h->noise_diag, h->K, h->Ky, h->ld, h->strideM, true, h->gram_ksplit, cov_kind(h->o.cov_form));
   fill_aug_kernel<<<dim3(ceil_div(h->ne, 128), h->batch), 128, 0, h->st>>>(
       h->Xaug, n, h->ne, h->d, h->ldx, h->strideX, h->meanw, h->ldmu, h->o.mean_form == 1, h->y, h->ld, h->meanv, h->Ky,
       h->ld, h->strideM, h->nrhs);

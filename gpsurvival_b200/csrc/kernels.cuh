@@ -7,13 +7,15 @@
 #include <math.h>
 #include <stdint.h>
 
+#include "dmma_gemm.cuh"
+
 namespace gps {
 
 constexpr int NB = 64;   // leaf block of the recursive Cholesky / triangular inverse
 
 // Options mirrored from gpsurv.h (kept as ints on the device)
 struct ModelOpts {
-  int cov_form;     // 0 SqExp, 1 ARD
+  int cov_form;     // 0 SqExp, 1 ARD, 2/3/4 Matern nu = 1/2, 3/2, 5/2
   int mean_form;    // 0 Zero, 1 Linear
   int noise_corr;   // 0 none, 1 learned (GPS2), 2 vec (GPS3)
   int ard_mode;     // 0 intended, 1 as written
@@ -177,7 +179,7 @@ __global__ void cov_finish_kernel(const double* __restrict__ Gpart, int n1, int 
                                   long long strideG, int ksplit, const double* __restrict__ normA,
                                   const double* __restrict__ normB, int ldn, const double* __restrict__ hyp,
                                   const double* __restrict__ noise_diag, double* __restrict__ Kout,
-                                  double* __restrict__ Kyout, int ldk, long long strideK, int sym) {
+                                  double* __restrict__ Kyout, int ldk, long long strideK, int sym, int kind) {
   int i = blockIdx.x * 32 + threadIdx.x, j = blockIdx.y * 8 + threadIdx.y, b = blockIdx.z;
   if (i >= n1 || j >= n2) return;
   if (sym && i < j) return;   // lower triangle only, like the fused path
@@ -186,7 +188,7 @@ __global__ void cov_finish_kernel(const double* __restrict__ Gpart, int n1, int 
     gsum += Gpart[(size_t)b * strideG + (size_t)s * strideSplit + (size_t)i + (size_t)j * ldg];
   double s2 = hyp[b * 4 + 1];
   double r2 = fmax(0.0, normA[(size_t)b * ldn + i] + normB[(size_t)b * ldn + j] - 2.0 * gsum);
-  double k = s2 * exp(-0.5 * r2), ky = k;
+  double k = cov_kernel_fn(kind, r2, s2), ky = k;
   if (sym && i == j) {
     k = s2;
     ky = noise_diag ? s2 + noise_diag[(size_t)b * ldn + i] : s2;

@@ -18,7 +18,7 @@ import ctypes as C
 import numpy as np
 
 from . import _lib
-from ._lib import COV, MEAN, NOISE_CORR, ARD_MODE, GpsError, NotPositiveDefinite, check, dptr, f64
+from ._lib import COV, MEAN, NOISE_CORR, ARD_MODE, GpsError, NotPositiveDefinite, check, cov_code, dptr, f64
 from . import optim as _optim
 
 
@@ -52,12 +52,11 @@ class Fit:
         check(rc, self.h)
 
     # -- configuration -------------------------------------------------------------------
-    def set_options(self, cov_form="SqExp", mean_form="Zero", noise_corr=False, ard_mode="intended"):
-        if cov_form not in COV:
-            raise GpsError(_lib.GPS_ERR_UNSUPPORTED, f"covFuncForm {cov_form!r} is not built (SqExp, ARD)")
-        self._ck(self.lib.gps_set_options(self.h, COV[cov_form], MEAN[mean_form], NOISE_CORR[noise_corr],
-                                          ARD_MODE[ard_mode]))
-        self.opts = (cov_form, mean_form, noise_corr, ard_mode)
+    def set_options(self, cov_form="SqExp", mean_form="Zero", noise_corr=False, ard_mode="intended", extra_param=None):
+        code = cov_code(cov_form, extra_param)
+        self._ck(self.lib.gps_set_options(self.h, code, MEAN[mean_form], NOISE_CORR[noise_corr], ARD_MODE[ard_mode]))
+        self.opts = (cov_form, mean_form, noise_corr, ard_mode) if cov_form != "Matern" else \
+            (cov_form, mean_form, noise_corr, ard_mode, int(extra_param))
 
     def set_data(self, X, y, events=None):
         if np.ndim(X) == 2:
@@ -152,7 +151,7 @@ class Fit:
         self._ck(self.lib.gps_adjust(self.h, dptr(a), dptr(mu), dptr(s), a.size, dptr(em), dptr(ev)))
         return em, ev
 
-    def cov(self, x1, x2, sf2, ell, cov_form="SqExp", ard_mode="intended"):
+    def cov(self, x1, x2, sf2, ell, cov_form="SqExp", ard_mode="intended", extra_param=None):
         x1 = f64(x1)
         n1, d = x1.shape
         ell = np.ascontiguousarray(np.atleast_1d(np.asarray(ell, dtype=np.float64)).ravel())
@@ -163,7 +162,7 @@ class Fit:
             x2p, n2 = x2a, x2a.shape[0]
         K = np.empty((n1, n2), order="F")
         self._ck(self.lib.gps_cov(self.h, dptr(x1), n1, dptr(x2p), n2, d, float(sf2), dptr(ell), ell.size,
-                                  COV[cov_form], ARD_MODE[ard_mode], dptr(K)))
+                                  cov_code(cov_form, extra_param), ARD_MODE[ard_mode], dptr(K)))
         return K
 
     # -- measurement helpers -------------------------------------------------------------
@@ -214,14 +213,15 @@ class _Session:
             self.fit.close()
         self.__init__()
 
-    def bind(self, X, y, events, cov_form, mean_form, noise_corr, lnc):
+    def bind(self, X, y, events, cov_form, mean_form, noise_corr, lnc, extra_param=None):
         if self.fit is None:
             self.fit = Fit(self.device)
         fit = self.fit
         nc = noise_corr if noise_corr in ("noiseCorrLearned", "noiseCorrVec") else False
-        opts = (cov_form, mean_form, nc, self.ard_mode)
+        opts = (cov_form, mean_form, nc, self.ard_mode) if cov_form != "Matern" else \
+            (cov_form, mean_form, nc, self.ard_mode, int(extra_param) if extra_param is not None else None)
         if fit.opts != opts:
-            fit.set_options(*opts)
+            fit.set_options(cov_form, mean_form, nc, self.ard_mode, extra_param)
         X = np.asarray(X, dtype=np.float64)
         y = np.asarray(y, dtype=np.float64).ravel()
         events = np.ones(X.shape[0]) if events is None else np.asarray(events, dtype=np.float64).ravel()
@@ -265,17 +265,16 @@ def set_ard_mode(mode: str):
 # Reference-named functions
 # =========================================================================================
 def CovFunc(x1, x2, x, y, extraParam, varFuncSqHyp, lengthHyp, covFuncForm):
-    """CovFunc.R:1 — covariance between the rows of x1 and x2 (x, y, extraParam unused for
-    SqExp / ARD).  'Matern', 'RF', 'InformedARD' raise (GPS_ERR_UNSUPPORTED)."""
-    if covFuncForm not in COV:
-        raise GpsError(_lib.GPS_ERR_UNSUPPORTED, f"covFuncForm {covFuncForm!r} is not built (SqExp, ARD)")
+    """CovFunc.R:1 — covariance between the rows of x1 and x2 (x, y unused).  'SqExp', 'ARD' and
+    'Matern' (extraParam = maternParam in 1, 3, 5); 'RF', 'InformedARD' raise GPS_ERR_UNSUPPORTED."""
+    cov_code(covFuncForm, extraParam)      # raises for RF / InformedARD / bad maternParam
     if SESSION.fit is None:
         SESSION.fit = Fit(SESSION.device)
     x1 = np.asarray(x1, dtype=np.float64)
     x2 = np.asarray(x2, dtype=np.float64)
     same = x1 is x2 or (x1.shape == x2.shape and np.array_equal(x1, x2))   # identical(x1, x2), CovFunc.R:24
     return np.asarray(SESSION.fit.cov(x1, None if same else x2, float(np.ravel(varFuncSqHyp)[0]),
-                                      np.ravel(lengthHyp), covFuncForm, SESSION.ard_mode))
+                                      np.ravel(lengthHyp), covFuncForm, SESSION.ard_mode, extraParam))
 
 
 def MeanFunc(meanHyp, x, meanFuncForm, n):
@@ -305,7 +304,7 @@ def ForOptimisationLog(logHyp, trainingData, trainingTargets, trainingEvents, me
     on the host side of the boundary)."""
     _reject_priors(imposePriors)
     fit = SESSION.bind(trainingData, trainingTargets, trainingEvents, covFuncForm, meanFuncForm, noiseCorr,
-                       logHypNoiseCorrection)
+                       logHypNoiseCorrection, extraParam)
     return np.array([[fit.nlml(np.ravel(logHyp))]])
 
 
@@ -314,7 +313,7 @@ def OptimisationGradientLog(logHyp, trainingData, trainingTargets, trainingEvent
     """OptimisationGradientLog.R:1 — gradient as a k x 1 matrix (:93), same order as logHyp."""
     _reject_priors(imposePriors)
     fit = SESSION.bind(trainingData, trainingTargets, trainingEvents, covFuncForm, meanFuncForm, noiseCorr,
-                       logHypNoiseCorrection)
+                       logHypNoiseCorrection, extraParam)
     _, g = fit.nlml_grad(np.ravel(logHyp))
     return g.reshape(-1, 1)
 
@@ -350,7 +349,8 @@ def GPRegression(logHyp, parameterStructure, trainingTestStructure, logHypNoiseC
     meanFuncForm, covFuncForm = ps["meanFuncForm"], ps["covFuncForm"]
     _reject_priors(ps.get("imposePriors", False))
     vec = _flatten(logHyp, d, meanFuncForm, noiseCorr, logHypNoiseCorrection)
-    fit = SESSION.bind(X, y, events, covFuncForm, meanFuncForm, noiseCorr, logHypNoiseCorrection)
+    extra = ps.get("extraParam", ps.get("maternParam"))                                  # :19
+    fit = SESSION.bind(X, y, events, covFuncForm, meanFuncForm, noiseCorr, logHypNoiseCorrection, extra)
     # a non-positive-definite Ky inside optim is reported to the optimiser as +Inf (the reference
     # would try Matrix::nearPD there, ForOptimisationLog.R:43-51 — out of scope)
     opt = _optim.optim(vec, fn=lambda p: fit.nlml(p, not_pd="inf"), gr=lambda p: fit.nlml_grad(p, not_pd="inf")[1],
@@ -392,7 +392,8 @@ def GPPredict(regressionStructure, parameterStructure, trainingTestStructure, lo
     corr = noiseCorr in ("noiseCorrVec", "noiseCorrLearned")
     par = _par_from_chosen(regressionStructure["logHypChosen"], d, meanFuncForm, noiseCorr, logHypNoiseCorrection)
     if corr:
-        fit = SESSION.bind(X, y, events, covFuncForm, meanFuncForm, noiseCorr, logHypNoiseCorrection)
+        fit = SESSION.bind(X, y, events, covFuncForm, meanFuncForm, noiseCorr, logHypNoiseCorrection,
+                           ps.get("extraParam", ps.get("maternParam")))
         mu, vf, vd = fit.predict(par, Xs, reuse_model=False)
     else:
         fit = SESSION.fit

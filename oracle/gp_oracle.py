@@ -23,7 +23,7 @@ import scipy.linalg as sla
 # --------------------------------------------------------------------------------------
 # option strings, exactly as the reference spells them (SURVEY.md §5 "Config")
 # --------------------------------------------------------------------------------------
-COV_FORMS = ("SqExp", "ARD")
+COV_FORMS = ("SqExp", "ARD", "Matern")
 MEAN_FORMS = ("Zero", "Linear")
 NOISE_CORRS = (False, "none", "noiseCorrLearned", "noiseCorrVec")
 
@@ -75,14 +75,24 @@ def rdist(z1, z2):
     return np.sqrt(acc)
 
 
-def cov_func(x1, x2, sf2, ell, cov_form="SqExp", ard_mode="intended"):
-    """CovFunc.R:21-29,38-39 — K_ij = sf2 * exp(-(rdist(x1/ell, x2/ell)_ij)^2 / 2).
+def cov_func(x1, x2, sf2, ell, cov_form="SqExp", ard_mode="intended", extra_param=None):
+    """CovFunc.R:21-29,33-39 — SqExp / ARD: K_ij = sf2 * exp(-(rdist(x1/ell, x2/ell)_ij)^2 / 2);
+    Matern with maternParamFlag = as.character(extraParam) in '1', '3', '5' (:31-37).
 
     Noise is NOT added here (callers add it, ForOptimisationLog.R:35).
     """
     if cov_form not in COV_FORMS:
-        raise NotImplementedError(cov_form)  # Matern/RF/InformedARD: SURVEY.md §2
+        raise NotImplementedError(cov_form)  # RF/InformedARD: SURVEY.md §2
     distance = rdist(_scale_inputs(x1, ell, ard_mode), _scale_inputs(x2, ell, ard_mode))
+    if cov_form == "Matern":
+        flag = str(int(extra_param)) if extra_param is not None else None
+        if flag == "1":
+            return float(sf2) * np.exp(-distance)                                                   # :34
+        if flag == "3":
+            return float(sf2) * (1 + (math.sqrt(3) * distance)) * np.exp(-(math.sqrt(3) * distance))   # :35
+        if flag == "5":
+            return float(sf2) * (1 + (math.sqrt(5) * distance) + (5 * distance ** 2) / 3) * np.exp(-(math.sqrt(5) * distance))  # :36
+        raise ValueError(f"maternParam {extra_param!r}")
     return float(sf2) * np.exp(-(distance ** 2) / 2.0)   # CovFunc.R:38-39
 
 
@@ -110,7 +120,7 @@ def unpack_log_hyp(par, d, cov_form, mean_form, noise_corr, log_hyp_noise_corr=N
     if noise_corr == "noiseCorrLearned":            # ForOptimisationLog.R:10-13
         log_hyp_noise_corr = par[-1:]
         par = par[:-1]
-    p = 1 if cov_form == "SqExp" else d             # :14-21
+    p = d if cov_form == "ARD" else 1               # :14-21 (SqExp | Matern share one length-scale)
     log_sn2 = par[0]
     log_sf2 = par[1]
     log_ell = par[2:2 + p]
@@ -148,7 +158,7 @@ def _solve_as_written(L, rhs):
 # ForOptimisationLog.R
 # --------------------------------------------------------------------------------------
 def nlml(par, X, y, events, cov_form="SqExp", mean_form="Zero", noise_corr=False,
-         log_hyp_noise_corr=None, ard_mode="intended", as_written_ops=True):
+         log_hyp_noise_corr=None, ard_mode="intended", as_written_ops=True, extra_param=None):
     """Negative log marginal likelihood (ForOptimisationLog.R:1-68, imposePriors=FALSE).
 
     ``as_written_ops=True`` repeats the reference's redundant work (Cholesky probed then
@@ -160,7 +170,7 @@ def nlml(par, X, y, events, cov_form="SqExp", mean_form="Zero", noise_corr=False
     log_sn2, log_sf2, log_ell, mean_hyp, lnc = unpack_log_hyp(
         par, d, cov_form, mean_form, noise_corr, log_hyp_noise_corr)
     m = mean_func(mean_hyp, X, mean_form)                                    # :34
-    K = cov_func(X, X, math.exp(log_sf2), np.exp(log_ell), cov_form, ard_mode)
+    K = cov_func(X, X, math.exp(log_sf2), np.exp(log_ell), cov_form, ard_mode, extra_param)
     Ky = K + np.diag(_noise_diag(n, log_sn2, events, noise_corr, lnc))       # :35-40
     if as_written_ops:
         _chol_lower(Ky)                                                      # :41 (probe)
@@ -256,7 +266,7 @@ def nlml_grad(par, X, y, events, cov_form="SqExp", mean_form="Zero", noise_corr=
 # GPRegression.R:60-71 (everything after optim)
 # --------------------------------------------------------------------------------------
 def regress_finalize(par, X, y, events, cov_form="SqExp", mean_form="Zero", noise_corr=False,
-                     log_hyp_noise_corr=None, ard_mode="intended", as_written_ops=True):
+                     log_hyp_noise_corr=None, ard_mode="intended", as_written_ops=True, extra_param=None):
     """Recompute K, L, alpha and the (positive-sign) log marginal likelihood at ``par``
     (GPRegression.R:32-71).  Returns the fields of the reference's list (:73-82)."""
     X = np.asarray(X, dtype=np.float64)
@@ -266,7 +276,7 @@ def regress_finalize(par, X, y, events, cov_form="SqExp", mean_form="Zero", nois
         par, d, cov_form, mean_form, noise_corr, log_hyp_noise_corr)
     sn2, sf2, ell = np.exp(log_sn2), np.exp(log_sf2), np.exp(log_ell)        # :39-52
     m = mean_func(mean_hyp, X, mean_form)                                    # :60
-    K = cov_func(X, X, sf2, ell, cov_form, ard_mode)                         # :61
+    K = cov_func(X, X, sf2, ell, cov_form, ard_mode, extra_param)            # :61
     # the reference re-logs the exponentiated values (:73): log(exp(x)) is not x bit-for-bit
     log_hyp_chosen = {"noise": float(np.log(sn2)), "func": float(np.log(sf2)),
                       "length": np.log(ell), "mean": np.array(mean_hyp, dtype=np.float64)}
@@ -293,7 +303,7 @@ def regress_finalize(par, X, y, events, cov_form="SqExp", mean_form="Zero", nois
 # GPPredict.R
 # --------------------------------------------------------------------------------------
 def predict(reg, X, y, events, Xstar, cov_form="SqExp", mean_form="Zero", noise_corr=False,
-            log_hyp_noise_corr=None, ard_mode="intended", as_written_ops=True):
+            log_hyp_noise_corr=None, ard_mode="intended", as_written_ops=True, extra_param=None):
     """GPPredict.R:24-56. ``reg`` is the dict from :func:`regress_finalize` (uses ``L``,
     ``alpha``, ``logHypChosen``).  For GPS2/GPS3 L and alpha are rebuilt from the passed
     noise correction and the *current* targets ``y`` (:36-46)."""
@@ -309,7 +319,7 @@ def predict(reg, X, y, events, Xstar, cov_form="SqExp", mean_form="Zero", noise_
     L, alpha = reg["L"], reg["alpha"]
     if _has_corr(noise_corr):                                                # :36-46
         m = mean_func(mean_hyp, X, mean_form)
-        K = cov_func(X, X, sf2, ell, cov_form, ard_mode) + np.diag(np.full(n, sn2))
+        K = cov_func(X, X, sf2, ell, cov_form, ard_mode, extra_param) + np.diag(np.full(n, sn2))
         corr = np.zeros(n)
         corr[np.asarray(events).ravel() == 0] = np.exp(
             np.asarray(log_hyp_noise_corr, dtype=np.float64).ravel())
@@ -317,10 +327,10 @@ def predict(reg, X, y, events, Xstar, cov_form="SqExp", mean_form="Zero", noise_
         alpha = _solve_as_written(L, y - m) if as_written_ops else \
             sla.solve_triangular(L, sla.solve_triangular(L, y - m, lower=True), lower=True, trans="T")
     mstar = mean_func(mean_hyp, Xstar, mean_form)                            # :49
-    kstar = cov_func(X, Xstar, sf2, ell, cov_form, ard_mode)                 # :50
+    kstar = cov_func(X, Xstar, sf2, ell, cov_form, ard_mode, extra_param)    # :50
     if as_written_ops:
         v = np.linalg.solve(L, kstar)                                        # :51 (general solve)
-        kss = cov_func(Xstar, Xstar, sf2, ell, cov_form, ard_mode)           # :55 full m x m
+        kss = cov_func(Xstar, Xstar, sf2, ell, cov_form, ard_mode, extra_param)   # :55 full m x m
         var_function = np.diag(kss - v.T @ v)
     else:
         v = sla.solve_triangular(L, kstar, lower=True)
@@ -704,9 +714,10 @@ def gp_regression(log_hyp, params, data, log_hyp_noise_corr, ard_mode="intended"
     maxit = params["maxitSurvival"] if params["modelType"] == "survival" else params["maxit"]   # :16
     mean_form, cov_form = params["meanFuncForm"], params["covFuncForm"]
     vec = flatten_log_hyp(log_hyp, d, mean_form, noise_corr, log_hyp_noise_corr)                 # :22-25
+    extra = params.get("extraParam", params.get("maternParam"))
     kw = dict(cov_form=cov_form, mean_form=mean_form, noise_corr=noise_corr,
               log_hyp_noise_corr=log_hyp_noise_corr, ard_mode=ard_mode)
-    fn = lambda p: nlml(p, X, y, events, as_written_ops=as_written_ops, **kw)
+    fn = lambda p: nlml(p, X, y, events, as_written_ops=as_written_ops, extra_param=extra, **kw)
     gr = lambda p: nlml_grad(p, X, y, events, **kw)
     method = params["optimType"]
     if method == "Nelder-Mead":                                                                  # :28-31
@@ -718,7 +729,7 @@ def gp_regression(log_hyp, params, data, log_hyp_noise_corr, ard_mode="intended"
     vec = opt["par"]
     lnc = log_hyp_noise_corr
     out = regress_finalize(vec, X, y, events, cov_form, mean_form, noise_corr, lnc, ard_mode,
-                           as_written_ops)                                                       # :32-71
+                           as_written_ops, extra)                                                # :32-71
     if noise_corr == "noiseCorrLearned":                                                         # :35-38
         out["logHypNoiseCorrection"] = vec[-1:]
     out["logHyp"] = log_hyp
@@ -742,7 +753,7 @@ def apply_gp(tts, params, data_source="Generate", ard_mode="intended", as_writte
     model_type = params["modelType"]
     noise_corr = params["noiseCorr"]
     kw = dict(cov_form=params["covFuncForm"], mean_form=params["meanFuncForm"], ard_mode=ard_mode,
-              as_written_ops=as_written_ops)
+              as_written_ops=as_written_ops, extra_param=params.get("extraParam", params.get("maternParam")))
     y = np.log(np.asarray(tts["trainingTargets"], dtype=np.float64).ravel())        # :79 / :94
     if model_type == "survival" and data_source in ("CuratedOvarian", "TCGA2STAT", "TCGASynapse",
                                                     "TCGAYuanEtAl"):

@@ -15,6 +15,9 @@ import mpmath as mp
 mp.mp.dps = 50
 
 
+MATERN = None   # module-level switch: None (SqExp / ARD) or 1, 3, 5 (CovFunc.R:33-37)
+
+
 def _cov(x1, x2, sf2, ell):
     n1, n2, d = len(x1), len(x2), len(x1[0])
     K = mp.zeros(n1, n2)
@@ -24,7 +27,16 @@ def _cov(x1, x2, sf2, ell):
             for k in range(d):
                 lk = ell[k] if len(ell) > 1 else ell[0]
                 r2 += ((mp.mpf(x1[i][k]) - mp.mpf(x2[j][k])) / lk) ** 2
-            K[i, j] = sf2 * mp.exp(-r2 / 2)
+            if MATERN is None:
+                K[i, j] = sf2 * mp.exp(-r2 / 2)
+            else:
+                r = mp.sqrt(r2)
+                if MATERN == 1:
+                    K[i, j] = sf2 * mp.exp(-r)
+                elif MATERN == 3:
+                    K[i, j] = sf2 * (1 + mp.sqrt(3) * r) * mp.exp(-mp.sqrt(3) * r)
+                else:
+                    K[i, j] = sf2 * (1 + mp.sqrt(5) * r + 5 * r2 / 3) * mp.exp(-mp.sqrt(5) * r)
     return K
 
 

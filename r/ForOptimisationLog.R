@@ -4,7 +4,7 @@ ForOptimisationLog <- function(logHyp,trainingData,trainingTargets,trainingEvent
   # Covariance, Cholesky, solves and the likelihood run in libgpsurv.so (gps_nlml).  NOT RUN IN THE BUILD IMAGE.
   #-------------------------------------------------------------------------------------------------------------------#
   if(imposePriors) stop('imposePriors=TRUE cannot run in the reference as shipped (LogPriorX takes 3 arguments, is called with 7)')
-  h <- GpsBind(trainingData,trainingTargets,trainingEvents,covFuncForm,meanFuncForm,noiseCorr,logHypNoiseCorrection)
+  h <- GpsBind(trainingData,trainingTargets,trainingEvents,covFuncForm,meanFuncForm,noiseCorr,logHypNoiseCorrection,extraParam)
   logMarLik <- tryCatch(.Call('gps_r_nlml', h, as.double(logHyp)),
     error = function(e){
       if(!grepl('^gps_not_pd', conditionMessage(e))) stop(e)

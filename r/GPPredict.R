@@ -16,7 +16,7 @@ GPPredict <- function(regressionStructure,parameterStructure,trainingTestStructu
   testData <- as.matrix(trainingTestStructure$testData); storage.mode(testData) <- 'double'
   if(corr){
     h <- GpsBind(trainingTestStructure$trainingData,trainingTestStructure$trainingTargets,trainingTestStructure$events,
-                 covFuncForm,meanFuncForm,noiseCorr,logHypNoiseCorrection)
+                 covFuncForm,meanFuncForm,noiseCorr,logHypNoiseCorrection,parameterStructure$extraParam)
     toReturn <- .Call('gps_r_predict', h, par, FALSE, testData)
   } else {
     toReturn <- .Call('gps_r_predict', .gps$handle, par, TRUE, testData)

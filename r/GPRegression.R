@@ -29,7 +29,7 @@ GPRegression <- function(logHyp,parameterStructure,trainingTestStructure,logHypN
   parOpt    <- as.double(optimOutput$par)
   objective <- optimOutput$value
 
-  h   <- GpsBind(trainingData,trainingTargets,trainingEvents,covFuncForm,meanFuncForm,noiseCorr,logHypNoiseCorrection)
+  h   <- GpsBind(trainingData,trainingTargets,trainingEvents,covFuncForm,meanFuncForm,noiseCorr,logHypNoiseCorrection,extraParam)
   fin <- .Call('gps_r_finalize', h, parOpt, as.integer(nTraining), TRUE)
 
   logHypVec <- as.matrix(parOpt)

@@ -6,7 +6,7 @@ OptimisationGradientLog <- function(logHyp,trainingData,trainingTargets,training
   # of its own likelihood).  NOT RUN IN THE BUILD IMAGE.
   #---------------------------------------------------------------------------------------------#
   if(imposePriors) stop('imposePriors=TRUE cannot run in the reference as shipped')
-  h <- GpsBind(trainingData,trainingTargets,trainingEvents,covFuncForm,meanFuncForm,noiseCorr,logHypNoiseCorrection)
+  h <- GpsBind(trainingData,trainingTargets,trainingEvents,covFuncForm,meanFuncForm,noiseCorr,logHypNoiseCorrection,extraParam)
   gradients <- .Call('gps_r_nlml_grad', h, as.double(logHyp))
   return(gradients)
 }

@@ -11,14 +11,16 @@
 .gps$handle <- NULL
 .gps$ardMode <- 0L      # 0 = intended (per-dimension scaling), 1 = as written (recycled, CovFunc.R:25,27)
 
-GpsCovCode  <- function(covFuncForm) switch(covFuncForm, 'SqExp' = 0L, 'ARD' = 1L,
-                 stop(paste0("covFuncForm '", covFuncForm, "' is not built in libgpsurv (SqExp, ARD)")))
+GpsCovCode  <- function(covFuncForm, extraParam=NULL) switch(covFuncForm, 'SqExp' = 0L, 'ARD' = 1L,
+                 'Matern' = switch(as.character(extraParam), '1' = 2L, '3' = 3L, '5' = 4L,
+                                   stop('Matern needs extraParam (maternParam) 1, 3 or 5')),   # CovFunc.R:31-37
+                 stop(paste0("covFuncForm '", covFuncForm, "' is not built in libgpsurv (SqExp, ARD, Matern)")))
 GpsMeanCode <- function(meanFuncForm) switch(meanFuncForm, 'Zero' = 0L, 'Linear' = 1L)
 GpsNcCode   <- function(noiseCorr) if(identical(noiseCorr, 'noiseCorrLearned')) 1L else if(identical(noiseCorr, 'noiseCorrVec')) 2L else 0L
 
-GpsBind <- function(trainingData, trainingTargets, trainingEvents, covFuncForm, meanFuncForm, noiseCorr, logHypNoiseCorrection){
+GpsBind <- function(trainingData, trainingTargets, trainingEvents, covFuncForm, meanFuncForm, noiseCorr, logHypNoiseCorrection, extraParam=NULL){
   if(is.null(.gps$handle)) .gps$handle <- .Call('gps_r_create', 0L)
-  opts <- c(GpsCovCode(covFuncForm), GpsMeanCode(meanFuncForm), GpsNcCode(noiseCorr), .gps$ardMode)
+  opts <- c(GpsCovCode(covFuncForm, extraParam), GpsMeanCode(meanFuncForm), GpsNcCode(noiseCorr), .gps$ardMode)
   if(!identical(opts, .gps$opts)){
     .Call('gps_r_set_options', .gps$handle, opts[1], opts[2], opts[3], opts[4]); .gps$opts <- opts
   }

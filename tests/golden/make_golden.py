@@ -25,6 +25,9 @@ CASES = [
     ("ard_linear_gps2", 9, 3, 2, 4, "ARD", "Linear", "noiseCorrLearned"),
     ("sqexp_linear_none", 8, 3, 3, 3, "SqExp", "Linear", False),
     ("ard_zero_gps1_d5", 13, 5, 5, 6, "ARD", "Zero", False),
+    ("matern1_zero_gps1", 9, 3, 2, 3, "Matern1", "Zero", False),
+    ("matern3_zero_gps3", 10, 4, 2, 4, "Matern3", "Zero", "noiseCorrVec"),
+    ("matern5_zero_gps2", 11, 3, 3, 5, "Matern5", "Zero", "noiseCorrLearned"),
 ]
 
 
@@ -47,11 +50,18 @@ def main():
         kw = dict(ard=(cov == "ARD"), linear_mean=(mean == "Linear"), gps2=(nc == "noiseCorrLearned"),
                   log_sc2_vec=lnc)
         Xl = X.tolist()
+        extra = None
+        if cov.startswith("Matern"):
+            extra = int(cov[-1])
+            cov = "Matern"
+        mpo.MATERN = extra
         nl = float(mpo.nlml(par, Xl, y, ev, **kw))
-        gr = [float(v) for v in mpo.nlml_grad(par, Xl, y, ev, **kw)]
+        # the reference has no Matern gradient (OptimisationGradientLog.R:6): none is pinned
+        gr = [float(v) for v in mpo.nlml_grad(par, Xl, y, ev, **kw)] if extra is None else None
         mu, vf, vd = mpo.predict(par, Xl, y, ev, Xs.tolist(), **kw)
+        mpo.MATERN = None
         out["cases"].append({
-            "name": name, "cov_form": cov, "mean_form": mean, "noise_corr": nc, "X": X.tolist(), "y": y.tolist(),
+            "name": name, "cov_form": cov, "extra_param": extra, "mean_form": mean, "noise_corr": nc, "X": X.tolist(), "y": y.tolist(),
             "events": ev.tolist(), "Xstar": Xs.tolist(), "par": [float(v) for v in par], "log_sc2_vec": lnc,
             "nlml": nl, "grad": gr, "pred_mean": [float(v) for v in mu], "pred_varf": [float(v) for v in vf],
             "pred_vard": [float(v) for v in vd]})

@@ -32,9 +32,9 @@ def fit0():
     f.close()
 
 
-def _make_fit(X, y, ev, cov_form, mean_form, noise_corr, lnc=None, ard_mode="intended"):
+def _make_fit(X, y, ev, cov_form, mean_form, noise_corr, lnc=None, ard_mode="intended", extra_param=None):
     fit = gp.Fit(0)
-    fit.set_options(cov_form, mean_form, noise_corr, ard_mode)
+    fit.set_options(cov_form, mean_form, noise_corr, ard_mode, extra_param)
     fit.set_data(X, y, ev)
     if noise_corr == "noiseCorrVec":
         fit.set_noise_corr(lnc)
@@ -46,11 +46,17 @@ def _make_fit(X, y, ev, cov_form, mean_form, noise_corr, lnc=None, ard_mode="int
 def test_golden_fixture(c):
     X, y, ev = np.array(c["X"]), np.array(c["y"]), np.array(c["events"])
     par = np.array(c["par"])
-    fit = _make_fit(X, y, ev, c["cov_form"], c["mean_form"], c["noise_corr"], c["log_sc2_vec"])
+    fit = _make_fit(X, y, ev, c["cov_form"], c["mean_form"], c["noise_corr"], c["log_sc2_vec"],
+                    extra_param=c.get("extra_param"))
     assert abs(fit.nlml(par) - c["nlml"]) <= TOL_NLML * abs(c["nlml"])
-    f, g = fit.nlml_grad(par)
-    assert abs(f - c["nlml"]) <= TOL_NLML * abs(c["nlml"])
-    assert relmax(g, c["grad"]) <= TOL_GRAD
+    if c["grad"] is None:                       # Matern: no gradient in the reference, none here
+        with pytest.raises(gp.GpsError) as e:
+            fit.nlml_grad(par)
+        assert e.value.code == _lib.GPS_ERR_UNSUPPORTED
+    else:
+        f, g = fit.nlml_grad(par)
+        assert abs(f - c["nlml"]) <= TOL_NLML * abs(c["nlml"])
+        assert relmax(g, c["grad"]) <= TOL_GRAD
     mu, vf, vd = fit.predict(par, np.array(c["Xstar"]))
     assert relmax(mu, c["pred_mean"]) <= TOL_PRED
     sf2 = float(np.exp(par[1]))
@@ -84,8 +90,10 @@ def test_cov_reference_named_entry_point():
     Ks = gp.CovFunc(x, xs, x, None, None, 0.5, 1.3, "SqExp")
     assert np.max(np.abs(K - orc.cov_func(x, x, 0.5, [1.3]))) <= 1e-12
     assert np.max(np.abs(Ks - orc.cov_func(x, xs, 0.5, [1.3]))) <= 1e-12
+    Km = gp.CovFunc(x, x, x, None, 3, 0.5, 1.3, "Matern")
+    assert np.max(np.abs(Km - orc.cov_func(x, x, 0.5, [1.3], "Matern", extra_param=3))) <= 1e-11
     with pytest.raises(gp.GpsError):
-        gp.CovFunc(x, x, x, None, 3, 0.5, 1.3, "Matern")
+        gp.CovFunc(x, x, x, None, None, 0.5, 1.3, "RF")
 
 
 # ---- NLML / gradient / finalize / predict against the oracle -----------------------------------
@@ -394,3 +402,45 @@ def test_not_pd_is_per_fit_and_non_fatal_for_optimisers():
     f2, g2 = bf.nlml_grad(par, not_pd="inf")
     assert np.isinf(f2[0]) and np.all(np.isnan(g2[0])) and relmax(g2[1], orc.nlml_grad(par[1], Xd, yd, evd)) <= 1e-9
     bf.close()
+
+
+# ---- Matern covariances (CovFunc.R:33-37): cov / NLML / finalize / predict / whole Nelder-Mead fit ------------
+@pytest.mark.parametrize("nu", [1, 3, 5])
+def test_matern_matches_oracle(fit0, nu):
+    rng = np.random.default_rng(nu)
+    x1, x2 = rng.standard_normal((150, 4)), rng.standard_normal((60, 4))
+    K = fit0.cov(x1, None, 0.8, [2.0], "Matern", extra_param=nu)
+    Ks = fit0.cov(x1, x2, 0.8, [2.0], "Matern", extra_param=nu)
+    # r = sqrt(r2): the Gram form's absolute error on r2 (~1e-16 * s) becomes ~eps*s/(2r) on r
+    assert np.max(np.abs(K - orc.cov_func(x1, x1, 0.8, [2.0], "Matern", extra_param=nu))) <= 1e-11
+    assert np.max(np.abs(Ks - orc.cov_func(x1, x2, 0.8, [2.0], "Matern", extra_param=nu))) <= 1e-11
+    assert np.all(np.diag(K) == 0.8)
+    pb = synth.make_problem(130, 30, 3, 50, 70 + nu)
+    X, y, ev, Xs = pb["trainingData"], np.log(pb["trainingTargets"]), pb["events"], pb["testData"]
+    lnc = np.full(50, np.log(0.3))
+    par = np.log([0.2, 0.8, 2.5])
+    fit = _make_fit(X, y, ev, "Matern", "Zero", "noiseCorrVec", lnc, extra_param=nu)
+    kw = dict(cov_form="Matern", noise_corr="noiseCorrVec", log_hyp_noise_corr=lnc, extra_param=nu)
+    fo = orc.nlml(par, X, y, ev, **kw)
+    assert abs(fit.nlml(par) - fo) <= TOL_NLML * abs(fo)
+    fin = fit.finalize(par, want_K=True, want_L=True)
+    reg = orc.regress_finalize(par, X, y, ev, "Matern", "Zero", "noiseCorrVec", lnc, extra_param=nu)
+    assert relmax(fin["L"], reg["L"]) <= 1e-9 and relmax(fin["alpha"], reg["alpha"]) <= TOL_PRED
+    mu, vf, vd = fit.predict(par, Xs)
+    reg["logHypChosen"] = {"noise": par[0], "func": par[1], "length": par[2:], "mean": np.zeros(4)}
+    pr = orc.predict(reg, X, y, ev, Xs, "Matern", "Zero", "noiseCorrVec", lnc, extra_param=nu)
+    assert relmax(mu, pr["funcMeanPred"]) <= TOL_PRED and np.max(np.abs(vd - pr["varData"])) <= TOL_PRED
+    fit.close()
+
+
+def test_apply_gp_matern_nelder_mead():
+    pb = synth.make_config_problem(synth.CONFIGS["C1"], scale=0.6)
+    params = dict(modelType="survival", noiseCorr="noiseCorrVec", optimType="Nelder-Mead", maxit=100, maxitSurvival=10,
+                  meanFuncForm="Zero", covFuncForm="Matern", extraParam=3, tolerance=1e-3, maxCount=8,
+                  logHypStart=synth.start_log_hyp(1, "SqExp"), burnIn=False, imposePriors=False)
+    gp.SESSION.reset()
+    r = gp.ApplyGP(pb, {"dataSource": "Generate"}, params)
+    ro = orc.apply_gp(pb, params)
+    assert r["count"] == ro["count"]
+    assert relmax(r["funcMeanPred"].ravel(), ro["funcMeanPred"]) <= 1e-6
+    gp.SESSION.reset()

@@ -23,17 +23,22 @@ def _case_kw(c):
                 log_hyp_noise_corr=c["log_sc2_vec"])
 
 
+def _extra(c):
+    return {"extra_param": c.get("extra_param")} if c.get("extra_param") is not None else {}
+
+
 @pytest.mark.parametrize("c", GOLD["cases"], ids=[c["name"] for c in GOLD["cases"]])
 def test_oracle_matches_mpmath_golden(c):
     X, y, ev = np.array(c["X"]), np.array(c["y"]), np.array(c["events"])
     par = np.array(c["par"])
     kw = _case_kw(c)
     for as_written in (True, False):
-        f = orc.nlml(par, X, y, ev, as_written_ops=as_written, **kw)
+        f = orc.nlml(par, X, y, ev, as_written_ops=as_written, **kw, **_extra(c))
         assert abs(f - c["nlml"]) <= 1e-11 * abs(c["nlml"])
-    g = orc.nlml_grad(par, X, y, ev, **kw)
-    assert np.max(np.abs(g - np.array(c["grad"]))) <= 1e-10 * np.max(np.abs(c["grad"]))
-    reg = orc.regress_finalize(par, X, y, ev, **kw)
+    if c["grad"] is not None:
+        g = orc.nlml_grad(par, X, y, ev, **kw)
+        assert np.max(np.abs(g - np.array(c["grad"]))) <= 1e-10 * np.max(np.abs(c["grad"]))
+    reg = orc.regress_finalize(par, X, y, ev, **kw, **_extra(c))
     assert abs(reg["logMarLik"] + c["nlml"]) <= 1e-11 * abs(c["nlml"])
     d = X.shape[1]
     p = d if c["cov_form"] == "ARD" else 1
@@ -42,10 +47,22 @@ def test_oracle_matches_mpmath_golden(c):
     lnc = par[-1:] if c["noise_corr"] == "noiseCorrLearned" else c["log_sc2_vec"]
     for as_written in (True, False):
         pr = orc.predict(reg, X, y, ev, np.array(c["Xstar"]), c["cov_form"], c["mean_form"], c["noise_corr"], lnc,
-                         as_written_ops=as_written)
+                         as_written_ops=as_written, **_extra(c))
         assert np.allclose(pr["funcMeanPred"], c["pred_mean"], rtol=1e-10, atol=1e-12)
         assert np.allclose(pr["varFunction"], c["pred_varf"], rtol=0, atol=1e-11)
         assert np.allclose(pr["varData"], c["pred_vard"], rtol=0, atol=1e-11)
+
+
+def test_matern_closed_forms():
+    """Matern 1/2 is the exponential kernel; all three equal sf2 at r = 0 and decrease in r."""
+    x = np.array([[0.0], [0.7], [2.0]])
+    for nu in (1, 3, 5):
+        K = orc.cov_func(x, x, 0.9, [1.3], "Matern", extra_param=nu)
+        assert np.allclose(np.diag(K), 0.9) and K[0, 1] > K[0, 2] > 0
+    K1 = orc.cov_func(x, x, 0.9, [1.3], "Matern", extra_param=1)
+    assert abs(K1[0, 1] - 0.9 * math.exp(-0.7 / 1.3)) < 1e-15
+    with pytest.raises(ValueError):
+        orc.cov_func(x, x, 0.9, [1.3], "Matern", extra_param=2)
 
 
 def test_golden_fixture_is_reproducible():
