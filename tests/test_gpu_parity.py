@@ -444,3 +444,72 @@ def test_apply_gp_matern_nelder_mead():
     assert r["count"] == ro["count"]
     assert relmax(r["funcMeanPred"].ravel(), ro["funcMeanPred"]) <= 1e-6
     gp.SESSION.reset()
+
+
+def test_full_size_c4_batch_properties():
+    """C4 shape (n=400, d=2000, ARD GPS3) as a batch of 8 fits: batch entries equal lone fits,
+    gradient agrees with a directional finite difference of the batched NLML."""
+    cfg = synth.CONFIGS["C4"]
+    B = 8
+    pbs = [synth.make_config_problem(cfg, fit_index=i) for i in range(2)]
+    X = np.stack([pbs[i % 2]["trainingData"] for i in range(B)])
+    y = np.stack([np.log(pbs[i % 2]["trainingTargets"]) for i in range(B)])
+    ev = np.stack([pbs[i % 2]["events"] for i in range(B)])
+    d = X.shape[2]
+    c = int(np.sum(ev[0] == 0))
+    lnc = np.full((B, c), np.log(0.2))
+    rng = np.random.default_rng(2)
+    par = np.tile(synth.start_par(cfg, d=d), (B, 1)) + 0.05 * rng.standard_normal((B, 2 + d))
+    bf = gp.Fit(0, batch=B)
+    bf.set_options("ARD", "Zero", "noiseCorrVec")
+    bf.set_data(X, y, ev)
+    bf.set_noise_corr(lnc)
+    f, g = bf.nlml_grad(par)
+    v = rng.standard_normal((B, 2 + d))
+    v /= np.linalg.norm(v, axis=1, keepdims=True)
+    h = 1e-4
+    fd = (bf.nlml(par + h * v) - bf.nlml(par - h * v)) / (2 * h)
+    an = np.sum(g * v, axis=1)
+    assert np.max(np.abs(fd - an) / np.maximum(1.0, np.abs(an))) <= 1e-6
+    one = _make_fit(X[3], y[3], ev[3], "ARD", "Zero", "noiseCorrVec", lnc[3])
+    f1, g1 = one.nlml_grad(par[3])
+    assert abs(f1 - f[3]) <= 1e-12 * abs(f1) and relmax(g[3], g1) <= 1e-10
+    # small enough for the oracle too (n = 400): the batch entry against the reference restatement
+    kw = dict(cov_form="ARD", noise_corr="noiseCorrVec", log_hyp_noise_corr=lnc[3])
+    fo = orc.nlml(par[3], X[3], y[3], ev[3], as_written_ops=False, **kw)
+    assert abs(f[3] - fo) <= TOL_NLML * abs(fo)
+    assert relmax(g[3], orc.nlml_grad(par[3], X[3], y[3], ev[3], **kw)) <= TOL_GRAD
+    one.close()
+    bf.close()
+
+
+def test_full_size_c5_properties():
+    """C5 shape (n=16384, d=50, SqExp, GPS1): too large for the oracle, so size-independent
+    properties — directional derivative, Ky alpha = y on a row sample with the library's own
+    covariance, prediction against K*' alpha, variance bounds."""
+    n, d, m = 16384, 50, 1024
+    rng = np.random.default_rng(4)
+    X = np.asfortranarray(rng.standard_normal((n, d)))
+    Xs = np.asfortranarray(rng.standard_normal((m, d)))
+    y = rng.standard_normal(n)
+    ev = (rng.random(n) > 0.5).astype(np.float64)
+    par = np.log([0.2, 0.8, 1.7 * np.sqrt(d)])
+    fit = gp.Fit(0)
+    fit.set_options("SqExp", "Zero", False)
+    fit.set_data(X, y, ev)
+    f, g = fit.nlml_grad(par)
+    v = np.array([0.6, -0.48, 0.64])
+    h = 1e-4
+    fd = (fit.nlml(par + h * v) - fit.nlml(par - h * v)) / (2 * h)
+    assert abs(fd - g @ v) <= 1e-6 * abs(fd)
+    fin = fit.finalize(par)
+    assert abs(-fin["logMarLik"] - f) <= 1e-12 * abs(f)
+    alpha = fin["alpha"]
+    idx = rng.choice(n, 48, replace=False)
+    Krows = fit.cov(X[idx], X, 0.8, [1.7 * np.sqrt(d)], "SqExp")
+    assert np.max(np.abs(Krows @ alpha + 0.2 * alpha[idx] - y[idx])) <= 1e-9
+    mu, vf, vd = fit.predict(par, Xs)
+    Ks = fit.cov(X, Xs[:24], 0.8, [1.7 * np.sqrt(d)], "SqExp")
+    assert np.max(np.abs(mu[:24] - Ks.T @ alpha)) <= TOL_PRED * max(1.0, np.max(np.abs(mu)))
+    assert np.all(vf >= -1e-9) and np.all(vf <= 0.8 + 1e-9) and np.allclose(vd - vf, 0.2, atol=1e-12)
+    fit.close()
