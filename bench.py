@@ -81,6 +81,17 @@ def config_dict(B, world, n, d, nhyp):
                   % (B, B * 5 * n * n * 8 / 1e9)}
 
 
+def measured_traffic(B):
+    """DRAM bytes of one step from the committed ncu capture of the same workload (bench.py cannot run
+    under ncu itself); None when no capture exists for this batch size."""
+    path = os.path.join(ROOT, "profiles", "r1c_traffic_c2_batch32.json")
+    try:
+        t = json.load(open(path))
+        return float(t["traffic_bytes_per_step"]) if int(t["fits_per_step"]) == int(B) else None
+    except (OSError, ValueError, KeyError):
+        return None
+
+
 def algorithmic_flops(n, d, ard=True):
     return (3.0 if ard else 1.0) * n * n * d + float(n) ** 3       # SURVEY.md §8d
 
@@ -341,7 +352,9 @@ def run_gpu(args):
             "gpu_launches": int(launches),
             "clocks": clocks,
             "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s",
-                         "frac": achieved / peak_tf if peak_tf else None, "traffic": None,
+                         "frac": achieved / peak_tf if peak_tf else None, "traffic": measured_traffic(B),
+                         "traffic_source": "profiles/r1c_traffic_c2_batch32.json: ncu dram__bytes_read.sum + dram__bytes_write.sum "
+                                           "summed over the 85 launches of one step (bytes)",
                          "kernel": "evaluation graph (1 launch = %d NLML+gradient evaluations, %d kernel nodes)"
                                    % (B, launches // max(K, 1)),
                          "algorithmic_flops_per_launch": B * flops,

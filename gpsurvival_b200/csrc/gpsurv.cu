@@ -101,7 +101,7 @@ struct gps_handle_s {
   double last_ms = 0.0;
   int last_pivot = 0;
   std::vector<int> pivots;      // per-fit failing pivot of the last evaluation (0 = factorised)
-  int force_tile = -1;          // developer override of the GEMM tile config (GPS_TILE=0|1|2)
+  int force_tile = -1;          // developer override of the GEMM tile config (GPS_TILE=2: 128 x 128, else 64 x 64)
   int large_min_dim = 1 << 30;  // 128 x 128 tiles only when both M and N reach this (GPS_LARGE_MIN_DIM); measured:
                                 // the 4-warp 64 x 64 tile (3 CTAs/SM) wins at every size up to 8192^3, alone and batched
   std::string err;
@@ -208,14 +208,8 @@ void gemm(H* h, const GemmParams& p, const Epi& epi) {
   if (h->force_tile >= 0) choice = h->force_tile;
   if (choice == 2)
     e = launch_gemm<CfgLarge, A_KC, B_KC, Epi>(p, epi, h->batch, h->st);
-  else if (choice == 1)
-    e = launch_gemm<CfgMid, A_KC, B_KC, Epi>(p, epi, h->batch, h->st);
-  else if (choice == 3)
-    e = launch_gemm<CfgS3, A_KC, B_KC, Epi>(p, epi, h->batch, h->st);
-  else if (choice == 4)
-    e = launch_gemm<CfgK32, A_KC, B_KC, Epi>(p, epi, h->batch, h->st);
   else
-    e = launch_gemm<CfgSmall, A_KC, B_KC, Epi>(p, epi, h->batch, h->st);
+    e = launch_gemm<CfgS3, A_KC, B_KC, Epi>(p, epi, h->batch, h->st);
   h->seq_launches++;
   CKV(h, e);
 }
