@@ -513,3 +513,96 @@ def test_full_size_c5_properties():
     assert np.max(np.abs(mu[:24] - Ks.T @ alpha)) <= TOL_PRED * max(1.0, np.max(np.abs(mu)))
     assert np.all(vf >= -1e-9) and np.all(vf <= 0.8 + 1e-9) and np.allclose(vd - vf, 0.2, atol=1e-12)
     fit.close()
+
+
+# ---- randomized sweep: shapes around every tile / block / padding edge, all option combinations -----------
+def _random_case(seed):
+    rng = np.random.default_rng(seed)
+    n = int(rng.choice([1, 2, 3, 5, 31, 32, 33, 63, 64, 65, 66, 95, 127, 128, 129, 130, 191, 193, 255, 257, 300]))
+    d = int(rng.choice([1, 2, 3, 7, 15, 16, 17, 33, 70]))
+    m = int(rng.choice([1, 2, 7, 64, 65, 130]))
+    cov_form = str(rng.choice(["SqExp", "ARD", "Matern"]))
+    mean_form = str(rng.choice(["Zero", "Linear"])) if n > d + 3 else "Zero"
+    noise_corr = [False, "noiseCorrLearned", "noiseCorrVec"][int(rng.integers(3))]
+    extra = int(rng.choice([1, 3, 5])) if cov_form == "Matern" else None
+    c = int(rng.integers(0, n)) if n > 1 else 0
+    return n, m, d, c, cov_form, mean_form, noise_corr, extra
+
+
+@pytest.mark.parametrize("seed", range(36))
+def test_randomized_shapes_and_options(seed):
+    n, m, d, c, cov_form, mean_form, noise_corr, extra = _random_case(1000 + seed)
+    rng = np.random.default_rng(seed)
+    X = np.asfortranarray(rng.standard_normal((n, d)))
+    Xs = np.asfortranarray(rng.standard_normal((m, d)))
+    y = rng.standard_normal(n)
+    ev = np.ones(n)
+    ev[rng.permutation(n)[:c]] = 0
+    p = d if cov_form == "ARD" else 1
+    par = [np.log(0.3), np.log(0.8)] + list(np.log(1.5 * np.sqrt(d)) + 0.2 * rng.standard_normal(p))
+    if mean_form == "Linear":
+        par += list(0.1 * rng.standard_normal(d + 1))
+    lnc = None
+    if noise_corr == "noiseCorrLearned":
+        par += [np.log(0.3)]
+    if noise_corr == "noiseCorrVec":
+        lnc = np.log(0.2) + 0.5 * rng.standard_normal(c)
+    par = np.array(par)
+    kw = dict(cov_form=cov_form, mean_form=mean_form, noise_corr=noise_corr, log_hyp_noise_corr=lnc)
+    ex = {"extra_param": extra} if extra is not None else {}
+    fit = _make_fit(X, y, ev, cov_form, mean_form, noise_corr, lnc, extra_param=extra)
+    fo = orc.nlml(par, X, y, ev, **kw, **ex)
+    assert abs(fit.nlml(par) - fo) <= TOL_NLML * max(1.0, abs(fo))
+    if cov_form != "Matern":
+        f, g = fit.nlml_grad(par)
+        go = orc.nlml_grad(par, X, y, ev, **kw)
+        assert np.max(np.abs(g - go)) <= TOL_GRAD * max(1.0, float(np.max(np.abs(go))))
+    fin = fit.finalize(par, want_K=True, want_L=True)
+    reg = orc.regress_finalize(par, X, y, ev, cov_form, mean_form, noise_corr, lnc, **ex)
+    assert np.max(np.abs(fin["K"] - reg["K"])) <= 1e-11 and relmax(fin["L"], reg["L"]) <= 1e-9
+    mu, vf, vd = fit.predict(par, Xs)
+    reg["logHypChosen"] = {"noise": par[0], "func": par[1], "length": par[2:2 + p],
+                           "mean": par[2 + p:2 + p + d + 1] if mean_form == "Linear" else np.zeros(d + 1)}
+    pr = orc.predict(reg, X, y, ev, Xs, cov_form, mean_form, noise_corr,
+                     par[-1:] if noise_corr == "noiseCorrLearned" else lnc, **ex)
+    scale = max(1.0, float(np.max(np.abs(pr["funcMeanPred"]))))
+    assert np.max(np.abs(mu - pr["funcMeanPred"])) <= TOL_PRED * scale
+    assert np.max(np.abs(vd - pr["varData"])) <= TOL_PRED
+    fit.close()
+
+
+def test_handle_lifecycle_and_interleaving():
+    """One handle across shape changes; two live handles used alternately (separate streams, graphs, caches)."""
+    rng = np.random.default_rng(9)
+    fa, fb = gp.Fit(0), gp.Fit(0)
+    data = {}
+    for tag, fit, n, d in (("a", fa, 90, 3), ("b", fb, 140, 5)):
+        X, y, ev = rng.standard_normal((n, d)), rng.standard_normal(n), (rng.random(n) > 0.4).astype(float)
+        fit.set_options("ARD", "Zero", "noiseCorrLearned")
+        fit.set_data(X, y, ev)
+        data[tag] = (X, y, ev, np.concatenate([[np.log(0.3), np.log(0.8)], np.full(d, np.log(2.0)), [np.log(0.2)]]))
+    kw = dict(cov_form="ARD", noise_corr="noiseCorrLearned")
+    for rep in range(4):                      # interleave: a.nlml, b.grad, a.grad (cached), b.nlml ...
+        for tag, fit in (("a", fa), ("b", fb)):
+            X, y, ev, par = data[tag]
+            par = par + 0.01 * rep
+            assert abs(fit.nlml(par) - orc.nlml(par, X, y, ev, **kw)) <= 1e-9 * 300
+            other = fb if fit is fa else fa
+            Xo, yo, evo, paro = data["b" if tag == "a" else "a"]
+            _, go = other.nlml_grad(paro)
+            assert relmax(go, orc.nlml_grad(paro, Xo, yo, evo, **kw)) <= TOL_GRAD
+            _, g = fit.nlml_grad(par)         # must reuse this handle's own cached factorisation
+            assert relmax(g, orc.nlml_grad(par, X, y, ev, **kw)) <= TOL_GRAD
+    # shape change on a live handle: reallocation, graphs rebuilt, old model dropped
+    X2, y2, ev2 = rng.standard_normal((33, 2)), rng.standard_normal(33), np.ones(33)
+    fa.set_options("SqExp", "Zero", False)
+    fa.set_data(X2, y2, ev2)
+    par2 = np.log([0.3, 0.8, 1.5])
+    assert abs(fa.nlml(par2) - orc.nlml(par2, X2, y2, ev2)) <= 1e-9 * 100
+    with pytest.raises(gp.GpsError):
+        fa.predict(par2, X2[:3], reuse_model=True)     # no resident model after set_data
+    mu, _, _ = fa.predict(par2, X2[:3])
+    assert np.all(np.isfinite(mu))
+    fa.close()
+    fb.close()
+    fa.close()                                          # double close is harmless
