@@ -21,6 +21,8 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <algorithm>
+#include <cmath>
 #include <string>
 #include <vector>
 
@@ -593,6 +595,12 @@ int copy_out_matrix(H* h, double* dst, const double* src, int rows, int cols, in
 // =========================================================================================
 // C ABI
 // =========================================================================================
+extern "C" {
+int gps_nlml(gps_handle h, const double* par, int len, double* nlml_out);
+int gps_nlml_grad(gps_handle h, const double* par, int len, double* nlml_out, double* grad_out);
+}
+#include "fit_batch.cuh"
+
 extern "C" {
 
 const char* gps_version(void) { return "gpsurv-b200 0.1.0 (sm_100a, FP64 DMMA)"; }
@@ -1182,6 +1190,157 @@ int gps_cov(gps_handle h, const double* X1, int n1, const double* X2, int n2, in
 int gps_batch_pivots(gps_handle h, int* pivots_out) {
   if (!h || !pivots_out) return fail(h, GPS_ERR_ARG, "gps_batch_pivots: bad arguments");
   for (int b = 0; b < h->batch; b++) pivots_out[b] = (b < (int)h->pivots.size()) ? h->pivots[b] : 0;
+  return GPS_OK;
+}
+
+// ApplyGP.R:136-282 for every fit of the batch, in lock-step (C++ twin of batchfit.apply_gp_batch).
+int gps_fit_batch(gps_handle h, const double* X, int n, int d, const double* y_log, const double* events,
+                  const double* par_start, int len, int method, int maxit, double tolerance, int max_count, int survival,
+                  const double* Xtest, int m, double* par_out, double* objective_out, double* logmarlik_out,
+                  int* rounds_out, double* targets_learned_out, double* test_mean, double* test_varf, double* test_vard,
+                  double* train_mean, long long* evaluations_out) {
+  int rc = check_handle(h);
+  if (rc) return rc;
+  if (!X || !y_log || !events || !par_start || !Xtest || n < 1 || d < 1 || m < 1 || (method != 0 && method != 1))
+    return fail(h, GPS_ERR_ARG, "gps_fit_batch: bad arguments");
+  rc = gps_set_data(h, X, n, d, y_log, events);
+  if (rc) return rc;
+  if (len != expected_len(h)) return fail(h, GPS_ERR_ARG, "gps_fit_batch: par_start has the wrong length for these options");
+  if (method == 1 && h->o.cov_form >= GPS_COV_MATERN1)
+    return fail(h, GPS_ERR_UNSUPPORTED, "gps_fit_batch: BFGS needs a gradient, the Matern covariances have none");
+  const int B = h->batch, p = h->p;
+  const int nc = survival ? h->o.noise_corr : GPS_NC_NONE;
+  if (!survival && h->o.noise_corr != GPS_NC_NONE)
+    return fail(h, GPS_ERR_ARG, "gps_fit_batch: a non-survival fit needs noise_corr = none (ApplyGP.R:229)");
+  // censored rows (events == 0), identical count across the batch
+  std::vector<std::vector<int>> cidx(B);
+  for (int b = 0; b < B; b++)
+    for (int i = 0; i < n; i++)
+      if (events[(size_t)b * n + i] == 0.0) cidx[b].push_back(i);
+  const int c = (int)cidx[0].size();
+  if (survival)
+    for (int b = 0; b < B; b++)
+      if ((int)cidx[b].size() != c) return fail(h, GPS_ERR_ARG, "gps_fit_batch: all fits of a batch need the same number of censored rows");
+  FitEvaluator ev{h, len};
+  auto run_opt = [&](const std::vector<double>& starts, const std::vector<char>& active, std::vector<OptResult>& res) {
+    return method == 0 ? run_nelder_mead(ev, starts, len, maxit, active, res) : run_bfgs(ev, starts, len, maxit, active, res);
+  };
+  // logHypChosen: the reference stores log(exp(.)) of noise, func and length (GPRegression.R:39-52,73)
+  auto chosen_vec = [&](const std::vector<double>& v, double* outv) {
+    for (int k = 0; k < len; k++) outv[k] = v[k];
+    for (int k = 0; k < 2 + p; k++) outv[k] = log(exp(v[k]));
+  };
+  std::vector<double> cur(par_start, par_start + (size_t)B * len), vecs((size_t)B * len), pars_pred((size_t)B * len);
+  std::vector<double> learned(y_log, y_log + (size_t)B * n), objective(B, 1.0), lml(B, 0.0), alpha_tmp((size_t)B * n),
+      mean_tmp((size_t)B * n);
+  std::vector<int> count(B, 0);
+  std::vector<OptResult> res;
+  if (survival) {
+    std::vector<double> a_start((size_t)B * c), lnc((size_t)B * (c > 0 ? c : 1)), used_lnc(lnc.size()), used_targets(learned),
+        Xc((size_t)B * (c > 0 ? c : 1) * d), mu((size_t)B * (c > 0 ? c : 1)), vf(mu.size()), vd(mu.size()), em(mu.size()), evr(mu.size()),
+        change(B, 1.0);
+    for (int b = 0; b < B; b++)
+      for (int r = 0; r < c; r++) {
+        a_start[(size_t)b * c + r] = y_log[(size_t)b * n + cidx[b][r]];                    // ApplyGP.R:108
+        lnc[(size_t)b * c + r] = par_start[(size_t)b * len];                               // :149 rep(logHypStart$noise, nCens)
+        for (int k = 0; k < d; k++)
+          Xc[((size_t)b * d + k) * c + r] = X[((size_t)b * d + k) * n + cidx[b][r]];
+      }
+    std::vector<char> active(B, 1);
+    for (;;) {
+      bool any = false;
+      for (int b = 0; b < B; b++) {
+        active[b] = ((change[b] > tolerance && count[b] < max_count) || count[b] <= 5) ? 1 : 0;   // :162
+        any |= active[b] != 0;
+      }
+      if (!any) break;
+      for (int b = 0; b < B; b++)
+        if (active[b]) {
+          std::copy(&learned[(size_t)b * n], &learned[(size_t)b * n] + n, &used_targets[(size_t)b * n]);
+          std::copy(&lnc[(size_t)b * c], &lnc[(size_t)b * c] + c, &used_lnc[(size_t)b * c]);
+        }
+      rc = gps_set_targets(h, used_targets.data());
+      if (rc) return rc;
+      if (nc == GPS_NC_VEC) {
+        rc = gps_set_noise_corr(h, used_lnc.data(), c);
+        if (rc) return rc;
+      }
+      rc = run_opt(cur, active, res);                                                      // :170 (optim)
+      if (rc) return rc;
+      for (int b = 0; b < B; b++)
+        if (active[b]) std::copy(res[b].par.begin(), res[b].par.end(), &vecs[(size_t)b * len]);
+      rc = gps_regress_finalize(h, vecs.data(), len, nullptr, nullptr, alpha_tmp.data(), mean_tmp.data(), lml.data());
+      if (rc) return rc;
+      for (int b = 0; b < B; b++) {
+        std::vector<double> v(&vecs[(size_t)b * len], &vecs[(size_t)b * len] + len);
+        chosen_vec(v, &pars_pred[(size_t)b * len]);
+      }
+      if (c > 0) {
+        rc = gps_predict(h, pars_pred.data(), len, nc == GPS_NC_NONE ? 1 : 0, Xc.data(), c, mu.data(), vf.data(), vd.data());   // :171
+        if (rc) return rc;
+        rc = gps_adjust(h, a_start.data(), mu.data(), vd.data(), B * c, em.data(), evr.data());                                  // :190
+        if (rc) return rc;
+      }
+      for (int b = 0; b < B; b++) {
+        if (!active[b]) continue;
+        std::copy(&pars_pred[(size_t)b * len], &pars_pred[(size_t)b * len] + len, &cur[(size_t)b * len]);    // :185
+        change[b] = fabs(objective[b] - res[b].value);                                                        // :195
+        objective[b] = res[b].value;
+        count[b]++;
+        for (int r = 0; r < c; r++) {
+          learned[(size_t)b * n + cidx[b][r]] = em[(size_t)b * c + r];                                        // :201
+          if (nc == GPS_NC_VEC) {                                                                             // :208-210
+            double lv = log(evr[(size_t)b * c + r]);
+            lnc[(size_t)b * c + r] = std::isinf(lv) ? -1e10 : lv;
+          }
+        }
+        if (logmarlik_out) logmarlik_out[b] = lml[b];
+      }
+    }
+    // final predictions use the post-update targets and noise correction (:237-246)
+    if (nc != GPS_NC_NONE) {
+      rc = gps_set_targets(h, learned.data());
+      if (rc) return rc;
+      if (nc == GPS_NC_VEC) {
+        rc = gps_set_noise_corr(h, lnc.data(), c);
+        if (rc) return rc;
+      }
+    }
+  } else {                                                                                 // :224-232
+    std::vector<char> active(B, 1);
+    rc = run_opt(cur, active, res);
+    if (rc) return rc;
+    for (int b = 0; b < B; b++) {
+      std::copy(res[b].par.begin(), res[b].par.end(), &vecs[(size_t)b * len]);
+      objective[b] = res[b].value;
+      count[b] = 1;
+    }
+    rc = gps_regress_finalize(h, vecs.data(), len, nullptr, nullptr, alpha_tmp.data(), mean_tmp.data(), lml.data());
+    if (rc) return rc;
+    for (int b = 0; b < B; b++) {
+      std::vector<double> v(&vecs[(size_t)b * len], &vecs[(size_t)b * len] + len);
+      chosen_vec(v, &cur[(size_t)b * len]);
+      if (logmarlik_out) logmarlik_out[b] = lml[b];
+    }
+  }
+  const int reuse = (nc == GPS_NC_NONE) ? 1 : 0;
+  std::vector<double> tm((size_t)B * m), tvf((size_t)B * m), tvd((size_t)B * m);
+  rc = gps_predict(h, cur.data(), len, reuse, Xtest, m, tm.data(), tvf.data(), tvd.data());                   // :243 / :245
+  if (rc) return rc;
+  if (test_mean) std::copy(tm.begin(), tm.end(), test_mean);
+  if (test_varf) std::copy(tvf.begin(), tvf.end(), test_varf);
+  if (test_vard) std::copy(tvd.begin(), tvd.end(), test_vard);
+  if (train_mean) {
+    std::vector<double> t2((size_t)B * n), t3((size_t)B * n), t4((size_t)B * n);
+    rc = gps_predict(h, cur.data(), len, reuse, X, n, t2.data(), t3.data(), t4.data());                       // :272 / :280
+    if (rc) return rc;
+    std::copy(t2.begin(), t2.end(), train_mean);
+  }
+  if (par_out) std::copy(cur.begin(), cur.end(), par_out);
+  if (objective_out) std::copy(objective.begin(), objective.end(), objective_out);
+  if (rounds_out) std::copy(count.begin(), count.end(), rounds_out);
+  if (targets_learned_out) std::copy(learned.begin(), learned.end(), targets_learned_out);
+  if (evaluations_out) *evaluations_out = ev.ticks;
   return GPS_OK;
 }
 

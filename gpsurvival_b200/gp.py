@@ -165,6 +165,33 @@ class Fit:
                                   cov_code(cov_form, extra_param), ARD_MODE[ard_mode], dptr(K)))
         return K
 
+    def fit_batch(self, X, y_log, events, par_start, Xtest, method="Nelder-Mead", maxit=10, tolerance=1e-3,
+                  max_count=500, survival=True):
+        """gps_fit_batch: ApplyGP.R:136-282 for every fit of this batched handle, entirely behind the C ABI
+        (optimisers restated in C++).  Arrays carry the batch first: X [B, n, d], Xtest [B, m, d]."""
+        X = np.asarray(X, dtype=np.float64)
+        Xt = np.asarray(Xtest, dtype=np.float64)
+        if X.ndim == 2:
+            X, Xt = X[None], Xt[None]
+        B, n, d = X.shape
+        m = Xt.shape[1]
+        Xc = np.ascontiguousarray(np.transpose(X, (0, 2, 1)))
+        Xtc = np.ascontiguousarray(np.transpose(Xt, (0, 2, 1)))
+        y = np.ascontiguousarray(np.asarray(y_log, dtype=np.float64)).reshape(B, n)
+        ev = np.ascontiguousarray(np.asarray(events, dtype=np.float64)).reshape(B, n)
+        ps = np.ascontiguousarray(np.asarray(par_start, dtype=np.float64)).reshape(B, -1)
+        ln = ps.shape[1]
+        par = np.empty((B, ln)); obj = np.empty(B); lml = np.zeros(B); rounds = (C.c_int * B)()
+        learned = np.empty((B, n)); tm = np.empty((B, m)); tvf = np.empty((B, m)); tvd = np.empty((B, m)); trm = np.empty((B, n))
+        ticks = C.c_longlong()
+        self._ck(self.lib.gps_fit_batch(self.h, dptr(Xc), n, d, dptr(y), dptr(ev), dptr(ps), ln,
+                                        {"Nelder-Mead": 0, "BFGS": 1}[method], int(maxit), float(tolerance), int(max_count),
+                                        1 if survival else 0, dptr(Xtc), m, dptr(par), dptr(obj), dptr(lml), rounds,
+                                        dptr(learned), dptr(tm), dptr(tvf), dptr(tvd), dptr(trm), C.byref(ticks)))
+        self.n, self.d = n, d
+        return {"par": par, "objective": obj, "logMarLik": lml, "count": np.array(list(rounds)), "trainingTargetsLearned": learned,
+                "funcMeanPred": tm, "varFunction": tvf, "varData": tvd, "trainingSetPredictions": trm, "ticks": int(ticks.value)}
+
     # -- measurement helpers -------------------------------------------------------------
     def launch_count(self):
         return int(self.lib.gps_launch_count(self.h))

@@ -129,6 +129,26 @@ int gps_predict(gps_handle h, const double* par, int len, int reuse_model, const
 int gps_adjust(gps_handle h, const double* a, const double* mu, const double* s, int c,
                double* mean_out, double* var_out);
 
+/* ---- whole fits: ApplyGP.R:136-282 with stats::optim restated in C++ ---------- */
+/* Runs, for every fit of the batch in lock-step, what ApplyGP does after its target transforms: for a
+ * survival model the GPS outer loop  while((change > tolerance & count < max_count) | count <= 5)
+ * { GPRegression (optim with `maxit`), GPPredict on the censored rows, AdjustTrainingSurvivalMeanVariance,
+ * target / noise-correction update }  (ApplyGP.R:162-214), otherwise one GPRegression (:224-232); then
+ * the test-set and training-set predictions (:237-282).  Options (covariance, mean, noiseCorr) come
+ * from gps_set_options; y_log are the log (and, for real data, median-shifted) targets of ApplyGP.R:77-96.
+ * method: 0 = 'Nelder-Mead' (R's nmmin), 1 = 'BFGS' (R's vmmin, dense state kept on the device).
+ * par_start: batch x len start vectors as GPRegression.R:22-25 assembles them (restarts may differ per fit;
+ * for GPS3 the start noise correction is rep(par_start[0], nCensored), ApplyGP.R:149).
+ * A point whose Ky is not positive definite is a rejected point (+Inf) for the optimiser.
+ * Outputs (any may be NULL): par_out batch x len = logHypChosen flattened; objective_out, logmarlik_out,
+ * rounds_out: batch; targets_learned_out, train_mean: batch x n; test_*: batch x m;
+ * evaluations_out: number of batched evaluations used. */
+int gps_fit_batch(gps_handle h, const double* X, int n, int d, const double* y_log, const double* events,
+                  const double* par_start, int len, int method, int maxit, double tolerance, int max_count, int survival,
+                  const double* Xtest, int m, double* par_out, double* objective_out, double* logmarlik_out,
+                  int* rounds_out, double* targets_learned_out, double* test_mean, double* test_varf, double* test_vard,
+                  double* train_mean, long long* evaluations_out);
+
 /* ---- introspection used by bench.py / tests ------------------------------------------- */
 /* Number of kernels this handle has launched since creation (bench.py's gpu_launches). */
 long long gps_launch_count(gps_handle h);

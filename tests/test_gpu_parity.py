@@ -606,3 +606,56 @@ def test_handle_lifecycle_and_interleaving():
     fa.close()
     fb.close()
     fa.close()                                          # double close is harmless
+
+
+# ---- C-side whole fits (gps_fit_batch) against the Python lock-step driver and the sequential mirror ----------
+@pytest.mark.parametrize("model,nc,method,cov", [("GPS1", False, "Nelder-Mead", "SqExp"), ("GPS2", "noiseCorrLearned", "Nelder-Mead", "SqExp"),
+                                                 ("GPS3", "noiseCorrVec", "Nelder-Mead", "ARD"), ("GPS3", "noiseCorrVec", "BFGS", "ARD"),
+                                                 ("GPS2", "noiseCorrLearned", "BFGS", "ARD")])
+def test_c_side_fit_batch_matches_python_driver(model, nc, method, cov):
+    from gpsurvival_b200 import batchfit
+    B, n, d = 4, 70, 2
+    pbs = [synth.make_problem(n, 15, d, 28, 900 + b) for b in range(B)]
+    rng = np.random.default_rng(3)
+    starts = [synth.start_log_hyp(d, cov, rng) for _ in range(B)]
+    maxit = 10 if method == "Nelder-Mead" else 4
+    params = dict(modelType="survival", noiseCorr=nc, optimType=method, maxit=100, maxitSurvival=maxit, meanFuncForm="Zero",
+                  covFuncForm=cov, tolerance=0.02, maxCount=9, logHypStart=starts, burnIn=False, imposePriors=False)
+    ref = batchfit.apply_gp_batch(pbs, params)
+    X = np.stack([p["trainingData"] for p in pbs])
+    Xt = np.stack([p["testData"] for p in pbs])
+    y = np.log(np.stack([p["trainingTargets"] for p in pbs]))
+    ev = np.stack([p["events"] for p in pbs])
+    par0 = np.stack([gp._flatten(s, d, "Zero", nc, s["noise"] if nc == "noiseCorrLearned" else None) for s in starts])
+    fit = gp.Fit(0, batch=B)
+    fit.set_options(cov, "Zero", nc)
+    out = fit.fit_batch(X, y, ev, par0, Xt, method=method, maxit=maxit, tolerance=0.02, max_count=9, survival=True)
+    for b in range(B):
+        assert out["count"][b] == ref[b]["count"]
+        assert abs(out["objective"][b] - ref[b]["objective"]) <= 1e-7 * max(1.0, abs(ref[b]["objective"]))
+        assert relmax(out["funcMeanPred"][b], ref[b]["funcMeanPred"].ravel()) <= 1e-6
+        assert relmax(out["varData"][b], ref[b]["varData"]) <= 1e-6
+        assert relmax(out["trainingSetPredictions"][b], ref[b]["trainingSetPredictions"].ravel()) <= 1e-6
+        assert relmax(out["trainingTargetsLearned"][b], ref[b]["trainingTargetsLearned"]) <= 1e-6
+    assert out["ticks"] == ref[0]["ticks"]
+    fit.close()
+
+
+def test_c_side_fit_batch_non_survival_and_errors():
+    pb = synth.make_problem(60, 10, 1, 0, 77)
+    X, y, ev = pb["trainingData"], np.log(pb["trainingTargets"]), pb["events"]
+    fit = gp.Fit(0)
+    fit.set_options("SqExp", "Zero", False)
+    par0 = np.log([0.2, 0.8, 1.7])
+    out = fit.fit_batch(X, y, ev, par0, pb["testData"], method="Nelder-Mead", maxit=200, survival=False)
+    params = dict(modelType="non-survival", noiseCorr=False, optimType="Nelder-Mead", maxit=200, maxitSurvival=10, meanFuncForm="Zero",
+                  covFuncForm="SqExp", tolerance=1e-3, maxCount=10, logHypStart=synth.start_log_hyp(1, "SqExp"))
+    ro = orc.apply_gp(pb, params)
+    assert abs(out["objective"][0] - ro["objective"]) <= 1e-7 * abs(ro["objective"])
+    assert relmax(out["funcMeanPred"][0], ro["funcMeanPred"]) <= 1e-6
+    fit.set_options("Matern", "Zero", False, "intended", 3)
+    with pytest.raises(gp.GpsError):
+        fit.fit_batch(X, y, ev, par0, pb["testData"], method="BFGS", survival=False)     # no Matern gradient
+    with pytest.raises(gp.GpsError):
+        fit.fit_batch(X, y, ev, np.zeros(5), pb["testData"], survival=False)              # wrong par length
+    fit.close()
