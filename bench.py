@@ -311,21 +311,17 @@ def run_gpu(args):
         # x one optim() run of maxitSurvival = 10 + test and training predictions), B fits in lock-step
         fits = {}
         try:
-            from gpsurvival_b200 import batchfit
-            probs = []
-            for i in range(B):
-                probs.append({"trainingData": X[i], "trainingTargets": np.exp(y[i]), "events": ev[i], "testData": X[i][:500]})
             rs = np.random.default_rng(5)
             starts = [synth.start_log_hyp(d, CFG.cov_form, rs) for _ in range(B)]
+            par_start = np.stack([gp._flatten(s0, d, "Zero", CFG.noise_corr, None) for s0 in starts])
+            Xtest = X[:, :500, :]
             for method in ("Nelder-Mead", "BFGS"):
-                prm = dict(modelType="survival", noiseCorr=CFG.noise_corr, optimType=method, maxit=100, maxitSurvival=10,
-                           meanFuncForm="Zero", covFuncForm=CFG.cov_form, tolerance=1e300, maxCount=6, logHypStart=starts,
-                           burnIn=False, imposePriors=False)
                 tt = time.perf_counter()
-                rr = batchfit.apply_gp_batch(probs, prm, fit=fit)
+                rr = fit.fit_batch(X, y, ev, par_start, Xtest, method=method, maxit=10, tolerance=1e300, max_count=6,
+                                   survival=True)                      # whole fits behind the C ABI (gps_fit_batch)
                 dtf = time.perf_counter() - tt
-                fits[method] = {"fits_per_sec": B / dtf, "seconds": dtf, "batched_evaluations": int(rr[0]["ticks"]),
-                                "rounds": int(rr[0]["count"]), "mean_objective": float(np.mean([q["objective"] for q in rr]))}
+                fits[method] = {"fits_per_sec": B / dtf, "seconds": dtf, "batched_evaluations": int(rr["ticks"]),
+                                "rounds": int(rr["count"][0]), "mean_objective": float(np.mean(rr["objective"]))}
             fit.set_options(CFG.cov_form, "Zero", CFG.noise_corr, "intended")
             fit.set_data(X, y, ev)
             fit.set_noise_corr(lnc)
@@ -364,8 +360,8 @@ def run_gpu(args):
                                "frac_of_cublas_dgemm": (2.0 * 8192 ** 3 / (gemm_ms * 1e-3) / 1e12) / peak_tf if peak_tf else None},
             "stages_ms": {"gram": stages[0], "cholesky": stages[1], "tri_inverse": stages[2], "kinv": stages[3],
                           "wk_grad": stages[4], "total": stages[7]},
-            "gps3_fits": dict(fits, protocol="6 GPS rounds x optim(maxitSurvival=10) + test/train predictions, %d fits in "
-                                             "lock-step on one GPU (SURVEY.md §8d)" % B),
+            "gps3_fits": dict(fits, protocol="gps_fit_batch (C ABI): 6 GPS rounds x optim(maxitSurvival=10) + test/train "
+                                             "predictions, %d fits in lock-step on one GPU (SURVEY.md §8d)" % B),
             "single_fit": {"nlml_grad_ms": single_ms, "nlml_ms": single_nlml_ms, "evals_per_sec": 1e3 / single_ms,
                            "tflops": flops / (single_ms * 1e-3) / 1e12},
             "cpu_baseline": {"value": cpu_val, "unit": UNIT, "cores": cpu_threads(), "kind": "port",
