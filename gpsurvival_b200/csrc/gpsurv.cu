@@ -64,11 +64,11 @@ struct gps_handle_s {
   // per-evaluation small state
   double *par = nullptr, *hyp = nullptr, *ell = nullptr, *meanw = nullptr, *noise_diag = nullptr;
   double *rnpart = nullptr, *rnorm = nullptr, *meanv = nullptr, *zvec = nullptr, *alpha = nullptr;
-  double *wdiag = nullptr, *rs = nullptr, *colpart = nullptr, *qtu = nullptr, *d_nlml = nullptr, *d_logdet = nullptr,
+  double *wdiag = nullptr, *rs = nullptr, *rs_part = nullptr, *colpart = nullptr, *qtu = nullptr, *d_nlml = nullptr, *d_logdet = nullptr,
          *d_grad = nullptr;
   int* info = nullptr;
   int par_cap = 0;
-  int rn_ksplit = 1, gram_ksplit = 1, mtiles_grad = 1;
+  int rn_ksplit = 1, gram_ksplit = 1, mtiles_grad = 1, grad_ksplit = 1;
   // matrices (work set)
   double *K = nullptr, *Ky = nullptr, *L = nullptr, *Linv = nullptr, *Kinv = nullptr, *gsplit = nullptr;
   size_t gsplit_elems = 0;
@@ -167,7 +167,7 @@ void free_data(H* h) {
   dfree(h->cens_rank); dfree(h->d_ncens);
   dfree(h->par); dfree(h->hyp); dfree(h->ell); dfree(h->meanw); dfree(h->noise_diag);
   dfree(h->rnpart); dfree(h->rnorm); dfree(h->meanv); dfree(h->zvec); dfree(h->alpha);
-  dfree(h->wdiag); dfree(h->rs); dfree(h->colpart); dfree(h->qtu); dfree(h->d_nlml); dfree(h->d_logdet);
+  dfree(h->wdiag); dfree(h->rs); dfree(h->rs_part); dfree(h->colpart); dfree(h->qtu); dfree(h->d_nlml); dfree(h->d_logdet);
   dfree(h->d_grad); dfree(h->info);
   dfree(h->K); dfree(h->Ky); dfree(h->L); dfree(h->Linv); dfree(h->Kinv); dfree(h->gsplit);
   dfree(h->mL); dfree(h->mLinv); dfree(h->m_alpha); dfree(h->m_hyp); dfree(h->m_ell); dfree(h->m_meanw);
@@ -420,19 +420,19 @@ void enqueue_grad(H* h) {
   wk_kernel<<<dim3(ceil_div(n, 32), ceil_div(n, 32), h->batch), dim3(32, 8), 0, h->st>>>(h->Kinv, h->K, n, ld, sM, aw,
                                                                                        h->ld, h->Ky, h->wdiag);
   LAUNCHED(h);
-  {  // (M Xaug) contracted with Xaug column by column; last column gives rowsum(M)
+  {  // (M Xaug) contracted with Xaug column by column; last column gives rowsum(M).  With few column tiles
+     // (small d) the K = n loop is split deterministically so that the launch fills the GPU.
     GemmParams p = gp(h->Ky, ld, sM, h->Xaug, h->ldx, h->strideX, n, h->d + 1, n);
+    p.ksplit = h->grad_ksplit;
     EpiColDot e;
     e.X = h->Xaug; e.ldx = h->ldx; e.strideX = h->strideX; e.colpart = h->colpart; e.ldp = h->ldmu;
-    e.rs = h->rs; e.ldn = h->ld;
-    // the tile config decides the number of m tiles: mirror gemm()'s choice
-    long long tl = (long long)ceil_div(n, 128) * ceil_div(h->d + 1, 128) * h->batch;
-    bool large = (tl >= 100 && h->d + 1 >= 96 && n >= h->large_min_dim && h->d + 1 >= h->large_min_dim);
-    if (h->force_tile >= 0) large = (h->force_tile == 2);
-    e.mtiles = ceil_div(n, large ? 128 : 64);
-    h->mtiles_grad = e.mtiles;
+    e.rs = h->rs_part; e.ldn = h->ld;
+    e.mtiles = ceil_div(n, h->force_tile == 2 ? 128 : 64);
+    h->mtiles_grad = e.mtiles * h->grad_ksplit;
     gemm<false, true>(h, p, e);
   }
+  rs_reduce_kernel<<<dim3(ceil_div(n, 256), h->batch), 256, 0, h->st>>>(h->rs_part, n, h->ld, h->grad_ksplit, h->rs);
+  LAUNCHED(h);
   grad_cols_kernel<<<dim3(ceil_div(h->d + 1, 8), h->batch), 256, 0, h->st>>>(h->Xaug, n, h->d, h->ldx, h->strideX,
                                                                              h->colpart, h->ldmu, h->mtiles_grad, h->rs,
                                                                              h->alpha, h->ld, h->qtu, h->ell, h->ldmu,
@@ -744,7 +744,14 @@ int gps_set_data(gps_handle h, const double* X, int n, int d, const double* y, c
   CK(h, dalloc(&h->alpha, vecB * 2));
   CK(h, dalloc(&h->wdiag, vecB));
   CK(h, dalloc(&h->rs, vecB));
-  CK(h, dalloc(&h->colpart, (size_t)h->ldmu * ceil_div(n, 64) * B));
+  {   // split-K of the gradient contraction: aim at >= 2 CTAs per SM, at least 8 k-tiles per slice
+    long long ctas = (long long)ceil_div(n, 64) * ceil_div(d + 1, 64) * B;
+    int ks = (int)((2 * 148 + ctas - 1) / ctas);
+    int maxks = n / 128 > 1 ? n / 128 : 1;
+    h->grad_ksplit = ks < 1 ? 1 : (ks > maxks ? maxks : (ks > 16 ? 16 : ks));
+  }
+  CK(h, dalloc(&h->colpart, (size_t)h->ldmu * ceil_div(n, 64) * h->grad_ksplit * B));
+  CK(h, dalloc(&h->rs_part, vecB * h->grad_ksplit));
   CK(h, dalloc(&h->qtu, (size_t)h->ldmu * 3 * B));
   CK(h, dalloc(&h->d_nlml, (size_t)B));
   CK(h, dalloc(&h->d_logdet, (size_t)B));

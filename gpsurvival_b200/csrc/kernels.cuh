@@ -634,6 +634,7 @@ __global__ void grad_cols_kernel(const double* __restrict__ X, int n, int d, int
                                  const double* __restrict__ rs, const double* __restrict__ alpha, int ldn,
                                  double* __restrict__ qtu, const double* __restrict__ ell, int ldell, int ard,
                                  int len, double* __restrict__ grad) {
+  // rs here is the REDUCED rowsum(M) (rs_reduce_kernel), mtiles counts the split-K slices too
   int k = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31, b = blockIdx.y;
   if (k > d) return;
   const double* x = X + (size_t)b * strideX + (size_t)k * ldx;
@@ -659,6 +660,16 @@ __global__ void grad_cols_kernel(const double* __restrict__ X, int n, int d, int
       grad[(size_t)b * len + 2 + k] = -(t - q) / (e * e);
     }
   }
+}
+
+// rowsum(M)[i] = sum over the split-K slices of the gradient GEMM's last column (fixed order).
+// grid (ceil(n/256), batch)
+__global__ void rs_reduce_kernel(const double* __restrict__ rs_part, int n, int ldn, int ksplit, double* __restrict__ rs) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x, b = blockIdx.y;
+  if (i >= n) return;
+  double s = 0.0;
+  for (int k = 0; k < ksplit; k++) s += rs_part[((size_t)b * ksplit + k) * ldn + i];
+  rs[(size_t)b * ldn + i] = s;
 }
 
 // grad_finish (OptimisationGradientLog.R:51-57,88-89 in W-form). grid (batch), block 256.
