@@ -1200,6 +1200,35 @@ int gps_batch_pivots(gps_handle h, int* pivots_out) {
   return GPS_OK;
 }
 
+// MakeSyntheticData.R:41,148: f = t(chol(K)) %*% d1 with K the covariance at `par` (its first entry, the
+// noise variance, acts as the diagonal jitter the reference obtains from nearPD when K is numerically singular).
+int gps_chol_matvec(gps_handle h, const double* par, int len, const double* v, double* out) {
+  int rc = check_handle(h);
+  if (rc) return rc;
+  if (!v || !out) return fail(h, GPS_ERR_ARG, "gps_chol_matvec: bad arguments");
+  rc = do_factor(h, par, len, true);
+  if (rc) return rc;
+  const int B = h->batch, n = h->n;
+  rc = ensure_pin(h, (size_t)2 * n * B + 4096);
+  if (rc) return rc;
+  CK(h, cudaStreamSynchronize(h->st));
+  memcpy(h->pin, v, sizeof(double) * n * B);
+  // zvec (2 x ld per fit) is free after the factorisation: slot 0 = v, slot 1 = L v
+  CK(h, cudaMemcpy2DAsync(h->zvec, (size_t)2 * h->ld * sizeof(double), h->pin, (size_t)n * sizeof(double),
+                          (size_t)n * sizeof(double), B, cudaMemcpyHostToDevice, h->st));
+  trmv_lower_kernel<<<dim3(ceil_div(n, 128), B), 128, 0, h->st>>>(h->L, n, h->ld, h->strideM, h->zvec, 2 * h->ld,
+                                                                   h->zvec + h->ld);
+  h->launches++;
+  CK(h, cudaGetLastError());
+  CK(h, cudaMemcpy2DAsync(h->pin + (size_t)n * B, (size_t)n * sizeof(double), h->zvec + h->ld, (size_t)2 * h->ld * sizeof(double),
+                          (size_t)n * sizeof(double), B, cudaMemcpyDeviceToHost, h->st));
+  rc = fetch_info(h);
+  if (rc) return rc;
+  memcpy(out, h->pin + (size_t)n * B, sizeof(double) * n * B);
+  h->fact_level = 0;
+  return GPS_OK;
+}
+
 // ApplyGP.R:136-282 for every fit of the batch, in lock-step (C++ twin of batchfit.apply_gp_batch).
 int gps_fit_batch(gps_handle h, const double* X, int n, int d, const double* y_log, const double* events,
                   const double* par_start, int len, int method, int maxit, double tolerance, int max_count, int survival,

@@ -744,6 +744,19 @@ __global__ void predict_finish_kernel(const double* __restrict__ Ks, const doubl
   }
 }
 
+// out[i] = sum_{k <= i} L[i,k] * v[k]   (t(chol(K)) %*% d1 of MakeSyntheticData.R:148; L lower, column-major).
+// One thread per row, serial over k (coalesced across the rows of a block). grid (ceil(n/128), batch), block 128.
+__global__ void trmv_lower_kernel(const double* __restrict__ L, int n, int ld, long long stride, const double* __restrict__ v,
+                                  int ldn, double* __restrict__ out) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x, b = blockIdx.y;
+  if (i >= n) return;
+  const double* Lb = L + (size_t)b * stride + i;
+  const double* vb = v + (size_t)b * ldn;
+  double s = 0.0;
+  for (int k = 0; k <= i; k++) s += Lb[(size_t)k * ld] * vb[k];
+  out[(size_t)b * ldn + i] = s;
+}
+
 // mstar[j] = Xc*[j,:] . w + b'  (MeanFunc.R on testData). grid (ceil(m/128), batch), block 128
 __global__ void mean_kernel(const double* __restrict__ X, int m, int d, int ldx, long long strideX,
                             const double* __restrict__ meanw, int ldmu, int linear, double* __restrict__ out,

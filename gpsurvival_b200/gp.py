@@ -165,6 +165,14 @@ class Fit:
                                   cov_code(cov_form, extra_param), ARD_MODE[ard_mode], dptr(K)))
         return K
 
+    def chol_matvec(self, par, v):
+        """t(chol(K(par) + exp(par[0]) I)) %*% v for the handle's data (MakeSyntheticData.R:41,148)."""
+        p, ln = self._par(par)
+        v = np.ascontiguousarray(np.asarray(v, dtype=np.float64)).reshape(self.batch, self.n)
+        out = np.empty_like(v)
+        self._ck(self.lib.gps_chol_matvec(self.h, dptr(p), ln, dptr(v), dptr(out)))
+        return out if self.batch > 1 else out[0]
+
     def fit_batch(self, X, y_log, events, par_start, Xtest, method="Nelder-Mead", maxit=10, tolerance=1e-3,
                   max_count=500, survival=True):
         """gps_fit_batch: ApplyGP.R:136-282 for every fit of this batched handle, entirely behind the C ABI

@@ -14,7 +14,8 @@ reference.  Generating hyper-parameters sn2=0.01, sf2=0.5 (runSyntheticExp1.R:97
 ell_gen = 1.1*sqrt(d); start hyper-parameters sn2=0.2, sf2=0.8, ell=1.7*sqrt(d)
 (runSyntheticExp1.R:139, scaled by sqrt(d) so r^2 = O(1) at every d).
 
-numpy only — no CUDA, no oracle imports.
+numpy only by default (runs anywhere); `gpu_sampler` optionally moves the one O(n^3) step of the recipe,
+t(chol(K)) %*% d1, to the GPU through gps_chol_matvec.  No oracle imports.
 """
 from __future__ import annotations
 
@@ -63,7 +64,27 @@ def _sqexp_gram(X, sf2, ell):
     return sf2 * np.exp(-0.5 * r2)
 
 
-def make_problem(n, m, d, c, seed, sn2_gen=0.01, sf2_gen=0.5):
+def gpu_sampler(device=0):
+    """Returns sampler(X, sf2, ell, d1) -> t(chol(K)) %*% d1 computed on the GPU (gps_chol_matvec), for
+    input generation at sizes where the host Cholesky would dominate (C5: 20 480 rows)."""
+    def sample(X, sf2, ell, d1):
+        from . import gp
+        fit = gp.Fit(device)
+        fit.set_options("SqExp", "Zero", False)
+        fit.set_data(X, np.zeros(X.shape[0]), None)
+        jitter = 1e-8
+        while True:
+            try:
+                out = fit.chol_matvec(np.log([jitter, sf2, ell]), d1)
+                break
+            except gp.NotPositiveDefinite:
+                jitter *= 10.0
+        fit.close()
+        return out
+    return sample
+
+
+def make_problem(n, m, d, c, seed, sn2_gen=0.01, sf2_gen=0.5, sampler=None):
     """One synthetic right-censored data set in the shape of trainingTestStructure.
 
     Returns a dict with trainingData (n x d), trainingTargets (n,), events (n,, 0=censored),
@@ -73,15 +94,20 @@ def make_problem(n, m, d, c, seed, sn2_gen=0.01, sf2_gen=0.5):
     nt = n + m
     X = rng.standard_normal((nt, d))
     ell = 1.1 * math.sqrt(d)
-    K = _sqexp_gram(X, sf2_gen, ell)
-    jitter = 1e-8
-    while True:
-        try:
-            L = np.linalg.cholesky(K + jitter * np.eye(nt))
-            break
-        except np.linalg.LinAlgError:
-            jitter *= 10.0
-    f = L @ rng.standard_normal(nt) + math.sqrt(sn2_gen) * rng.standard_normal(nt)
+    d1 = rng.standard_normal(nt)
+    if sampler is not None:
+        f = sampler(X, sf2_gen, ell, d1)
+    else:
+        K = _sqexp_gram(X, sf2_gen, ell)
+        jitter = 1e-8
+        while True:
+            try:
+                L = np.linalg.cholesky(K + jitter * np.eye(nt))
+                break
+            except np.linalg.LinAlgError:
+                jitter *= 10.0
+        f = L @ d1
+    f = f + math.sqrt(sn2_gen) * rng.standard_normal(nt)
     y_pre = np.exp(f)
     # the first n rows are the training set (rows are iid, so a fixed split is a random split)
     y = y_pre.copy()

@@ -129,6 +129,12 @@ int gps_predict(gps_handle h, const double* par, int len, int reuse_model, const
 int gps_adjust(gps_handle h, const double* a, const double* mu, const double* s, int c,
                double* mean_out, double* var_out);
 
+/* ---- MakeSyntheticData.R:41,148 (synthetic targets) ---------------------------------- */
+/* out = t(chol(Ky)) %*% v = L v, with Ky = K(par) + exp(par[0]) I built from the handle's data and options
+ * (par[0] plays the role of the jitter the reference gets from nearPD when K is numerically singular).
+ * v, out: batch x n.  The caller finishes the recipe: y = exp(mean + out + sqrt(sn2_gen) * d2). */
+int gps_chol_matvec(gps_handle h, const double* par, int len, const double* v, double* out);
+
 /* ---- whole fits: ApplyGP.R:136-282 with stats::optim restated in C++ ---------- */
 /* Runs, for every fit of the batch in lock-step, what ApplyGP does after its target transforms: for a
  * survival model the GPS outer loop  while((change > tolerance & count < max_count) | count <= 5)

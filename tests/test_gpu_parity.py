@@ -659,3 +659,24 @@ def test_c_side_fit_batch_non_survival_and_errors():
     with pytest.raises(gp.GpsError):
         fit.fit_batch(X, y, ev, np.zeros(5), pb["testData"], survival=False)              # wrong par length
     fit.close()
+
+
+def test_chol_matvec_and_gpu_sampler():
+    """MakeSyntheticData.R:41,148: t(chol(K)) %*% d1 on the device against numpy."""
+    rng = np.random.default_rng(8)
+    n, d = 333, 6
+    X = rng.standard_normal((n, d))
+    par = np.log([1e-6, 0.5, 1.1 * np.sqrt(d)])
+    fit = gp.Fit(0)
+    fit.set_options("SqExp", "Zero", False)
+    fit.set_data(X, np.zeros(n), None)
+    v = rng.standard_normal(n)
+    out = fit.chol_matvec(par, v)
+    K = orc.cov_func(X, X, 0.5, [1.1 * np.sqrt(d)]) + 1e-6 * np.eye(n)
+    ref = np.linalg.cholesky(K) @ v
+    assert relmax(out, ref) <= 1e-9
+    fit.close()
+    a = synth.make_problem(200, 40, 3, 80, 5)
+    b = synth.make_problem(200, 40, 3, 80, 5, sampler=synth.gpu_sampler(0))
+    assert np.array_equal(a["trainingData"], b["trainingData"])
+    assert relmax(np.log(b["trainingTargetsPreCensoring"]), np.log(a["trainingTargetsPreCensoring"])) <= 1e-5
