@@ -48,8 +48,10 @@ struct DevBuf {
 struct gps_handle_s {
   int device = 0;
   int batch = 1;
-  cudaStream_t st = nullptr;
-  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  cudaStream_t st = nullptr, st2 = nullptr, cur = nullptr;   // main stream, look-ahead helper, stream of the next launch
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_fork = nullptr, ev_join = nullptr;
+  bool pending_join = false;    // work on st2 that the main stream must wait for after its next panel
+  bool lookahead = false;       // measured SLOWER on B200 (graph fork/join latency > overlapped panel): off; GPS_LOOKAHEAD=1 to try
   ModelOpts o{0, 0, 0, 0};
   bool have_data = false;
   int n = 0, d = 0, p = 1, ne = 0, nrhs = 1, naug = 0;
@@ -209,9 +211,9 @@ void gemm(H* h, const GemmParams& p, const Epi& epi) {
   int choice = (tl >= need && p.N >= 96 && p.M >= h->large_min_dim && p.N >= h->large_min_dim) ? 2 : 3;
   if (h->force_tile >= 0) choice = h->force_tile;
   if (choice == 2)
-    e = launch_gemm<CfgLarge, A_KC, B_KC, Epi>(p, epi, h->batch, h->st);
+    e = launch_gemm<CfgLarge, A_KC, B_KC, Epi>(p, epi, h->batch, h->cur);
   else
-    e = launch_gemm<CfgS3, A_KC, B_KC, Epi>(p, epi, h->batch, h->st);
+    e = launch_gemm<CfgS3, A_KC, B_KC, Epi>(p, epi, h->batch, h->cur);
   h->seq_launches++;
   CKV(h, e);
 }
@@ -304,6 +306,11 @@ void launch_panel(H* h, int e0, int nb, int M, long long* dbg) {
   else
     panel_kernel<128><<<grid, 256, PANEL_SMEM, h->st>>>(h->Ky, h->L, h->Linv, h->ld, h->strideM, e0, nb, M, best_T, h->info, dbg);
   LAUNCHED(h);
+  if (h->pending_join) {   // look-ahead: the rest of the previous trailing update ran beside this panel
+    CKV(h, cudaEventRecord(h->ev_join, h->st2));
+    CKV(h, cudaStreamWaitEvent(h->st, h->ev_join, 0));
+    h->pending_join = false;
+  }
 }
 
 // ---------------------------------------------------------------------------------------
@@ -325,10 +332,31 @@ void potrf_range(H* h, int j0, int j1) {
   potrf_range(h, j0, mid);
   int r0 = mid * NB, c0 = j0 * NB, c1 = (j1 * NB < h->ne) ? j1 * NB : h->ne;
   // Ky[r0:naug, r0:c1] -= L[r0:naug, c0:r0] * L[r0:c1, c0:r0]'
-  GemmParams p = gp(h->L + r0 + (size_t)c0 * ld, ld, sM, h->L + r0 + (size_t)c0 * ld, ld, sM, h->naug - r0, c1 - r0,
-                    r0 - c0);
-  p.lower = 1;
-  gemm<false, false>(h, p, plain(h->Ky + r0 + (size_t)r0 * ld, ld, sM, -1.0, 1.0));
+  // Optional look-ahead (GPS_LOOKAHEAD=1, default off): the next panel only needs block column r0 of this
+  // update, so the update is split into (a) that block column, on the main stream, and (b) the remaining
+  // lower square, on the helper stream, which then runs beside the next panel (the join is issued right after
+  // that panel's launch).  Measured on B200 (round 1): correct but slower — lone C2 1.87 -> 2.22 ms, n = 8192
+  // Cholesky 10.9 -> 12.4 ms, C2 x 32 13.1 -> 13.4 ms: the extra launch and the cross-stream dependency
+  // latency of the graph cost more than the 18 us panel they hide.
+  const int K = r0 - c0, ncols = c1 - r0;
+  if (h->lookahead && ncols > NB) {
+    GemmParams pa = gp(h->L + r0 + (size_t)c0 * ld, ld, sM, h->L + r0 + (size_t)c0 * ld, ld, sM, h->naug - r0, NB, K);
+    pa.lower = 1;
+    gemm<false, false>(h, pa, plain(h->Ky + r0 + (size_t)r0 * ld, ld, sM, -1.0, 1.0));
+    CKV(h, cudaEventRecord(h->ev_fork, h->st));
+    CKV(h, cudaStreamWaitEvent(h->st2, h->ev_fork, 0));
+    const int r1 = r0 + NB;
+    GemmParams pb = gp(h->L + r1 + (size_t)c0 * ld, ld, sM, h->L + r1 + (size_t)c0 * ld, ld, sM, h->naug - r1, c1 - r1, K);
+    pb.lower = 1;
+    h->cur = h->st2;
+    gemm<false, false>(h, pb, plain(h->Ky + r1 + (size_t)r1 * ld, ld, sM, -1.0, 1.0));
+    h->cur = h->st;
+    h->pending_join = true;
+  } else {
+    GemmParams p = gp(h->L + r0 + (size_t)c0 * ld, ld, sM, h->L + r0 + (size_t)c0 * ld, ld, sM, h->naug - r0, ncols, K);
+    p.lower = 1;
+    gemm<false, false>(h, p, plain(h->Ky + r0 + (size_t)r0 * ld, ld, sM, -1.0, 1.0));
+  }
   potrf_range(h, mid, j1);
 }
 
@@ -633,6 +661,9 @@ int gps_create_batch(int device, int batch, gps_handle* out) {
   h->device = device;
   h->batch = batch;
   if (cudaSetDevice(device) != cudaSuccess || cudaStreamCreateWithFlags(&h->st, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaStreamCreateWithFlags(&h->st2, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
+      cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming) != cudaSuccess ||
       cudaEventCreate(&h->ev0) != cudaSuccess || cudaEventCreate(&h->ev1) != cudaSuccess ||
       cudaMallocHost((void**)&h->pin_info, sizeof(int) * batch) != cudaSuccess) {
     std::string m = cudaGetErrorString(cudaGetLastError());
@@ -646,6 +677,8 @@ int gps_create_batch(int device, int batch, gps_handle* out) {
     delete h;
     return fail(nullptr, GPS_ERR_CUDA, std::string("gps_create: ") + cudaGetErrorString(e));
   }
+  h->cur = h->st;
+  if (const char* ev = getenv("GPS_LOOKAHEAD")) h->lookahead = atoi(ev) != 0;
   *out = h;
   return GPS_OK;
 }
@@ -656,6 +689,7 @@ int gps_destroy(gps_handle h) {
   if (!h) return GPS_OK;
   cudaSetDevice(h->device);
   if (h->st) cudaStreamSynchronize(h->st);
+  if (h->st2) cudaStreamSynchronize(h->st2);
   drop_graphs(h);
   free_data(h);
   dfree(h->adj);
@@ -663,6 +697,9 @@ int gps_destroy(gps_handle h) {
   if (h->pin_info) cudaFreeHost(h->pin_info);
   if (h->ev0) cudaEventDestroy(h->ev0);
   if (h->ev1) cudaEventDestroy(h->ev1);
+  if (h->ev_fork) cudaEventDestroy(h->ev_fork);
+  if (h->ev_join) cudaEventDestroy(h->ev_join);
+  if (h->st2) cudaStreamDestroy(h->st2);
   if (h->st) cudaStreamDestroy(h->st);
   delete h;
   return GPS_OK;
