@@ -45,15 +45,32 @@ struct GemmParams {
   int klo_n;   // k >= n0          (B lower-triangular in (k,n): B[k,n] = 0 for k < n)
   int klo_m;   // k >= m0          (A upper-triangular in (m,k): A[m,k] = 0 for k < m)
   int khi_m;   // k <  m0 + BM     (A lower-triangular in (m,k): A[m,k] = 0 for k > m)
+  int khi_n;   // k <  n0 + BN     (B upper-triangular in (k,n): B[k,n] = 0 for k > n)
   int ksplit;  // split-K factor (>= 1); gridDim.z = batch * nodes * ksplit
   // "nodes": several independent sub-problems of one matrix in a single launch (the merges of
   // one level of the triangular-inverse tree).  Node i adds i*nodeStride{A,B} to the operand
   // pointers; its row count is clipped to the matrix edge: M_i = min(M, clip_total - i*clip_step)
-  // (nodes with M_i <= 0 exit) and, with k_eq_m, K_i = M_i.
+  // (nodes with M_i <= 0 exit) and, with k_eq_m, K_i = M_i.  With clip_n the clipped extent is N instead
+  // (N_i = min(N, ...), k_eq_m then means K_i = N_i).
   int nodes;
   long long nodeStrideA, nodeStrideB;
-  int clip_total, clip_step, k_eq_m;
+  int clip_total, clip_step, k_eq_m, clip_n;
 };
+
+// per-node clipping of the problem extents (see GemmParams); false when the node has nothing to do
+__device__ __forceinline__ bool apply_clip(GemmParams& p, int node) {
+  if (p.clip_step) {
+    const int lim = p.clip_total - node * p.clip_step;
+    if (p.clip_n) {
+      p.N = min(p.N, lim);
+      if (p.k_eq_m) p.K = p.N;
+    } else {
+      p.M = min(p.M, lim);
+      if (p.k_eq_m) p.K = p.M;
+    }
+  }
+  return p.M > 0 && p.N > 0;
+}
 
 __device__ __forceinline__ void dmma884(double& d0, double& d1, double a_mma, double b_mma) {
   asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
@@ -79,6 +96,7 @@ struct TileCfg {
   static constexpr int FM = WM / 8, FN = WN / 8;
   static_assert(BM % (8 * WARPS_M) == 0 && BN % (8 * WARPS_N) == 0, "warp tiling");
   static_assert(BK % 4 == 0 && BM % BK == 0 && BK % 16 == 0, "k tiling");
+  static __device__ __forceinline__ void sync() { __syncthreads(); }   // all threads that run the epilogue
 };
 
 // Accumulator view handed to epilogues: acc[mi][ni][0..1] <-> element
@@ -153,11 +171,8 @@ __global__ void __launch_bounds__(Cfg::NT) dmma_gemm_kernel(GemmParams p_in, Epi
   const int zz = blockIdx.z / p.ksplit, split = blockIdx.z % p.ksplit;
   const int batch = zz / p.nodes, node = zz % p.nodes;
 
-  if (p.clip_step) {
-    p.M = min(p.M, p.clip_total - node * p.clip_step);
-    if (p.k_eq_m) p.K = p.M;
-  }
-  if (m0 >= p.M) return;
+  if (!apply_clip(p, node)) return;
+  if (m0 >= p.M || n0 >= p.N) return;
   if (p.lower && (m0 + BM - 1 + p.diag_off < n0)) return;
 
   const double* __restrict__ A = p.A + (size_t)batch * p.strideA + (size_t)node * p.nodeStrideA;
@@ -167,6 +182,7 @@ __global__ void __launch_bounds__(Cfg::NT) dmma_gemm_kernel(GemmParams p_in, Epi
   if (p.klo_n) k_lo = max(k_lo, n0);
   if (p.klo_m) k_lo = max(k_lo, m0);
   if (p.khi_m) k_hi = min(k_hi, m0 + BM);
+  if (p.khi_n) k_hi = min(k_hi, n0 + BN);
   if (p.ksplit > 1) {
     int kc = ((p.K + BK - 1) / BK + p.ksplit - 1) / p.ksplit * BK;
     k_lo = max(k_lo, split * kc);
@@ -250,9 +266,27 @@ struct EpiPlain {
   double alpha, beta;
   int lower_strict_mask;   // 1: do not write elements with row + diag_off < col (keeps upper triangle untouched)
   int diag_off;
+  // optional second, TRANSPOSED copy of alpha*acc (no beta): Ct[n + m*ldct]; same batch stride as C
+  double* Ct;
+  int ldct;
+  long long nodeStrideCt;
   template <class Cfg>
   __device__ __forceinline__ void operator()(const GemmParams& p, AccTile<Cfg>& a, double*) const {
     double* __restrict__ Cb = C + (size_t)a.batch * strideC + (size_t)a.split * strideSplit + (size_t)a.node * nodeStrideC;
+    if (Ct) {
+      double* __restrict__ Tb = Ct + (size_t)a.batch * strideC + (size_t)a.node * nodeStrideCt;
+#pragma unroll
+      for (int i = 0; i < Cfg::FM; i++) {
+        int m = a.m_base + 8 * i;
+#pragma unroll
+        for (int j = 0; j < Cfg::FN; j++) {
+          int n = a.n_base + 8 * j;
+          if (n >= p.N) continue;
+          if (m < p.M) Tb[(size_t)n + (size_t)m * ldct] = alpha * a.v[i][j][0];
+          if (m + 1 < p.M) Tb[(size_t)n + (size_t)(m + 1) * ldct] = alpha * a.v[i][j][1];
+        }
+      }
+    }
 #pragma unroll
     for (int j = 0; j < Cfg::FN; j++) {
       int n = a.n_base + 8 * j;
@@ -390,14 +424,14 @@ struct EpiColDot {
 #pragma unroll
       for (int j = 0; j < Cfg::FN; j++) red[wmi * Cfg::BN + wn0 + 8 * j + (lane >> 2)] = part[j];
     }
-    __syncthreads();
+    Cfg::sync();
     for (int c = threadIdx.x; c < Cfg::BN; c += Cfg::NT) {
       int n = a.n0 + c;
       if (n < p.N) {
         double s = 0.0;
 #pragma unroll
         for (int w = 0; w < Cfg::WARPS_M; w++) s += red[w * Cfg::BN + c];
-        colpart[(((size_t)a.batch * mtiles + blockIdx.x) * p.ksplit + a.split) * ldp + n] = s;
+        colpart[(((size_t)a.batch * mtiles + a.m0 / Cfg::BM) * p.ksplit + a.split) * ldp + n] = s;
       }
     }
   }

@@ -27,6 +27,7 @@
 #include <vector>
 
 #include "dmma_gemm.cuh"
+#include "dmma_ws.cuh"
 #include "kernels.cuh"
 
 using namespace gps;
@@ -61,6 +62,9 @@ struct gps_handle_s {
   std::vector<int> ncens;
 
   // data
+  double* XaugT = nullptr;       // Xaug' ((d+1) x n, ld = ldxt): the "NT" operand of the gradient contraction
+  int ldxt = 0;
+  long long strideXT = 0;
   double *Xaug = nullptr, *Z = nullptr, *mu = nullptr, *y = nullptr, *events = nullptr, *lsc = nullptr;
   int *cens_rank = nullptr, *d_ncens = nullptr;
   // per-evaluation small state
@@ -73,6 +77,16 @@ struct gps_handle_s {
   int rn_ksplit = 1, gram_ksplit = 1, mtiles_grad = 1, grad_ksplit = 1;
   // matrices (work set)
   double *K = nullptr, *Ky = nullptr, *L = nullptr, *Linv = nullptr, *Kinv = nullptr, *gsplit = nullptr;
+  double* U = nullptr;           // U = Linv' (upper triangular), built next to Linv by trtri_levels
+  int num_sms = 148;
+  int ws_enabled = 1;            // GPS_WS=0: never use the warp-specialised 128 x 128 kernel
+  int ws_min_tiles = 296;        // GPS_WS_MIN: minimum number of 128 x 128 tiles in a launch
+  int ws_min_n = 3072;           // GPS_WS_MIN_N: smallest problem (rows of the covariance) that uses it.  Measured on
+                                 // B200: its tiles run at 34.5 TF/s against 30 for the 64 x 64 kernel, but 128-wide tiles
+                                 // over-compute a triangular n = 2000 matrix by 20 % (64-wide: 10 %), and one 288-thread
+                                 // CTA per SM leaves no room for another stream group's panel kernels
+  int* ws_sched = nullptr;       // tile counters of the persistent kernel: WS_SLOTS x 2 ints, one slot per launch in turn
+  unsigned ws_seq = 0;
   size_t gsplit_elems = 0;
   // resident model (after gps_regress_finalize)
   double *mL = nullptr, *mLinv = nullptr, *m_alpha = nullptr, *m_hyp = nullptr, *m_ell = nullptr, *m_meanw = nullptr;
@@ -96,9 +110,16 @@ struct gps_handle_s {
   int fact_level = 0;
   // graphs
   bool graphs_enabled = true;
-  cudaGraphExec_t g_factor = nullptr, g_inverse = nullptr, g_grad = nullptr;
-  int warm_factor = 0, warm_inverse = 0, warm_grad = 0;
-  long long cnt_factor = 0, cnt_inverse = 0, cnt_grad = 0;
+  cudaGraphExec_t g_factor = nullptr, g_inverse = nullptr, g_grad = nullptr, g_full = nullptr;
+  int warm_factor = 0, warm_inverse = 0, warm_grad = 0, warm_full = 0;
+  long long cnt_factor = 0, cnt_inverse = 0, cnt_grad = 0, cnt_full = 0;
+  // stream groups: the fits of a batch are independent, so every sequence is enqueued once per GROUP of fits
+  // on its own stream (parallel branches of the captured graph): one group's latency-bound panel kernels and
+  // launch tails run beside another group's GEMMs.  GPS_GROUPS overrides (1 = off).
+  static constexpr int MAX_GROUPS = 8;
+  int groups = 1;
+  cudaStream_t gst[MAX_GROUPS] = {nullptr};
+  cudaEvent_t ev_gfork = nullptr, ev_gjoin[MAX_GROUPS] = {nullptr};
   // bookkeeping
   long long launches = 0;
   long long seq_launches = 0;   // launches issued by the sequence being recorded
@@ -171,7 +192,7 @@ void free_data(H* h) {
   dfree(h->rnpart); dfree(h->rnorm); dfree(h->meanv); dfree(h->zvec); dfree(h->alpha);
   dfree(h->wdiag); dfree(h->rs); dfree(h->rs_part); dfree(h->colpart); dfree(h->qtu); dfree(h->d_nlml); dfree(h->d_logdet);
   dfree(h->d_grad); dfree(h->info);
-  dfree(h->K); dfree(h->Ky); dfree(h->L); dfree(h->Linv); dfree(h->Kinv); dfree(h->gsplit);
+  dfree(h->K); dfree(h->Ky); dfree(h->L); dfree(h->Linv); dfree(h->Kinv); dfree(h->gsplit); dfree(h->U); dfree(h->XaugT);
   dfree(h->mL); dfree(h->mLinv); dfree(h->m_alpha); dfree(h->m_hyp); dfree(h->m_ell); dfree(h->m_meanw);
   dfree(h->Xs); dfree(h->Zs); dfree(h->snorm); dfree(h->snpart); dfree(h->Ks); dfree(h->V); dfree(h->mstar);
   dfree(h->pout);
@@ -187,8 +208,9 @@ void drop_graphs(H* h) {
   if (h->g_factor) cudaGraphExecDestroy(h->g_factor);
   if (h->g_inverse) cudaGraphExecDestroy(h->g_inverse);
   if (h->g_grad) cudaGraphExecDestroy(h->g_grad);
-  h->g_factor = h->g_inverse = h->g_grad = nullptr;
-  h->warm_factor = h->warm_inverse = h->warm_grad = 0;
+  if (h->g_full) cudaGraphExecDestroy(h->g_full);
+  h->g_factor = h->g_inverse = h->g_grad = h->g_full = nullptr;
+  h->warm_factor = h->warm_inverse = h->warm_grad = h->warm_full = 0;
 }
 
 int expected_len(const H* h) {
@@ -198,16 +220,68 @@ int expected_len(const H* h) {
 // ---------------------------------------------------------------------------------------
 // GEMM dispatch: pick the tile configuration from the amount of tile-level parallelism.
 // ---------------------------------------------------------------------------------------
+// The warp-specialised persistent 128 x 128 kernel (dmma_ws.cuh; "NT" operands only) wins when a launch
+// has enough big tiles to fill the 148 SMs for several rounds; small or narrow problems stay on the
+// 64 x 64 cp.async kernel (4 CTAs/SM).
+constexpr int WS_SLOTS = 256;
+bool use_ws128(const H* h, const GemmParams& p) {
+  if (!h->ws_enabled || !h->ws_sched || h->ne < h->ws_min_n || p.M < 96 || p.N < 96 || p.K < 128) return false;
+  ws::TileEnum te;
+  te.init(p.M, p.N, 128, 128, p.lower, 0);
+  const long long total = (long long)te.per_z * h->batch * p.nodes * p.ksplit;
+  if (total < h->ws_min_tiles) return false;
+  // tiles of equal length come in whole rounds of num_sms: ask for a well-filled last round; with triangular
+  // operands the lengths differ and the dynamic scheduler packs them, so only the count matters
+  if (p.klo_m || p.klo_n || p.khi_m || p.khi_n) return true;
+  const long long rounds = (total + h->num_sms - 1) / h->num_sms;
+  return (double)total >= 0.85 * (double)(rounds * h->num_sms);
+}
+
+// Tile configuration of an "NT" GEMM: 128 / 80 / 64 = warp-specialised persistent kernel with that square
+// tile (dmma_ws.cuh), 0 = the 64 x 64 cp.async kernel (short k-loops: K < 128, where a persistent tile's
+// un-overlapped epilogue dominates; and every developer override).
+int pick_nt_tile(const H* h, const GemmParams& p) {
+  if (h->force_tile >= 0 || !h->ws_enabled || !h->ws_sched || p.K < 128) return 0;
+  if (use_ws128(h, p)) return 128;
+  {   // a launch that cannot even fill the persistent grid once (a lone mid-size fit) is latency-bound: the plain
+      // kernel starts faster (no barrier set-up, no scheduler round trip) — measured 1.87 vs 2.02 ms on a lone C2 fit
+    ws::TileEnum te;
+    te.init(p.M, p.N, 64, 64, p.lower, 0);
+    if ((long long)te.per_z * h->batch * p.nodes * p.ksplit < (long long)h->num_sms * WsCfg64::CTAS_PER_SM) return 0;
+  }
+  // 80-wide tiles when they pad the rows and columns of a small problem visibly less than 64-wide ones
+  if (p.M <= 1024 && p.N >= 80 && p.M >= 80) {
+    const double w64 = (double)round_up(p.M, 64) * round_up(p.N, 64), w80 = (double)round_up(p.M, 80) * round_up(p.N, 80);
+    if (w80 < 0.93 * w64) return 80;
+  }
+  return 64;
+}
+
 template <bool A_KC, bool B_KC, class Epi>
 void gemm(H* h, const GemmParams& p, const Epi& epi) {
+  cudaError_t e;
+  if constexpr (!A_KC && !B_KC) {
+    const int tile = pick_nt_tile(h, p);
+    if (tile) {
+      int* sched = h->ws_sched + 2 * (h->ws_seq++ % WS_SLOTS);   // launches of different stream groups may overlap: own slot each
+      if (tile == 128)
+        e = launch_gemm_ws<WsCfg128, false, false, Epi>(p, epi, h->batch, h->num_sms, sched, h->cur);
+      else if (tile == 80)
+        e = launch_gemm_ws<WsCfg80, false, false, Epi>(p, epi, h->batch, h->num_sms, sched, h->cur);
+      else
+        e = launch_gemm_ws<WsCfg64, false, false, Epi>(p, epi, h->batch, h->num_sms, sched, h->cur);
+      h->seq_launches++;
+      CKV(h, e);
+      return;
+    }
+  }
   long long tl = (long long)ceil_div(p.M, 128) * ceil_div(p.N, 128);
   if (p.lower) tl = tl / 2 + 1;
   tl *= (long long)h->batch * p.ksplit * p.nodes;
   // triangular operands make the per-tile K range uneven: a single wave of big tiles is then
   // gated by its longest tile, so ask for several waves before using the 128 x 128 config
-  const long long need = (p.klo_m || p.klo_n || p.khi_m) ? 600 : 100;
-  cudaError_t e;
-  // default: 64 x 64 x 16 tile, 4 warps, 3-stage cp.async pipeline (4 CTAs/SM) — measured best at every size
+  const long long need = (p.klo_m || p.klo_n || p.khi_m || p.khi_n) ? 600 : 100;
+  // 64 x 64 x 16 tile, 4 warps, 3-stage cp.async pipeline (4 CTAs/SM); CfgLarge only by developer override
   int choice = (tl >= need && p.N >= 96 && p.M >= h->large_min_dim && p.N >= h->large_min_dim) ? 2 : 3;
   if (h->force_tile >= 0) choice = h->force_tile;
   if (choice == 2)
@@ -231,6 +305,7 @@ EpiPlain plain(double* C, int ldc, long long sC, double alpha, double beta) {
   EpiPlain e;
   e.C = C; e.ldc = ldc; e.strideC = sC; e.strideSplit = 0; e.nodeStrideC = 0; e.alpha = alpha; e.beta = beta;
   e.lower_strict_mask = 0; e.diag_off = 0;
+  e.Ct = nullptr; e.ldct = 0; e.nodeStrideCt = 0;
   return e;
 }
 
@@ -302,9 +377,9 @@ void launch_panel(H* h, int e0, int nb, int M, long long* dbg) {
   const int tiles = ceil_div(Mr, best_rt);
   dim3 grid(ceil_div(tiles, best_T) + 1, B);
   if (best_rt == 32)
-    panel_kernel<32><<<grid, 256, PANEL_SMEM, h->st>>>(h->Ky, h->L, h->Linv, h->ld, h->strideM, e0, nb, M, best_T, h->info, dbg);
+    panel_kernel<32><<<grid, 256, PANEL_SMEM, h->st>>>(h->Ky, h->L, h->Linv, h->U, h->ld, h->strideM, e0, nb, M, best_T, h->info, dbg);
   else
-    panel_kernel<128><<<grid, 256, PANEL_SMEM, h->st>>>(h->Ky, h->L, h->Linv, h->ld, h->strideM, e0, nb, M, best_T, h->info, dbg);
+    panel_kernel<128><<<grid, 256, PANEL_SMEM, h->st>>>(h->Ky, h->L, h->Linv, h->U, h->ld, h->strideM, e0, nb, M, best_T, h->info, dbg);
   LAUNCHED(h);
   if (h->pending_join) {   // look-ahead: the rest of the previous trailing update ran beside this panel
     CKV(h, cudaEventRecord(h->ev_join, h->st2));
@@ -360,35 +435,41 @@ void potrf_range(H* h, int j0, int j1) {
   potrf_range(h, mid, j1);
 }
 
-// Inverse of the lower-triangular factor.  The NB x NB diagonal blocks were inverted by panel_kernel;
-// merge pairs of blocks bottom-up, one LEVEL per pair of launches: at level s (block size
-// bs = NB * 2^s) node i covers rows/cols [i*2bs, (i+1)*2bs) and computes
-//   Linv21 = -Linv22 * (L21 * Linv11)
-// for its own 2x2 partition; all nodes of a level are independent and share two launches.
-// Kinv is the temporary for T = L21 * Linv11.
+// Inverse of the lower-triangular factor, kept in both orientations: Linv = L^-1 (lower) and U = Linv'
+// (upper).  The NB x NB diagonal blocks of both were published by panel_kernel; merge pairs of blocks
+// bottom-up, one LEVEL per pair of launches: at level s (block size bs = NB * 2^s) node i covers rows/cols
+// [i*2bs, (i+1)*2bs) and computes, for its own 2x2 partition,
+//   T   = U11 * L21'          (bs x m22;  U11 upper triangular: k >= m)
+//   U12 = -T * U22            (bs x m22;  U22[k,n] = Linv22[n,k], upper triangular: k <= n)
+// and stores U12 together with its transpose Linv21 (dual-store epilogue).  Keeping both orientations
+// makes every product an "NT" GEMM — each operand row is a long contiguous run in memory, which is what the
+// bulk-copy producer of the warp-specialised kernel streams best — and Kinv = U U' likewise.
+// All nodes of a level are independent and share the two launches.  Kinv is the temporary for T.
 void trtri_levels(H* h) {
   const int ld = h->ld, ne = h->ne;
   const long long sM = h->strideM;
   for (int bs = NB; bs < ne; bs *= 2) {
     const int nodes = ceil_div(ne, 2 * bs);
     const long long nstride = (long long)2 * bs * (1 + (long long)ld);
-    {  // T = L21 * Linv11   (Linv11 lower: k >= n)
-      GemmParams p = gp(h->L + bs, ld, sM, h->Linv, ld, sM, bs, bs, bs);
-      p.klo_n = 1;
+    const size_t off12 = (size_t)bs * ld, off21 = (size_t)bs, off22 = (size_t)bs + (size_t)bs * ld;
+    {  // T = U11 * L21'
+      GemmParams p = gp(h->U, ld, sM, h->L + off21, ld, sM, bs, bs, bs);
+      p.klo_m = 1;
       p.nodes = nodes; p.nodeStrideA = nstride; p.nodeStrideB = nstride;
-      p.clip_total = ne - bs; p.clip_step = 2 * bs; p.k_eq_m = 0;
-      EpiPlain e = plain(h->Kinv + bs, ld, sM, 1.0, 0.0);
+      p.clip_total = ne - bs; p.clip_step = 2 * bs; p.k_eq_m = 0; p.clip_n = 1;
+      EpiPlain e = plain(h->Kinv + off12, ld, sM, 1.0, 0.0);
       e.nodeStrideC = nstride;
-      gemm<false, true>(h, p, e);
+      gemm<false, false>(h, p, e);
     }
-    {  // Linv21 = -Linv22 * T   (Linv22 lower: k <= m; K = rows of the node)
-      GemmParams p = gp(h->Linv + bs + (size_t)bs * ld, ld, sM, h->Kinv + bs, ld, sM, bs, bs, bs);
-      p.khi_m = 1;
+    {  // U12 = -T * U22 (B = Linv22, read transposed), Linv21 = U12'
+      GemmParams p = gp(h->Kinv + off12, ld, sM, h->Linv + off22, ld, sM, bs, bs, bs);
+      p.khi_n = 1;
       p.nodes = nodes; p.nodeStrideA = nstride; p.nodeStrideB = nstride;
-      p.clip_total = ne - bs; p.clip_step = 2 * bs; p.k_eq_m = 1;
-      EpiPlain e = plain(h->Linv + bs, ld, sM, -1.0, 0.0);
+      p.clip_total = ne - bs; p.clip_step = 2 * bs; p.k_eq_m = 1; p.clip_n = 1;
+      EpiPlain e = plain(h->U + off12, ld, sM, -1.0, 0.0);
       e.nodeStrideC = nstride;
-      gemm<false, true>(h, p, e);
+      e.Ct = h->Linv + off21; e.ldct = ld; e.nodeStrideCt = nstride;
+      gemm<false, false>(h, p, e);
     }
   }
 }
@@ -434,15 +515,17 @@ void enqueue_inverse(H* h) {
   LAUNCHED(h);
 }
 
+void enqueue_kinv(H* h) {   // Kinv = Linv' * Linv = U * U'  (lower tiles; k >= m because U is upper triangular)
+  GemmParams p = gp(h->U, h->ld, h->strideM, h->U, h->ld, h->strideM, h->ne, h->ne, h->ne);
+  p.lower = 1;
+  p.klo_m = 1;
+  gemm<false, false>(h, p, plain(h->Kinv, h->ld, h->strideM, 1.0, 0.0));
+}
+
 void enqueue_grad(H* h) {
   const int n = h->n, ld = h->ld;
   const long long sM = h->strideM;
-  {  // Kinv = Linv' * Linv  (lower tiles; k >= m because Linv is lower triangular)
-    GemmParams p = gp(h->Linv, ld, sM, h->Linv, ld, sM, h->ne, h->ne, h->ne);
-    p.lower = 1;
-    p.klo_m = 1;
-    gemm<true, true>(h, p, plain(h->Kinv, ld, sM, 1.0, 0.0));
-  }
+  enqueue_kinv(h);
   // M = (a a' - Kinv) o K  into the (now free) Ky buffer
   const double* aw = h->alpha + (h->nrhs == 2 ? h->ld : 0);
   wk_kernel<<<dim3(ceil_div(n, 32), ceil_div(n, 32), h->batch), dim3(32, 8), 0, h->st>>>(h->Kinv, h->K, n, ld, sM, aw,
@@ -450,14 +533,15 @@ void enqueue_grad(H* h) {
   LAUNCHED(h);
   {  // (M Xaug) contracted with Xaug column by column; last column gives rowsum(M).  With few column tiles
      // (small d) the K = n loop is split deterministically so that the launch fills the GPU.
-    GemmParams p = gp(h->Ky, ld, sM, h->Xaug, h->ldx, h->strideX, n, h->d + 1, n);
+    GemmParams p = gp(h->Ky, ld, sM, h->XaugT, h->ldxt, h->strideXT, n, h->d + 1, n);
     p.ksplit = h->grad_ksplit;
     EpiColDot e;
     e.X = h->Xaug; e.ldx = h->ldx; e.strideX = h->strideX; e.colpart = h->colpart; e.ldp = h->ldmu;
     e.rs = h->rs_part; e.ldn = h->ld;
-    e.mtiles = ceil_div(n, h->force_tile == 2 ? 128 : 64);
+    const int tile = pick_nt_tile(h, p);
+    e.mtiles = ceil_div(n, tile ? tile : (h->force_tile == 2 ? 128 : 64));
     h->mtiles_grad = e.mtiles * h->grad_ksplit;
-    gemm<false, true>(h, p, e);
+    gemm<false, false>(h, p, e);
   }
   rs_reduce_kernel<<<dim3(ceil_div(n, 256), h->batch), 256, 0, h->st>>>(h->rs_part, n, h->ld, h->grad_ksplit, h->rs);
   LAUNCHED(h);
@@ -473,6 +557,75 @@ void enqueue_grad(H* h) {
 
 typedef void (*SeqFn)(H*);
 
+void enqueue_full(H* h) {   // one whole NLML + gradient evaluation
+  enqueue_factor(h);
+  enqueue_inverse(h);
+  enqueue_grad(h);
+}
+
+// A view of fits [g0, g0 + cnt) of the batch: same handle, every per-fit array advanced by g0 fits.
+// (Strides as the kernels index them; colpart is scratch private to one sequence, advanced by its
+// allocation stride.)
+template <class T>
+inline void adv(T*& p, size_t elems) {
+  if (p) p += elems;
+}
+void make_view(const H* h, int g0, int cnt, cudaStream_t st, H* v) {
+  *v = *h;
+  v->batch = cnt;
+  v->st = v->cur = st;
+  v->lookahead = false;
+  v->seq_launches = 0;
+  const size_t g = (size_t)g0;
+  adv(v->Xaug, g * h->strideX); adv(v->Z, g * h->strideX); adv(v->XaugT, g * h->strideXT);
+  adv(v->mu, g * h->ldmu); adv(v->ell, g * h->ldmu); adv(v->meanw, g * h->ldmu);
+  adv(v->y, g * h->ld); adv(v->events, g * h->ld); adv(v->noise_diag, g * h->ld); adv(v->rnorm, g * h->ld);
+  adv(v->meanv, g * h->ld); adv(v->wdiag, g * h->ld); adv(v->rs, g * h->ld); adv(v->cens_rank, g * h->ld);
+  adv(v->lsc, g * h->ldc);
+  adv(v->rnpart, g * h->ld * h->rn_ksplit); adv(v->rs_part, g * h->ld * h->grad_ksplit);
+  adv(v->zvec, g * 2 * h->ld); adv(v->alpha, g * 2 * h->ld);
+  adv(v->colpart, g * h->ldmu * ceil_div(h->n, 64) * h->grad_ksplit);
+  adv(v->qtu, g * 3 * h->ldmu);
+  adv(v->par, g * h->par_cap); adv(v->d_grad, g * h->par_cap);
+  adv(v->hyp, g * 4);
+  adv(v->d_nlml, g); adv(v->d_logdet, g); adv(v->info, g); adv(v->d_ncens, g);
+  adv(v->K, g * h->strideM); adv(v->Ky, g * h->strideM); adv(v->L, g * h->strideM); adv(v->Linv, g * h->strideM);
+  adv(v->Kinv, g * h->strideM); adv(v->U, g * h->strideM);
+  adv(v->gsplit, g * h->gram_ksplit * h->strideM);
+}
+
+// Enqueue a sequence for the whole batch: once, or once per stream group (fork from / join into h->st).
+void enqueue_grouped(H* h, SeqFn fn) {
+  const int G = std::min(h->groups, h->batch);
+  if (G <= 1 || h->lookahead) {
+    fn(h);
+    return;
+  }
+  CKV(h, cudaEventRecord(h->ev_gfork, h->st));
+  const long long base_launches = h->seq_launches;
+  long long launched = 0;
+  for (int g = 0; g < G; g++) {
+    const int g0 = (int)((long long)h->batch * g / G), g1 = (int)((long long)h->batch * (g + 1) / G);
+    cudaStream_t sg = (g == 0) ? h->st : h->gst[g];
+    if (g > 0) CKV(h, cudaStreamWaitEvent(sg, h->ev_gfork, 0));
+    H v;
+    make_view(h, g0, g1 - g0, sg, &v);
+    v.ws_seq = h->ws_seq;
+    fn(&v);
+    h->ws_seq = v.ws_seq;
+    launched += v.seq_launches;
+    if (v.cu_err != cudaSuccess && h->cu_err == cudaSuccess) {
+      h->cu_err = v.cu_err;
+      h->err = v.err;
+    }
+    if (g > 0) {
+      CKV(h, cudaEventRecord(h->ev_gjoin[g], sg));
+      CKV(h, cudaStreamWaitEvent(h->st, h->ev_gjoin[g], 0));
+    }
+  }
+  h->seq_launches = base_launches + launched;
+}
+
 // Run a sequence: first call direct (also sets kernel attributes), second call captures a
 // CUDA graph, later calls replay it.
 int run_seq(H* h, SeqFn fn, cudaGraphExec_t* gexec, int* warm, long long* cnt) {
@@ -486,7 +639,7 @@ int run_seq(H* h, SeqFn fn, cudaGraphExec_t* gexec, int* warm, long long* cnt) {
     cudaGraph_t graph = nullptr;
     h->seq_launches = 0;
     CK(h, cudaStreamBeginCapture(h->st, cudaStreamCaptureModeThreadLocal));
-    fn(h);
+    enqueue_grouped(h, fn);
     cudaError_t e = cudaStreamEndCapture(h->st, &graph);
     if (e != cudaSuccess || h->cu_err != cudaSuccess) {
       if (graph) cudaGraphDestroy(graph);
@@ -505,7 +658,7 @@ int run_seq(H* h, SeqFn fn, cudaGraphExec_t* gexec, int* warm, long long* cnt) {
     return GPS_OK;
   }
   h->seq_launches = 0;
-  fn(h);
+  enqueue_grouped(h, fn);
   h->launches += h->seq_launches;
   *cnt = h->seq_launches;
   (*warm)++;
@@ -516,6 +669,7 @@ int run_seq(H* h, SeqFn fn, cudaGraphExec_t* gexec, int* warm, long long* cnt) {
 int run_factor(H* h) { return run_seq(h, enqueue_factor, &h->g_factor, &h->warm_factor, &h->cnt_factor); }
 int run_inverse(H* h) { return run_seq(h, enqueue_inverse, &h->g_inverse, &h->warm_inverse, &h->cnt_inverse); }
 int run_grad(H* h) { return run_seq(h, enqueue_grad, &h->g_grad, &h->warm_grad, &h->cnt_grad); }
+int run_full(H* h) { return run_seq(h, enqueue_full, &h->g_full, &h->warm_full, &h->cnt_full); }
 
 int ensure_pin(H* h, size_t elems) {
   if (h->pin_elems >= elems) return GPS_OK;
@@ -562,11 +716,14 @@ int upload_par(H* h, const double* par, int len) {
 }
 
 // Level-1 evaluation with cache: returns nlml values in h->pin[0..batch)
-int do_factor(H* h, const double* par, int len, bool force) {
+bool fact_hit(const H* h, const double* par, int len) {
   size_t tot = (size_t)len * h->batch;
-  bool hit = !force && h->fact_level >= 1 && h->fact_tv == h->targets_version && h->fact_ncv == h->nc_version &&
-             h->fact_par.size() == tot && memcmp(h->fact_par.data(), par, tot * sizeof(double)) == 0;
-  if (hit) return GPS_OK;
+  return h->fact_level >= 1 && h->fact_tv == h->targets_version && h->fact_ncv == h->nc_version &&
+         h->fact_par.size() == tot && memcmp(h->fact_par.data(), par, tot * sizeof(double)) == 0;
+}
+
+int do_factor(H* h, const double* par, int len, bool force) {
+  if (!force && fact_hit(h, par, len)) return GPS_OK;
   h->fact_level = 0;
   int rc = upload_par(h, par, len);
   if (rc) return rc;
@@ -658,6 +815,10 @@ int gps_create_batch(int device, int batch, gps_handle* out) {
   H* h = new H();
   if (const char* ev = getenv("GPS_TILE")) h->force_tile = atoi(ev);
   if (const char* ev = getenv("GPS_LARGE_MIN_DIM")) h->large_min_dim = atoi(ev);
+  if (const char* ev = getenv("GPS_WS")) h->ws_enabled = atoi(ev) != 0;
+  if (const char* ev = getenv("GPS_WS_MIN")) h->ws_min_tiles = atoi(ev);
+  if (const char* ev = getenv("GPS_WS_MIN_N")) h->ws_min_n = atoi(ev);
+  h->num_sms = prop.multiProcessorCount;
   h->device = device;
   h->batch = batch;
   if (cudaSetDevice(device) != cudaSuccess || cudaStreamCreateWithFlags(&h->st, cudaStreamNonBlocking) != cudaSuccess ||
@@ -678,7 +839,26 @@ int gps_create_batch(int device, int batch, gps_handle* out) {
     return fail(nullptr, GPS_ERR_CUDA, std::string("gps_create: ") + cudaGetErrorString(e));
   }
   h->cur = h->st;
+  if (cudaMalloc((void**)&h->ws_sched, sizeof(int) * 2 * WS_SLOTS) != cudaSuccess ||
+      cudaMemsetAsync(h->ws_sched, 0, sizeof(int) * 2 * WS_SLOTS, h->st) != cudaSuccess ||
+      cudaStreamSynchronize(h->st) != cudaSuccess) {
+    std::string m = cudaGetErrorString(cudaGetLastError());
+    delete h;
+    return fail(nullptr, GPS_ERR_CUDA, "gps_create: " + m);
+  }
   if (const char* ev = getenv("GPS_LOOKAHEAD")) h->lookahead = atoi(ev) != 0;
+  h->groups = batch >= 16 ? 2 : 1;
+  if (const char* ev = getenv("GPS_GROUPS")) h->groups = atoi(ev);
+  h->groups = std::max(1, std::min(std::min(h->groups, (int)H::MAX_GROUPS), batch));
+  bool okg = cudaEventCreateWithFlags(&h->ev_gfork, cudaEventDisableTiming) == cudaSuccess;
+  for (int g = 1; g < h->groups && okg; g++)
+    okg = cudaStreamCreateWithFlags(&h->gst[g], cudaStreamNonBlocking) == cudaSuccess &&
+          cudaEventCreateWithFlags(&h->ev_gjoin[g], cudaEventDisableTiming) == cudaSuccess;
+  if (!okg) {
+    std::string m = cudaGetErrorString(cudaGetLastError());
+    delete h;
+    return fail(nullptr, GPS_ERR_CUDA, "gps_create: " + m);
+  }
   *out = h;
   return GPS_OK;
 }
@@ -695,11 +875,17 @@ int gps_destroy(gps_handle h) {
   dfree(h->adj);
   if (h->pin) cudaFreeHost(h->pin);
   if (h->pin_info) cudaFreeHost(h->pin_info);
+  if (h->ws_sched) cudaFree(h->ws_sched);
   if (h->ev0) cudaEventDestroy(h->ev0);
   if (h->ev1) cudaEventDestroy(h->ev1);
   if (h->ev_fork) cudaEventDestroy(h->ev_fork);
   if (h->ev_join) cudaEventDestroy(h->ev_join);
   if (h->st2) cudaStreamDestroy(h->st2);
+  for (int g = 1; g < H::MAX_GROUPS; g++) {
+    if (h->gst[g]) cudaStreamDestroy(h->gst[g]);
+    if (h->ev_gjoin[g]) cudaEventDestroy(h->ev_gjoin[g]);
+  }
+  if (h->ev_gfork) cudaEventDestroy(h->ev_gfork);
   if (h->st) cudaStreamDestroy(h->st);
   delete h;
   return GPS_OK;
@@ -751,6 +937,8 @@ int gps_set_data(gps_handle h, const double* X, int n, int d, const double* y, c
   h->ldc = round_up(n, 16);
   h->strideM = (long long)h->ld * round_up(h->ne, 2);
   h->strideX = (long long)h->ldx * (d + 1);
+  h->ldxt = round_up(d + 1, 16);
+  h->strideXT = (long long)h->ldxt * round_up(n, 2);
   {
     int want = ceil_div(160000, n * B);     // ~160 K threads in flight: the pre-scale is pure streaming
     int cap = d / 8 > 1 ? d / 8 : 1;        // at least 8 columns per thread
@@ -761,6 +949,7 @@ int gps_set_data(gps_handle h, const double* X, int n, int d, const double* y, c
   size_t vecB = (size_t)h->ld * B;
   CK(h, dalloc(&h->Xaug, (size_t)h->strideX * B));
   CK(h, dalloc(&h->Z, (size_t)h->strideX * B));
+  CK(h, dalloc(&h->XaugT, (size_t)h->strideXT * B));
   CK(h, dalloc(&h->mu, (size_t)h->ldmu * B));
   CK(h, dalloc(&h->y, vecB));
   CK(h, dalloc(&h->events, vecB));
@@ -799,6 +988,7 @@ int gps_set_data(gps_handle h, const double* X, int n, int d, const double* y, c
   CK(h, dalloc(&h->L, mat));
   CK(h, dalloc(&h->Linv, mat));
   CK(h, dalloc(&h->Kinv, mat));
+  CK(h, dalloc(&h->U, mat));
   CK(h, dalloc(&h->mL, mat));
   CK(h, dalloc(&h->mLinv, mat));
   if (h->gram_ksplit > 1) {
@@ -830,8 +1020,10 @@ int gps_set_data(gps_handle h, const double* X, int n, int d, const double* y, c
   }
   colmean_kernel<<<dim3(ceil_div(d, 8), B), 256, 0, h->st>>>(h->Xaug, n, d, h->ldx, h->strideX, h->mu, h->ldmu);
   center_kernel<<<dim3(ceil_div(n, 256), d + 1, B), 256, 0, h->st>>>(h->Xaug, n, d, h->ldx, h->strideX, h->mu, h->ldmu);
+  transpose_kernel<<<dim3(ceil_div(n, 32), ceil_div(d + 1, 32), B), dim3(32, 8), 0, h->st>>>(
+      h->Xaug, n, d + 1, h->ldx, h->strideX, h->XaugT, h->ldxt, h->strideXT);
   cens_rank_kernel<<<ceil_div(B, 64), 64, 0, h->st>>>(h->events, n, h->ld, h->cens_rank, h->d_ncens, B);
-  h->launches += 3;
+  h->launches += 4;
   CK(h, cudaGetLastError());
   h->ncens.assign(B, 0);
   CK(h, cudaMemcpyAsync(h->ncens.data(), h->d_ncens, sizeof(int) * B, cudaMemcpyDeviceToHost, h->st));
@@ -917,16 +1109,22 @@ int gps_nlml_grad(gps_handle h, const double* par, int len, double* nlml_out, do
     return fail(h, GPS_ERR_UNSUPPORTED,
                 "the analytic ARD gradient is defined for ard_mode = INTENDED only (the reference's as-written ARD "
                 "gradient, OptimisationGradientLog.R:58-69, is not the derivative of its likelihood)");
-  rc = do_factor(h, par, len, false);
-  if (rc) return rc;
-  bool had_factor = (h->fact_level >= 1);
-  if (had_factor) CK(h, cudaEventRecord(h->ev0, h->st));
-  if (h->fact_level < 2) {
-    rc = run_inverse(h);
+  if (fact_hit(h, par, len)) {   // optim() calls fn(par) then gr(par): reuse fn's factorisation
+    CK(h, cudaEventRecord(h->ev0, h->st));
+    if (h->fact_level < 2) {
+      rc = run_inverse(h);
+      if (rc) return rc;
+    }
+    rc = run_grad(h);
+    if (rc) return rc;
+  } else {                       // one graph for the whole evaluation (stream groups stay apart until its end)
+    h->fact_level = 0;
+    rc = upload_par(h, par, len);
+    if (rc) return rc;
+    CK(h, cudaEventRecord(h->ev0, h->st));
+    rc = run_full(h);
     if (rc) return rc;
   }
-  rc = run_grad(h);
-  if (rc) return rc;
   CK(h, cudaEventRecord(h->ev1, h->st));
   size_t tot = (size_t)len * h->batch;
   rc = ensure_pin(h, tot + h->batch + 4096);
@@ -1436,14 +1634,8 @@ int gps_time_eval(gps_handle h, int kind, int reps, double* ms_out) {
   CK(h, cudaStreamSynchronize(h->st));
   CK(h, cudaEventRecord(h->ev0, h->st));
   for (int r = 0; r < reps; r++) {
-    rc = run_factor(h);
+    rc = (kind == 1) ? run_full(h) : run_factor(h);
     if (rc) return rc;
-    if (kind == 1) {
-      rc = run_inverse(h);
-      if (rc) return rc;
-      rc = run_grad(h);
-      if (rc) return rc;
-    }
   }
   CK(h, cudaEventRecord(h->ev1, h->st));
   CK(h, cudaStreamSynchronize(h->st));
@@ -1483,12 +1675,7 @@ int gps_time_stages(gps_handle h, double* ms_out) {
   CK(h, cudaEventRecord(ev[2], h->st));
   enqueue_inverse(h);
   CK(h, cudaEventRecord(ev[3], h->st));
-  {
-    GemmParams p = gp(h->Linv, h->ld, h->strideM, h->Linv, h->ld, h->strideM, h->ne, h->ne, h->ne);
-    p.lower = 1;
-    p.klo_m = 1;
-    gemm<true, true>(h, p, plain(h->Kinv, h->ld, h->strideM, 1.0, 0.0));
-  }
+  enqueue_kinv(h);
   CK(h, cudaEventRecord(ev[4], h->st));
   enqueue_grad(h);   // includes Kinv again: stage 4 = wk + grad GEMM + finish + (Kinv repeated)
   CK(h, cudaEventRecord(ev[5], h->st));

@@ -373,7 +373,8 @@ __device__ __forceinline__ void trinv_merge(const double* S, double* sX, double*
 // T = consecutive tiles per CTA.  The LAST CTA along x only publishes L11 / X11.
 template <int RT>
 __global__ void __launch_bounds__(256) panel_kernel(const double* __restrict__ A, double* __restrict__ L,
-                                                    double* __restrict__ Linv, int ld, long long stride, int e0,
+                                                    double* __restrict__ Linv, double* __restrict__ Uinv, int ld,
+                                                    long long stride, int e0,
                                                     int nb, int M, int T, int* __restrict__ info,
                                                     long long* __restrict__ dbg) {
   extern __shared__ __align__(16) double panel_smem[];
@@ -472,15 +473,17 @@ __global__ void __launch_bounds__(256) panel_kernel(const double* __restrict__ A
   __syncthreads();
   PANEL_STAMP();
 
-  if (publisher) {                              // publish L11 and X11 (lower, zeros above)
+  if (publisher) {                              // publish L11 and X11 (lower, zeros above) and X11' (upper)
     if (tid == 0 && bad != 0 && bad <= nb) atomicCAS(&info[b], 0, e0 + bad);
     double* Lb = L + (size_t)b * stride + (size_t)e0 + (size_t)e0 * ld;
     double* Ib = Linv + (size_t)b * stride + (size_t)e0 + (size_t)e0 * ld;
+    double* Ub = Uinv + (size_t)b * stride + (size_t)e0 + (size_t)e0 * ld;
     for (int idx = tid; idx < NB * NB; idx += 256) {
       int r = idx & 63, c = idx >> 6;
       if (r < nb && c < nb) {
         Lb[(size_t)r + (size_t)c * ld] = (r >= c) ? S[c * PS + r] : 0.0;
         Ib[(size_t)r + (size_t)c * ld] = (r >= c) ? sX[r * PX + c] : 0.0;
+        Ub[(size_t)r + (size_t)c * ld] = (c >= r) ? sX[c * PX + r] : 0.0;   // U = Linv' (trtri_levels works on both)
       }
     }
     PANEL_STAMP();
@@ -537,6 +540,29 @@ __global__ void __launch_bounds__(256) panel_kernel(const double* __restrict__ A
   }
   PANEL_STAMP();
 #undef PANEL_STAMP
+}
+
+// ---------------------------------------------------------------------------------------
+// Out-of-place transpose of a batch of column-major matrices: T[c + r*ldt] = A[r + c*lda].
+// grid (ceil(rows/32), ceil(cols/32), batch), block (32, 8).  Used once per gps_set_data to keep
+// Xaug' next to Xaug, so that the gradient contraction M * Xaug is an "NT" GEMM whose operands
+// both stream as long contiguous rows.
+// ---------------------------------------------------------------------------------------
+__global__ void transpose_kernel(const double* __restrict__ A, int rows, int cols, int lda, long long strideA,
+                                 double* __restrict__ T, int ldt, long long strideT) {
+  __shared__ double tile[32][33];
+  const double* Ab = A + (size_t)blockIdx.z * strideA;
+  double* Tb = T + (size_t)blockIdx.z * strideT;
+  const int r0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+  for (int k = threadIdx.y; k < 32; k += 8) {
+    int r = r0 + threadIdx.x, c = c0 + k;
+    tile[k][threadIdx.x] = (r < rows && c < cols) ? Ab[(size_t)r + (size_t)c * lda] : 0.0;
+  }
+  __syncthreads();
+  for (int k = threadIdx.y; k < 32; k += 8) {
+    int c = c0 + threadIdx.x, r = r0 + k;
+    if (r < rows && c < cols) Tb[(size_t)c + (size_t)r * ldt] = tile[threadIdx.x][k];
+  }
 }
 
 // ---------------------------------------------------------------------------------------
