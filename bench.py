@@ -384,7 +384,7 @@ def main():
     ap.add_argument("--steps", type=int, default=30)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--batch", type=int, default=32, help="independent fits evaluated per step on each GPU")
+    ap.add_argument("--batch", type=int, default=64, help="independent fits evaluated per step on each GPU")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)

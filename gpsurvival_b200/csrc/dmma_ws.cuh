@@ -370,6 +370,7 @@ __global__ void __launch_bounds__(Cfg::NTHREADS, Cfg::CTAS_PER_SM)
 using WsCfg128 = WsCfg<128, 128, 16, 2, 4, 5>;        // 8 consumer warps of 64 x 32, 5 stages, 170 KB smem
 using WsCfg64 = WsCfg<64, 64, 16, 2, 2, 3, 3>;        // 4 consumer warps of 32 x 32, 3 stages, 52 KB smem
 using WsCfg80 = WsCfg<80, 80, 16, 2, 2, 4, 2>;        // 4 consumer warps of 40 x 40, 4 stages, 86 KB smem
+using WsCfgN32 = WsCfg<128, 32, 16, 4, 1, 4, 3>;      // narrow outputs (N <= 32, e.g. M * Xaug with d = 20): 4 warps of 32 x 32
 
 // `sched`: two ints in device memory, zero before the first launch that uses them (the kernel re-arms them);
 // launches that may overlap in time must not share them.

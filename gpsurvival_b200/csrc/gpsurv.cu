@@ -238,11 +238,12 @@ bool use_ws128(const H* h, const GemmParams& p) {
 }
 
 // Tile configuration of an "NT" GEMM: 128 / 80 / 64 = warp-specialised persistent kernel with that square
-// tile (dmma_ws.cuh), 0 = the 64 x 64 cp.async kernel (short k-loops: K < 128, where a persistent tile's
+// tile, 32 = its 128 x 32 tile for narrow outputs (dmma_ws.cuh), 0 = the 64 x 64 cp.async kernel (short k-loops: K < 128, where a persistent tile's
 // un-overlapped epilogue dominates; and every developer override).
 int pick_nt_tile(const H* h, const GemmParams& p) {
   if (h->force_tile >= 0 || !h->ws_enabled || !h->ws_sched || p.K < 128) return 0;
   if (use_ws128(h, p)) return 128;
+  if (p.N <= 32 && !p.lower && (long long)ceil_div(p.M, 128) * h->batch * p.nodes * p.ksplit >= h->num_sms) return 32;
   {   // a launch that cannot even fill the persistent grid once (a lone mid-size fit) is latency-bound: the plain
       // kernel starts faster (no barrier set-up, no scheduler round trip) — measured 1.87 vs 2.02 ms on a lone C2 fit
     ws::TileEnum te;
@@ -268,6 +269,8 @@ void gemm(H* h, const GemmParams& p, const Epi& epi) {
         e = launch_gemm_ws<WsCfg128, false, false, Epi>(p, epi, h->batch, h->num_sms, sched, h->cur);
       else if (tile == 80)
         e = launch_gemm_ws<WsCfg80, false, false, Epi>(p, epi, h->batch, h->num_sms, sched, h->cur);
+      else if (tile == 32)
+        e = launch_gemm_ws<WsCfgN32, false, false, Epi>(p, epi, h->batch, h->num_sms, sched, h->cur);
       else
         e = launch_gemm_ws<WsCfg64, false, false, Epi>(p, epi, h->batch, h->num_sms, sched, h->cur);
       h->seq_launches++;
@@ -539,7 +542,7 @@ void enqueue_grad(H* h) {
     e.X = h->Xaug; e.ldx = h->ldx; e.strideX = h->strideX; e.colpart = h->colpart; e.ldp = h->ldmu;
     e.rs = h->rs_part; e.ldn = h->ld;
     const int tile = pick_nt_tile(h, p);
-    e.mtiles = ceil_div(n, tile ? tile : (h->force_tile == 2 ? 128 : 64));
+    e.mtiles = ceil_div(n, tile == 32 ? 128 : tile ? tile : (h->force_tile == 2 ? 128 : 64));
     h->mtiles_grad = e.mtiles * h->grad_ksplit;
     gemm<false, false>(h, p, e);
   }
