@@ -55,6 +55,10 @@ struct GemmParams {
   int nodes;
   long long nodeStrideA, nodeStrideB;
   int clip_total, clip_step, k_eq_m, clip_n;
+  // weighted product C = A diag(w) B (warp-specialised kernel only, template flag KS): w[k] per batch entry,
+  // readable in whole 16-element groups up to K rounded up to 16 (zeros beyond K)
+  const double* kscale;
+  long long strideScale;
 };
 
 // per-node clipping of the problem extents (see GemmParams); false when the node has nothing to do

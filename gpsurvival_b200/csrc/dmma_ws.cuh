@@ -165,11 +165,14 @@ struct WsSmem {
   static constexpr int A_STAGE = A_ROWS * LDA;
   static constexpr int B_STAGE = B_ROWS * LDB;
   static constexpr int SCRATCH = Cfg::WARPS_M * Cfg::BN;   // doubles, for epilogues (EpiColDot)
-  static constexpr size_t BYTES =
-      ((size_t)Cfg::STAGES * (A_STAGE + B_STAGE) + SCRATCH) * sizeof(double) + 2 * Cfg::STAGES * 8 + Cfg::STAGES * sizeof(int);
+  static constexpr int WSC = Cfg::STAGES * Cfg::BK;        // doubles, per-stage k-weights (KS kernels)
+  static constexpr size_t BYTES = ((size_t)Cfg::STAGES * (A_STAGE + B_STAGE) + SCRATCH + WSC) * sizeof(double) +
+                                  2 * Cfg::STAGES * 8 + Cfg::STAGES * sizeof(int);
 };
 
-template <class Cfg, bool A_KC, bool B_KC, class Epi>
+// KS: weighted product A diag(w) B — the producer also stages w[kbase .. kbase+BK) and the consumers scale their
+// A fragments by it (CovFunc's x / ell without ever materialising the scaled copy of X).
+template <class Cfg, bool A_KC, bool B_KC, class Epi, bool KS = false>
 __global__ void __launch_bounds__(Cfg::NTHREADS, Cfg::CTAS_PER_SM)
     dmma_ws_kernel(GemmParams p_in, Epi epi, int zcount, int rev_m, int rev_n, int* __restrict__ sched) {
   using SL = WsSmem<Cfg, A_KC, B_KC>;
@@ -179,7 +182,8 @@ __global__ void __launch_bounds__(Cfg::NTHREADS, Cfg::CTAS_PER_SM)
   double* sA = smem;
   double* sB = smem + STAGES * SL::A_STAGE;
   double* scratch = smem + STAGES * (SL::A_STAGE + SL::B_STAGE);
-  unsigned long long* full = reinterpret_cast<unsigned long long*>(scratch + SL::SCRATCH);
+  double* s_w = scratch + SL::SCRATCH;
+  unsigned long long* full = reinterpret_cast<unsigned long long*>(s_w + SL::WSC);
   unsigned long long* empty = full + STAGES;
   volatile int* stage_tile = reinterpret_cast<volatile int*>(empty + STAGES);   // tile index carried by each stage
 
@@ -261,8 +265,11 @@ __global__ void __launch_bounds__(Cfg::NTHREADS, Cfg::CTAS_PER_SM)
             }
           }
         }
+        if (KS && lane == 0) bytes += BK * 8;
         if (vk < BK) asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
         ws::mbar_arrive_tx(full + s, bytes);
+        if (KS && lane == 0)
+          ws::bulk_g2s(s_w + s * BK, p.kscale + (size_t)w.batch * p.strideScale + (size_t)kbase, BK * 8, full + s);
         // pass 2: the copies
         if (!A_KC) {
           const unsigned nb = ((vm + 1) & ~1) * 8;
@@ -333,6 +340,11 @@ __global__ void __launch_bounds__(Cfg::NTHREADS, Cfg::CTAS_PER_SM)
             int m = wm0 + 8 * i + g, k = 4 * ks + t4;
             af[i] = A_KC ? a_s[m * SL::LDA + k] : a_s[k * SL::LDA + m];
           }
+          if (KS) {
+            const double wk = s_w[s * BK + 4 * ks + t4];
+#pragma unroll
+            for (int i = 0; i < FM; i++) af[i] *= wk;
+          }
 #pragma unroll
           for (int j = 0; j < FN; j++) {
             int n = wn0 + 8 * j + g, k = 4 * ks + t4;
@@ -370,14 +382,16 @@ __global__ void __launch_bounds__(Cfg::NTHREADS, Cfg::CTAS_PER_SM)
 using WsCfg128 = WsCfg<128, 128, 16, 2, 4, 5>;        // 8 consumer warps of 64 x 32, 5 stages, 170 KB smem
 using WsCfg64 = WsCfg<64, 64, 16, 2, 2, 3, 3>;        // 4 consumer warps of 32 x 32, 3 stages, 52 KB smem
 using WsCfg80 = WsCfg<80, 80, 16, 2, 2, 4, 2>;        // 4 consumer warps of 40 x 40, 4 stages, 86 KB smem
+using WsCfg96 = WsCfg<96, 96, 16, 2, 4, 6, 1>;         // 8 consumer warps of 48 x 24: row counts just under a multiple of 96 (n = 285)
+using WsCfg96x64 = WsCfg<96, 64, 16, 2, 2, 3, 3>;     // 4 consumer warps of 48 x 32, 3 CTAs/SM: the same rows against a wide N (M * Xaug, d = 10^4)
 using WsCfgN32 = WsCfg<128, 32, 16, 4, 1, 4, 3>;      // narrow outputs (N <= 32, e.g. M * Xaug with d = 20): 4 warps of 32 x 32
 
 // `sched`: two ints in device memory, zero before the first launch that uses them (the kernel re-arms them);
 // launches that may overlap in time must not share them.
-template <class Cfg, bool A_KC, bool B_KC, class Epi>
+template <class Cfg, bool A_KC, bool B_KC, class Epi, bool KS = false>
 cudaError_t launch_gemm_ws(const GemmParams& p, const Epi& epi, int batch, int num_sms, int* sched, cudaStream_t st) {
   using SL = WsSmem<Cfg, A_KC, B_KC>;
-  auto kern = dmma_ws_kernel<Cfg, A_KC, B_KC, Epi>;
+  auto kern = dmma_ws_kernel<Cfg, A_KC, B_KC, Epi, KS>;
   static bool attr_set[64] = {false};   // per instantiation, per device
   int dev = 0;
   cudaGetDevice(&dev);

@@ -78,6 +78,7 @@ struct gps_handle_s {
   // matrices (work set)
   double *K = nullptr, *Ky = nullptr, *L = nullptr, *Linv = nullptr, *Kinv = nullptr, *gsplit = nullptr;
   double* U = nullptr;           // U = Linv' (upper triangular), built next to Linv by trtri_levels
+  double* wsc = nullptr;         // [batch][ldmu] k-weights 1/ell_k^2 of the weighted Gram product (hyp_prep_kernel)
   int num_sms = 148;
   int ws_enabled = 1;            // GPS_WS=0: never use the warp-specialised 128 x 128 kernel
   int ws_min_tiles = 296;        // GPS_WS_MIN: minimum number of 128 x 128 tiles in a launch
@@ -118,6 +119,8 @@ struct gps_handle_s {
   // launch tails run beside another group's GEMMs.  GPS_GROUPS overrides (1 = off).
   static constexpr int MAX_GROUPS = 8;
   int groups = 1;
+  bool groups_forced = false;   // GPS_GROUPS given: use it at every n (default: groups only from n = 1024 up, where the
+                                // Cholesky's panel chains are a visible share; measured neutral-to-slower below)
   cudaStream_t gst[MAX_GROUPS] = {nullptr};
   cudaEvent_t ev_gfork = nullptr, ev_gjoin[MAX_GROUPS] = {nullptr};
   // bookkeeping
@@ -192,7 +195,7 @@ void free_data(H* h) {
   dfree(h->rnpart); dfree(h->rnorm); dfree(h->meanv); dfree(h->zvec); dfree(h->alpha);
   dfree(h->wdiag); dfree(h->rs); dfree(h->rs_part); dfree(h->colpart); dfree(h->qtu); dfree(h->d_nlml); dfree(h->d_logdet);
   dfree(h->d_grad); dfree(h->info);
-  dfree(h->K); dfree(h->Ky); dfree(h->L); dfree(h->Linv); dfree(h->Kinv); dfree(h->gsplit); dfree(h->U); dfree(h->XaugT);
+  dfree(h->K); dfree(h->Ky); dfree(h->L); dfree(h->Linv); dfree(h->Kinv); dfree(h->gsplit); dfree(h->U); dfree(h->XaugT); dfree(h->wsc);
   dfree(h->mL); dfree(h->mLinv); dfree(h->m_alpha); dfree(h->m_hyp); dfree(h->m_ell); dfree(h->m_meanw);
   dfree(h->Xs); dfree(h->Zs); dfree(h->snorm); dfree(h->snpart); dfree(h->Ks); dfree(h->V); dfree(h->mstar);
   dfree(h->pout);
@@ -250,12 +253,28 @@ int pick_nt_tile(const H* h, const GemmParams& p) {
     te.init(p.M, p.N, 64, 64, p.lower, 0);
     if ((long long)te.per_z * h->batch * p.nodes * p.ksplit < (long long)h->num_sms * WsCfg64::CTAS_PER_SM) return 0;
   }
-  // 80-wide tiles when they pad the rows and columns of a small problem visibly less than 64-wide ones
-  if (p.M <= 1024 && p.N >= 80 && p.M >= 80) {
-    const double w64 = (double)round_up(p.M, 64) * round_up(p.N, 64), w80 = (double)round_up(p.M, 80) * round_up(p.N, 80);
-    if (w80 < 0.93 * w64) return 80;
+  // small problems: the tile size that pads the rows and columns least (64 unless another wins by > 7 %)
+  if (p.M <= 1024 && p.M >= 80) {
+    const double w64 = (double)round_up(p.M, 64) * round_up(p.N, 64);
+    double best = 0.93 * w64;
+    int pick = 64;
+    if (p.N >= 80) {
+      const double w80 = (double)round_up(p.M, 80) * round_up(p.N, 80);
+      if (w80 < best) { best = w80; pick = 80; }
+      const double w96 = (double)round_up(p.M, 96) * round_up(p.N, 96);
+      if (w96 < best) { best = w96; pick = 96; }
+    }
+    if (!p.lower && p.N >= 512) {
+      const double w96w = (double)round_up(p.M, 96) * round_up(p.N, 64);
+      if (w96w < best * 1.02) { best = w96w; pick = 97; }   // 96 x 64, three CTAs per SM
+    }
+    return pick;
   }
   return 64;
+}
+inline int tile_bm(const H* h, int code) {   // rows of the tile a pick_nt_tile() code stands for
+  return code == 128 || code == 32 ? 128 : code == 80 ? 80 : code == 96 || code == 97 ? 96 : code == 64 ? 64
+         : (h->force_tile == 2 ? 128 : 64);
 }
 
 template <bool A_KC, bool B_KC, class Epi>
@@ -271,6 +290,10 @@ void gemm(H* h, const GemmParams& p, const Epi& epi) {
         e = launch_gemm_ws<WsCfg80, false, false, Epi>(p, epi, h->batch, h->num_sms, sched, h->cur);
       else if (tile == 32)
         e = launch_gemm_ws<WsCfgN32, false, false, Epi>(p, epi, h->batch, h->num_sms, sched, h->cur);
+      else if (tile == 96)
+        e = launch_gemm_ws<WsCfg96, false, false, Epi>(p, epi, h->batch, h->num_sms, sched, h->cur);
+      else if (tile == 97)
+        e = launch_gemm_ws<WsCfg96x64, false, false, Epi>(p, epi, h->batch, h->num_sms, sched, h->cur);
       else
         e = launch_gemm_ws<WsCfg64, false, false, Epi>(p, epi, h->batch, h->num_sms, sched, h->cur);
       h->seq_launches++;
@@ -291,6 +314,27 @@ void gemm(H* h, const GemmParams& p, const Epi& epi) {
     e = launch_gemm<CfgLarge, A_KC, B_KC, Epi>(p, epi, h->batch, h->cur);
   else
     e = launch_gemm<CfgS3, A_KC, B_KC, Epi>(p, epi, h->batch, h->cur);
+  h->seq_launches++;
+  CKV(h, e);
+}
+
+// Weighted "NT" product A diag(w) B' on the warp-specialised kernel (p.kscale set; pick_nt_tile(h, p) != 0).
+void gemm_ks(H* h, const GemmParams& p, const EpiPlain& epi) {
+  const int tile = pick_nt_tile(h, p);
+  int* sched = h->ws_sched + 2 * (h->ws_seq++ % WS_SLOTS);
+  cudaError_t e;
+  if (tile == 128)
+    e = launch_gemm_ws<WsCfg128, false, false, EpiPlain, true>(p, epi, h->batch, h->num_sms, sched, h->cur);
+  else if (tile == 80)
+    e = launch_gemm_ws<WsCfg80, false, false, EpiPlain, true>(p, epi, h->batch, h->num_sms, sched, h->cur);
+  else if (tile == 96)
+    e = launch_gemm_ws<WsCfg96, false, false, EpiPlain, true>(p, epi, h->batch, h->num_sms, sched, h->cur);
+  else if (tile == 97)
+    e = launch_gemm_ws<WsCfg96x64, false, false, EpiPlain, true>(p, epi, h->batch, h->num_sms, sched, h->cur);
+  else if (tile == 32)
+    e = launch_gemm_ws<WsCfgN32, false, false, EpiPlain, true>(p, epi, h->batch, h->num_sms, sched, h->cur);
+  else
+    e = launch_gemm_ws<WsCfg64, false, false, EpiPlain, true>(p, epi, h->batch, h->num_sms, sched, h->cur);
   h->seq_launches++;
   CKV(h, e);
 }
@@ -320,15 +364,34 @@ int pick_gram_ksplit(const H* h, int n1, int n2, int d, bool sym) {
     int v = atoi(ev);
     if (v >= 1) return v > 32 ? 32 : v;
   }
-  long long tiles = (long long)ceil_div(n1, 64) * ceil_div(n2, 64);
-  if (sym) tiles = tiles / 2 + 1;
-  tiles *= h->batch;
-  if (tiles >= 148 || d < 256) return 1;
-  int ks = (int)((2 * 148 + tiles - 1) / tiles);
-  int maxks = d / 128;
-  if (ks > maxks) ks = maxks;
-  if (ks > 32) ks = 32;
-  return ks < 1 ? 1 : ks;
+  if (d < 512) return 1;
+  // The Gram GEMM runs on the persistent kernel: equal-length tiles come in whole rounds of `slots`, so few
+  // long tiles leave the last round mostly empty (C3 x 32 with 64-wide tiles: 480 tiles on 444 slots = 2
+  // rounds for 1.08 rounds of work).  Split K so that the rounds fill; the price is the split workspace and the
+  // finishing pass.  Cost model in microseconds (a resident CTA's 16-deep k-step at the DMMA peak).
+  const int per_launch = (h->groups_forced || n1 >= 1024) ? ceil_div(h->batch, std::max(1, std::min(h->groups, h->batch))) : h->batch;
+  GemmParams probe = gp(nullptr, 0, 0, nullptr, 0, 0, n1, n2, d);
+  probe.lower = sym ? 1 : 0;
+  H hv = *h;
+  hv.batch = per_launch;
+  const int code = pick_nt_tile(&hv, probe);
+  const int bm = tile_bm(h, code), bn = (code == 97) ? 64 : (code == 32 ? 32 : bm);
+  const int cps = (code == 64 || code == 97 || code == 32) ? 3 : (code == 80 ? 2 : (code == 0 ? 4 : 1));
+  ws::TileEnum te;
+  te.init(n1, n2, bm, bn, (sym && bm == bn) ? 1 : 0, 0);
+  const long long tiles = (long long)te.per_z * per_launch;
+  const long long slots = (long long)h->num_sms * cps;
+  const double step_us = 2.0 * bm * bn * 16.0 * cps * h->num_sms / 37.0e6;
+  int best = 1;
+  double best_cost = 1e300;
+  for (int ks = 1; ks <= 32 && ks <= d / 256; ks++) {
+    const long long rounds = (tiles * ks + slots - 1) / slots;
+    const double klen = std::ceil((double)d / ks / 16.0);
+    double cost = rounds * (klen * step_us + 3.0);
+    if (ks > 1) cost += 15.0 + (double)ks * n1 * n2 * 8.0 * per_launch / 4.0e6;   // finish: read ks slices at ~4 TB/s
+    if (cost < best_cost * 0.97) { best_cost = cost; best = ks; }
+  }
+  return best;
 }
 
 inline int cov_kind(int cov_form) {   // ModelOpts.cov_form -> cov_kernel_fn selector
@@ -491,16 +554,49 @@ void enqueue_prescale_train(H* h, const double* ell, int ell_batched) {
   LAUNCHED(h);
 }
 
+// Training covariance K, Ky (CovFunc.R:21-39 + ForOptimisationLog.R:35-40).  Two routes:
+//  * weighted Gram (default): G = X diag(1/ell^2) X' straight from the centred X on the warp-specialised
+//    kernel (the scaled copy Z = X / ell is never written or re-read: 2 x 8 n d bytes per evaluation, the
+//    largest memory stream at d >> n), raw slices into the split workspace, row norms = diag(G), then one
+//    finishing pass (r2 -> covariance function -> K, Ky);
+//  * pre-scale + Gram with the fused covariance epilogue: lone small fits (the plain kernel has no k-weights)
+//    and the as-written ARD recycling (CovFunc.R:25, weights depend on the row).
+void enqueue_gram_train(H* h) {
+  const int n = h->n;
+  GemmParams p = gp(h->Xaug, h->ldx, h->strideX, h->Xaug, h->ldx, h->strideX, n, n, h->d);
+  p.lower = 1;
+  p.ksplit = std::max(1, h->gram_ksplit);
+  const bool as_written = (h->o.ard_mode == 1 && h->p > 1);
+  if (h->wsc && h->gsplit && !as_written && pick_nt_tile(h, p) != 0) {
+    const int ks = p.ksplit;
+    p.kscale = h->wsc;
+    p.strideScale = h->ldmu;
+    EpiPlain e = plain(h->gsplit, h->ld, (long long)ks * h->strideM, 1.0, 0.0);
+    e.strideSplit = h->strideM;
+    gemm_ks(h, p, e);
+    gram_diag_kernel<<<dim3(ceil_div(n, 256), h->batch), 256, 0, h->st>>>(h->gsplit, n, h->ld, h->strideM,
+                                                                          (long long)ks * h->strideM, ks, h->rnorm, h->ld);
+    LAUNCHED(h);
+    dim3 grid(ceil_div(n, 32), ceil_div(n, 8), h->batch), block(32, 8);
+    cov_finish_kernel<<<grid, block, 0, h->st>>>(h->gsplit, n, n, h->ld, h->strideM, (long long)ks * h->strideM, ks, h->rnorm,
+                                                  h->rnorm, h->ld, h->hyp, h->noise_diag, h->K, h->Ky, h->ld, h->strideM, 1,
+                                                  cov_kind(h->o.cov_form));
+    LAUNCHED(h);
+    return;
+  }
+  enqueue_prescale_train(h, h->ell, 1);
+  enqueue_cov(h, h->Z, n, h->ldx, h->strideX, h->rnorm, h->Z, n, h->ldx, h->strideX, h->rnorm, h->d, h->hyp,
+              h->noise_diag, h->K, h->Ky, h->ld, h->strideM, true, h->gram_ksplit, cov_kind(h->o.cov_form));
+}
+
 void enqueue_factor(H* h) {
   const int n = h->n;
   CKV(h, cudaMemsetAsync(h->info, 0, sizeof(int) * h->batch, h->st));
   hyp_prep_kernel<<<h->batch, 256, 0, h->st>>>(h->par, h->par_cap, h->o, n, h->d, h->p, h->events, h->cens_rank, h->lsc,
                                                 h->ldc, h->ld, h->mu, h->ldmu, h->hyp, h->ell, h->ldmu, h->meanw,
-                                                h->noise_diag);
+                                                h->noise_diag, h->wsc);
   LAUNCHED(h);
-  enqueue_prescale_train(h, h->ell, 1);
-  enqueue_cov(h, h->Z, n, h->ldx, h->strideX, h->rnorm, h->Z, n, h->ldx, h->strideX, h->rnorm, h->d, h->hyp,
-              h->noise_diag, h->K, h->Ky, h->ld, h->strideM, true, h->gram_ksplit, cov_kind(h->o.cov_form));
+  enqueue_gram_train(h);
   fill_aug_kernel<<<dim3(ceil_div(h->ne, 128), h->batch), 128, 0, h->st>>>(
       h->Xaug, n, h->ne, h->d, h->ldx, h->strideX, h->meanw, h->ldmu, h->o.mean_form == 1, h->y, h->ld, h->meanv, h->Ky,
       h->ld, h->strideM, h->nrhs);
@@ -542,7 +638,7 @@ void enqueue_grad(H* h) {
     e.X = h->Xaug; e.ldx = h->ldx; e.strideX = h->strideX; e.colpart = h->colpart; e.ldp = h->ldmu;
     e.rs = h->rs_part; e.ldn = h->ld;
     const int tile = pick_nt_tile(h, p);
-    e.mtiles = ceil_div(n, tile == 32 ? 128 : tile ? tile : (h->force_tile == 2 ? 128 : 64));
+    e.mtiles = ceil_div(n, tile_bm(h, tile));
     h->mtiles_grad = e.mtiles * h->grad_ksplit;
     gemm<false, false>(h, p, e);
   }
@@ -581,7 +677,7 @@ void make_view(const H* h, int g0, int cnt, cudaStream_t st, H* v) {
   v->seq_launches = 0;
   const size_t g = (size_t)g0;
   adv(v->Xaug, g * h->strideX); adv(v->Z, g * h->strideX); adv(v->XaugT, g * h->strideXT);
-  adv(v->mu, g * h->ldmu); adv(v->ell, g * h->ldmu); adv(v->meanw, g * h->ldmu);
+  adv(v->mu, g * h->ldmu); adv(v->ell, g * h->ldmu); adv(v->meanw, g * h->ldmu); adv(v->wsc, g * h->ldmu);
   adv(v->y, g * h->ld); adv(v->events, g * h->ld); adv(v->noise_diag, g * h->ld); adv(v->rnorm, g * h->ld);
   adv(v->meanv, g * h->ld); adv(v->wdiag, g * h->ld); adv(v->rs, g * h->ld); adv(v->cens_rank, g * h->ld);
   adv(v->lsc, g * h->ldc);
@@ -594,12 +690,12 @@ void make_view(const H* h, int g0, int cnt, cudaStream_t st, H* v) {
   adv(v->d_nlml, g); adv(v->d_logdet, g); adv(v->info, g); adv(v->d_ncens, g);
   adv(v->K, g * h->strideM); adv(v->Ky, g * h->strideM); adv(v->L, g * h->strideM); adv(v->Linv, g * h->strideM);
   adv(v->Kinv, g * h->strideM); adv(v->U, g * h->strideM);
-  adv(v->gsplit, g * h->gram_ksplit * h->strideM);
+  adv(v->gsplit, g * std::max(1, h->gram_ksplit) * h->strideM);
 }
 
 // Enqueue a sequence for the whole batch: once, or once per stream group (fork from / join into h->st).
 void enqueue_grouped(H* h, SeqFn fn) {
-  const int G = std::min(h->groups, h->batch);
+  const int G = (h->groups_forced || h->n >= 1024) ? std::min(h->groups, h->batch) : 1;
   if (G <= 1 || h->lookahead) {
     fn(h);
     return;
@@ -851,7 +947,10 @@ int gps_create_batch(int device, int batch, gps_handle* out) {
   }
   if (const char* ev = getenv("GPS_LOOKAHEAD")) h->lookahead = atoi(ev) != 0;
   h->groups = batch >= 16 ? 2 : 1;
-  if (const char* ev = getenv("GPS_GROUPS")) h->groups = atoi(ev);
+  if (const char* ev = getenv("GPS_GROUPS")) {
+    h->groups = atoi(ev);
+    h->groups_forced = true;
+  }
   h->groups = std::max(1, std::min(std::min(h->groups, (int)H::MAX_GROUPS), batch));
   bool okg = cudaEventCreateWithFlags(&h->ev_gfork, cudaEventDisableTiming) == cudaSuccess;
   for (int g = 1; g < h->groups && okg; g++)
@@ -994,10 +1093,9 @@ int gps_set_data(gps_handle h, const double* X, int n, int d, const double* y, c
   CK(h, dalloc(&h->U, mat));
   CK(h, dalloc(&h->mL, mat));
   CK(h, dalloc(&h->mLinv, mat));
-  if (h->gram_ksplit > 1) {
-    h->gsplit_elems = mat * h->gram_ksplit;
-    CK(h, dalloc(&h->gsplit, h->gsplit_elems, false));
-  }
+  h->gsplit_elems = mat * std::max(1, h->gram_ksplit);   // raw Gram slices (>= 1: the weighted-Gram path always goes through it)
+  CK(h, dalloc(&h->gsplit, h->gsplit_elems, false));
+  CK(h, dalloc(&h->wsc, (size_t)h->ldmu * B));
   CK(h, dalloc(&h->m_alpha, vecB * 2));
   CK(h, dalloc(&h->m_hyp, (size_t)4 * B));
   CK(h, dalloc(&h->m_ell, (size_t)h->ldmu * B));
@@ -1664,10 +1762,8 @@ int gps_time_stages(gps_handle h, double* ms_out) {
   CKV(h, cudaMemsetAsync(h->info, 0, sizeof(int) * h->batch, h->st));
   hyp_prep_kernel<<<h->batch, 256, 0, h->st>>>(h->par, h->par_cap, h->o, n, h->d, h->p, h->events, h->cens_rank, h->lsc,
                                                 h->ldc, h->ld, h->mu, h->ldmu, h->hyp, h->ell, h->ldmu, h->meanw,
-                                                h->noise_diag);
-  enqueue_prescale_train(h, h->ell, 1);
-  enqueue_cov(h, h->Z, n, h->ldx, h->strideX, h->rnorm, h->Z, n, h->ldx, h->strideX, h->rnorm, h->d, h->hyp,
-              h->noise_diag, h->K, h->Ky, h->ld, h->strideM, true, h->gram_ksplit, cov_kind(h->o.cov_form));
+                                                h->noise_diag, h->wsc);
+  enqueue_gram_train(h);
   fill_aug_kernel<<<dim3(ceil_div(h->ne, 128), h->batch), 128, 0, h->st>>>(
       h->Xaug, n, h->ne, h->d, h->ldx, h->strideX, h->meanw, h->ldmu, h->o.mean_form == 1, h->y, h->ld, h->meanv, h->Ky,
       h->ld, h->strideM, h->nrhs);

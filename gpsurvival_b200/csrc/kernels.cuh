@@ -93,7 +93,8 @@ __global__ void hyp_prep_kernel(const double* __restrict__ par, int len, ModelOp
                                 const double* __restrict__ log_sc2_vec, int ldc, int ldn,
                                 const double* __restrict__ mu, int ldmu,
                                 double* __restrict__ hyp, double* __restrict__ ell, int ldell,
-                                double* __restrict__ meanw, double* __restrict__ noise_diag) {
+                                double* __restrict__ meanw, double* __restrict__ noise_diag,
+                                double* __restrict__ wsc) {
   __shared__ double sh[256];
   int b = blockIdx.x, tid = threadIdx.x;
   const double* pr = par + (size_t)b * len;
@@ -107,6 +108,12 @@ __global__ void hyp_prep_kernel(const double* __restrict__ par, int len, ModelOp
     hyp[b * 4 + 3] = 0.0;
   }
   for (int k = tid; k < p; k += blockDim.x) ell[(size_t)b * ldell + k] = exp(pr[2 + k]);
+  // k-weights of the weighted Gram product X diag(1/ell^2) X' (entries beyond d stay zero)
+  if (wsc)
+    for (int k = tid; k < d; k += blockDim.x) {
+      const double e = exp(pr[2 + (p == 1 ? 0 : k)]);
+      wsc[(size_t)b * ldell + k] = 1.0 / (e * e);
+    }
   // mean weights
   double dot = 0.0;
   if (o.mean_form == 1) {
@@ -151,7 +158,31 @@ __global__ void prescale_kernel(const double* __restrict__ X, int n, int d, int 
   const double* el = ell + (ell_batch_stride_on ? (size_t)b * ldell : 0);
   const double* m = mu + (mu_batch_stride_on ? (size_t)b * ldmu : 0);
   double acc = 0.0;
-  for (int k = k0; k < k1; k++) {
+  // 8 independent loads in flight per thread: with one, the loop is bound by DRAM latency, not bandwidth
+  // (measured 643 us for 1.46 GB at C3 x 32); the sum stays in column order.
+  constexpr int UN = 8;
+  int k = k0;
+  for (; k + UN <= k1; k += UN) {
+    double xv[UN], dv[UN];
+#pragma unroll
+    for (int u = 0; u < UN; u++) xv[u] = x[(size_t)(k + u) * ldx];
+#pragma unroll
+    for (int u = 0; u < UN; u++) {
+      if (p == 1) dv[u] = el[0];
+      else if (!as_written) dv[u] = el[k + u];
+      else {
+        xv[u] += m[k + u];
+        dv[u] = el[(int)(((long long)i + (long long)(k + u) * nrec) % p)];
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < UN; u++) {
+      const double v = xv[u] / dv[u];
+      z[(size_t)(k + u) * ldz] = v;
+      acc += v * v;
+    }
+  }
+  for (; k < k1; k++) {
     double xv = x[(size_t)k * ldx];
     double v;
     if (p == 1) v = xv / el[0];
@@ -170,6 +201,17 @@ __global__ void rownorm_finish_kernel(const double* __restrict__ part, int n, in
   if (i >= n) return;
   double a = 0.0;
   for (int ks = 0; ks < ksplit; ks++) a += part[((size_t)b * ksplit + ks) * ldn + i];
+  s[(size_t)b * ldn + i] = a;
+}
+
+// Squared row norms of the scaled rows = diagonal of the (split) Gram matrix, slices summed in fixed order.
+// grid (ceil(n/256), batch)
+__global__ void gram_diag_kernel(const double* __restrict__ Gpart, int n, int ldg, long long strideSplit,
+                                 long long strideG, int ksplit, double* __restrict__ s, int ldn) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x, b = blockIdx.y;
+  if (i >= n) return;
+  double a = 0.0;
+  for (int k = 0; k < ksplit; k++) a += Gpart[(size_t)b * strideG + (size_t)k * strideSplit + (size_t)i + (size_t)i * ldg];
   s[(size_t)b * ldn + i] = a;
 }
 
