@@ -383,59 +383,84 @@ struct EpiCov {
 };
 
 // Gradient contraction epilogue (north_star item 4): P = M * Xaug is never written.
-//   colpart[mtile][n] = sum_{m in tile} Xaug[m,n] * P[m,n]      (deterministic per-tile partials)
-//   rs[m]            = P[m, N-1]                                  (Xaug's last column is all ones => rowsum(M))
+//   colpart[mtile][split][n] = sum_{m in tile} Xaug[m,n] * P[m,n]          (deterministic per-tile partials)
+//   tpart[mtile][n]          = sum_{m in tile} rs[m] * Xaug[m,n]^2         (rs = rowsum(M), from wk_kernel; split 0 only)
+// so that 2 rowsum(M) . x_k^2 - 2 x_k' M x_k needs no further pass over Xaug.
 struct EpiColDot {
   const double* X;   // Xaug, column-major, ldx
   int ldx;
   long long strideX;
   double* colpart;   // [batch][mtiles * ksplit][ldp]   (slice = mtile * ksplit + split)
   int ldp, mtiles;
-  double* rs;        // [batch][ksplit][ldn]: per-split partial of the last column (summed in fixed order later)
+  const double* rs;  // [batch][ldn] rowsum(M)
+  double* tpart;     // [batch][mtiles][ldp]
   int ldn;
   template <class Cfg>
   __device__ __forceinline__ void operator()(const GemmParams& p, AccTile<Cfg>& a, double* smem) const {
     const double* __restrict__ Xb = X + (size_t)a.batch * strideX;
-    double part[Cfg::FN];
+    const double* __restrict__ rb = rs + (size_t)a.batch * ldn;
+    const bool want_t = (a.split == 0);
+    double rsm[Cfg::FM][2];
+#pragma unroll
+    for (int i = 0; i < Cfg::FM; i++) {
+      int m = a.m_base + 8 * i;
+      rsm[i][0] = (want_t && m < p.M) ? rb[m] : 0.0;
+      rsm[i][1] = (want_t && m + 1 < p.M) ? rb[m + 1] : 0.0;
+    }
+    double part[Cfg::FN], tp[Cfg::FN];
 #pragma unroll
     for (int j = 0; j < Cfg::FN; j++) {
       int n = a.n_base + 8 * j;
-      double s = 0.0;
+      double s = 0.0, ts = 0.0;
       if (n < p.N) {
 #pragma unroll
         for (int i = 0; i < Cfg::FM; i++) {
           int m = a.m_base + 8 * i;
-          if (m < p.M) s += Xb[(size_t)m + (size_t)n * ldx] * a.v[i][j][0];
-          if (m + 1 < p.M) s += Xb[(size_t)m + 1 + (size_t)n * ldx] * a.v[i][j][1];
-          if (n == p.N - 1) {
-            double* r = rs + ((size_t)a.batch * p.ksplit + a.split) * ldn;
-            if (m < p.M) r[m] = a.v[i][j][0];
-            if (m + 1 < p.M) r[m + 1] = a.v[i][j][1];
+          if (m < p.M) {
+            const double x0 = Xb[(size_t)m + (size_t)n * ldx];
+            s += x0 * a.v[i][j][0];
+            ts += rsm[i][0] * (x0 * x0);
+          }
+          if (m + 1 < p.M) {
+            const double x1 = Xb[(size_t)m + 1 + (size_t)n * ldx];
+            s += x1 * a.v[i][j][1];
+            ts += rsm[i][1] * (x1 * x1);
           }
         }
       }
       // fixed-order reduction over the 4 lanes (t) that share column n
       s += __shfl_xor_sync(0xffffffffu, s, 1);
       s += __shfl_xor_sync(0xffffffffu, s, 2);
+      ts += __shfl_xor_sync(0xffffffffu, ts, 1);
+      ts += __shfl_xor_sync(0xffffffffu, ts, 2);
       part[j] = s;
+      tp[j] = ts;
     }
     // across the WARPS_M warps that share the same columns: shared memory, fixed order
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int wmi = warp % Cfg::WARPS_M;
     const int wn0 = (warp / Cfg::WARPS_M) * Cfg::WN;
-    double* red = smem;   // [WARPS_M][BN]
+    double* red = smem;                              // [WARPS_M][BN]
+    double* redt = smem + Cfg::WARPS_M * Cfg::BN;    // [WARPS_M][BN]
     if ((lane & 3) == 0) {
 #pragma unroll
-      for (int j = 0; j < Cfg::FN; j++) red[wmi * Cfg::BN + wn0 + 8 * j + (lane >> 2)] = part[j];
+      for (int j = 0; j < Cfg::FN; j++) {
+        red[wmi * Cfg::BN + wn0 + 8 * j + (lane >> 2)] = part[j];
+        redt[wmi * Cfg::BN + wn0 + 8 * j + (lane >> 2)] = tp[j];
+      }
     }
     Cfg::sync();
     for (int c = threadIdx.x; c < Cfg::BN; c += Cfg::NT) {
       int n = a.n0 + c;
       if (n < p.N) {
-        double s = 0.0;
+        double s = 0.0, ts = 0.0;
 #pragma unroll
-        for (int w = 0; w < Cfg::WARPS_M; w++) s += red[w * Cfg::BN + c];
+        for (int w = 0; w < Cfg::WARPS_M; w++) {
+          s += red[w * Cfg::BN + c];
+          ts += redt[w * Cfg::BN + c];
+        }
         colpart[(((size_t)a.batch * mtiles + a.m0 / Cfg::BM) * p.ksplit + a.split) * ldp + n] = s;
+        if (want_t) tpart[((size_t)a.batch * mtiles + a.m0 / Cfg::BM) * ldp + n] = ts;
       }
     }
   }

@@ -70,7 +70,7 @@ struct gps_handle_s {
   // per-evaluation small state
   double *par = nullptr, *hyp = nullptr, *ell = nullptr, *meanw = nullptr, *noise_diag = nullptr;
   double *rnpart = nullptr, *rnorm = nullptr, *meanv = nullptr, *zvec = nullptr, *alpha = nullptr;
-  double *wdiag = nullptr, *rs = nullptr, *rs_part = nullptr, *colpart = nullptr, *qtu = nullptr, *d_nlml = nullptr, *d_logdet = nullptr,
+  double *wdiag = nullptr, *rs = nullptr, *rs_part = nullptr, *colpart = nullptr, *tpart = nullptr, *qtu = nullptr, *d_nlml = nullptr, *d_logdet = nullptr,
          *d_grad = nullptr;
   int* info = nullptr;
   int par_cap = 0;
@@ -193,7 +193,7 @@ void free_data(H* h) {
   dfree(h->cens_rank); dfree(h->d_ncens);
   dfree(h->par); dfree(h->hyp); dfree(h->ell); dfree(h->meanw); dfree(h->noise_diag);
   dfree(h->rnpart); dfree(h->rnorm); dfree(h->meanv); dfree(h->zvec); dfree(h->alpha);
-  dfree(h->wdiag); dfree(h->rs); dfree(h->rs_part); dfree(h->colpart); dfree(h->qtu); dfree(h->d_nlml); dfree(h->d_logdet);
+  dfree(h->wdiag); dfree(h->rs); dfree(h->rs_part); dfree(h->colpart); dfree(h->tpart); dfree(h->qtu); dfree(h->d_nlml); dfree(h->d_logdet);
   dfree(h->d_grad); dfree(h->info);
   dfree(h->K); dfree(h->Ky); dfree(h->L); dfree(h->Linv); dfree(h->Kinv); dfree(h->gsplit); dfree(h->U); dfree(h->XaugT); dfree(h->wsc);
   dfree(h->mL); dfree(h->mLinv); dfree(h->m_alpha); dfree(h->m_hyp); dfree(h->m_ell); dfree(h->m_meanw);
@@ -625,29 +625,30 @@ void enqueue_grad(H* h) {
   const int n = h->n, ld = h->ld;
   const long long sM = h->strideM;
   enqueue_kinv(h);
-  // M = (a a' - Kinv) o K  into the (now free) Ky buffer
+  // M = (a a' - Kinv) o K  into the (now free) Ky buffer, with its row sums as per-column-block partials
   const double* aw = h->alpha + (h->nrhs == 2 ? h->ld : 0);
-  wk_kernel<<<dim3(ceil_div(n, 32), ceil_div(n, 32), h->batch), dim3(32, 8), 0, h->st>>>(h->Kinv, h->K, n, ld, sM, aw,
-                                                                                       h->ld, h->Ky, h->wdiag);
+  const int nt32 = ceil_div(n, 32);
+  wk_kernel<<<dim3(nt32, nt32, h->batch), dim3(32, 8), 0, h->st>>>(h->Kinv, h->K, n, ld, sM, aw, h->ld, h->Ky, h->wdiag,
+                                                                   h->rs_part, nt32);
   LAUNCHED(h);
-  {  // (M Xaug) contracted with Xaug column by column; last column gives rowsum(M).  With few column tiles
-     // (small d) the K = n loop is split deterministically so that the launch fills the GPU.
+  rs_reduce_kernel<<<dim3(ceil_div(n, 256), h->batch), 256, 0, h->st>>>(h->rs_part, n, h->ld, nt32, h->rs);
+  LAUNCHED(h);
+  int mtiles = 1;
+  {  // (M Xaug) contracted with Xaug column by column in the epilogue, together with rowsum(M) . Xaug^2.  With few
+     // column tiles (small d) the K = n loop is split deterministically so that the launch fills the GPU.
     GemmParams p = gp(h->Ky, ld, sM, h->XaugT, h->ldxt, h->strideXT, n, h->d + 1, n);
     p.ksplit = h->grad_ksplit;
     EpiColDot e;
     e.X = h->Xaug; e.ldx = h->ldx; e.strideX = h->strideX; e.colpart = h->colpart; e.ldp = h->ldmu;
-    e.rs = h->rs_part; e.ldn = h->ld;
+    e.rs = h->rs; e.tpart = h->tpart; e.ldn = h->ld;
     const int tile = pick_nt_tile(h, p);
-    e.mtiles = ceil_div(n, tile_bm(h, tile));
+    e.mtiles = mtiles = ceil_div(n, tile_bm(h, tile));
     h->mtiles_grad = e.mtiles * h->grad_ksplit;
     gemm<false, false>(h, p, e);
   }
-  rs_reduce_kernel<<<dim3(ceil_div(n, 256), h->batch), 256, 0, h->st>>>(h->rs_part, n, h->ld, h->grad_ksplit, h->rs);
-  LAUNCHED(h);
-  grad_cols_kernel<<<dim3(ceil_div(h->d + 1, 8), h->batch), 256, 0, h->st>>>(h->Xaug, n, h->d, h->ldx, h->strideX,
-                                                                             h->colpart, h->ldmu, h->mtiles_grad, h->rs,
-                                                                             h->alpha, h->ld, h->qtu, h->ell, h->ldmu,
-                                                                             h->o.cov_form == 1 ? 1 : 0, h->par_cap, h->d_grad);
+  grad_cols_kernel<<<dim3(ceil_div(h->d + 1, 8), h->batch), 256, 0, h->st>>>(
+      h->Xaug, n, h->d, h->ldx, h->strideX, h->colpart, h->ldmu, mtiles, h->grad_ksplit, h->tpart, h->alpha, h->ld, h->qtu,
+      h->ell, h->ldmu, h->o.cov_form == 1 ? 1 : 0, h->o.mean_form == 1 ? 1 : 0, h->par_cap, h->d_grad);
   LAUNCHED(h);
   grad_finish_kernel<<<h->batch, 256, 0, h->st>>>(h->qtu, h->ldmu, n, h->d, h->p, h->o, h->wdiag, h->cens_rank, h->ld,
                                                    h->hyp, h->ell, h->ldmu, h->mu, h->ldmu, h->par_cap, h->d_grad);
@@ -681,9 +682,10 @@ void make_view(const H* h, int g0, int cnt, cudaStream_t st, H* v) {
   adv(v->y, g * h->ld); adv(v->events, g * h->ld); adv(v->noise_diag, g * h->ld); adv(v->rnorm, g * h->ld);
   adv(v->meanv, g * h->ld); adv(v->wdiag, g * h->ld); adv(v->rs, g * h->ld); adv(v->cens_rank, g * h->ld);
   adv(v->lsc, g * h->ldc);
-  adv(v->rnpart, g * h->ld * h->rn_ksplit); adv(v->rs_part, g * h->ld * h->grad_ksplit);
+  adv(v->rnpart, g * h->ld * h->rn_ksplit); adv(v->rs_part, g * h->ld * ceil_div(h->n, 32));
   adv(v->zvec, g * 2 * h->ld); adv(v->alpha, g * 2 * h->ld);
   adv(v->colpart, g * h->ldmu * ceil_div(h->n, 64) * h->grad_ksplit);
+  adv(v->tpart, g * h->ldmu * ceil_div(h->n, 64));
   adv(v->qtu, g * 3 * h->ldmu);
   adv(v->par, g * h->par_cap); adv(v->d_grad, g * h->par_cap);
   adv(v->hyp, g * 4);
@@ -1079,7 +1081,8 @@ int gps_set_data(gps_handle h, const double* X, int n, int d, const double* y, c
     h->grad_ksplit = ks < 1 ? 1 : (ks > maxks ? maxks : (ks > 16 ? 16 : ks));
   }
   CK(h, dalloc(&h->colpart, (size_t)h->ldmu * ceil_div(n, 64) * h->grad_ksplit * B));
-  CK(h, dalloc(&h->rs_part, vecB * h->grad_ksplit));
+  CK(h, dalloc(&h->rs_part, vecB * ceil_div(n, 32)));
+  CK(h, dalloc(&h->tpart, (size_t)h->ldmu * ceil_div(n, 64) * B));
   CK(h, dalloc(&h->qtu, (size_t)h->ldmu * 3 * B));
   CK(h, dalloc(&h->d_nlml, (size_t)B));
   CK(h, dalloc(&h->d_logdet, (size_t)B));

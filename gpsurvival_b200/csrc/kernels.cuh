@@ -655,7 +655,7 @@ __global__ void alpha_kernel(const double* __restrict__ Linv, int n, int ld, lon
 // ---------------------------------------------------------------------------------------
 __global__ void wk_kernel(const double* __restrict__ Kinv, const double* __restrict__ K, int n, int ld,
                           long long stride, const double* __restrict__ alpha_w, int ldn,
-                          double* __restrict__ M, double* __restrict__ wdiag) {
+                          double* __restrict__ M, double* __restrict__ wdiag, double* __restrict__ rs_part, int nt32) {
   __shared__ double tile[32][33];
   int ti = blockIdx.x, tj = blockIdx.y, b = blockIdx.z;
   if (ti < tj) return;
@@ -679,8 +679,26 @@ __global__ void wk_kernel(const double* __restrict__ Kinv, const double* __restr
     }
     tile[jl][threadIdx.x] = m;
   }
-  if (ti == tj) return;
   __syncthreads();
+  // partial row sums of M over this tile's 32 columns (fixed order): rs_part[b][tj][i]; the mirrored block
+  // gives rs_part[b][ti][j].  Every (row block, column block) pair is written exactly once.
+  double* rp = rs_part + (size_t)b * nt32 * ldn;
+  if (threadIdx.y == 0 && i < n) {
+    double sum = 0.0;
+#pragma unroll 8
+    for (int jl = 0; jl < 32; jl++) sum += tile[jl][threadIdx.x];
+    rp[(size_t)tj * ldn + i] = sum;
+  }
+  if (ti == tj) return;
+  if (threadIdx.y == 1) {
+    int jo = tj * 32 + threadIdx.x;
+    if (jo < n) {
+      double sum = 0.0;
+#pragma unroll 8
+      for (int il = 0; il < 32; il++) sum += tile[threadIdx.x][il];
+      rp[(size_t)ti * ldn + jo] = sum;
+    }
+  }
   // mirrored write: M[j, i] for the tile (tj, ti); coalesced along j
   int jo = tj * 32 + threadIdx.x;
   for (int rr = 0; rr < 4; rr++) {
@@ -693,32 +711,33 @@ __global__ void wk_kernel(const double* __restrict__ Kinv, const double* __restr
 // ---------------------------------------------------------------------------------------
 // Gradient assembly.  grad_cols: one warp per column k of Xaug (k = 0..d):
 //   q[k] = sum_mt colpart[mt][k]          (= sum_i Xaug[i,k] (M Xaug)[i,k];  q[d] = sum(M))
-//   t[k] = sum_i rs[i] * Xaug[i,k]^2
+//   t[k] = sum_mt tpart[mt][k]            (= sum_i rowsum(M)[i] * Xaug[i,k]^2, contracted in the GEMM epilogue)
 //   u[k] = sum_i Xaug[i,k] * alpha_c[i]   (mean-function gradients; u[d] = sum alpha_c)
 // grid (ceil((d+1)/8), batch), block 256.
 // ---------------------------------------------------------------------------------------
 __global__ void grad_cols_kernel(const double* __restrict__ X, int n, int d, int ldx, long long strideX,
-                                 const double* __restrict__ colpart, int ldp, int mtiles,
-                                 const double* __restrict__ rs, const double* __restrict__ alpha, int ldn,
+                                 const double* __restrict__ colpart, int ldp, int mtiles, int ksplit,
+                                 const double* __restrict__ tpart, const double* __restrict__ alpha, int ldn,
                                  double* __restrict__ qtu, const double* __restrict__ ell, int ldell, int ard,
-                                 int len, double* __restrict__ grad) {
-  // rs here is the REDUCED rowsum(M) (rs_reduce_kernel), mtiles counts the split-K slices too
+                                 int linear, int len, double* __restrict__ grad) {
+  // colpart holds mtiles * ksplit slices per fit (m-tile major), tpart mtiles slices (written by split 0)
   int k = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31, b = blockIdx.y;
   if (k > d) return;
-  const double* x = X + (size_t)b * strideX + (size_t)k * ldx;
-  const double* r = rs + (size_t)b * ldn;
-  const double* ac = alpha + (size_t)b * 2 * ldn;   // rhs 0 = centred targets
-  double t = 0.0, u = 0.0;
-  for (int i = lane; i < n; i += 32) {
-    double xv = x[i];
-    t += r[i] * xv * xv;
-    u += xv * ac[i];
+  double u = 0.0;
+  if (linear) {   // mean-function gradients only (MeanFunc.R 'Linear')
+    const double* x = X + (size_t)b * strideX + (size_t)k * ldx;
+    const double* ac = alpha + (size_t)b * 2 * ldn;   // rhs 0 = centred targets
+    for (int i = lane; i < n; i += 32) u += x[i] * ac[i];
+    u = warp_sum(u);
   }
+  // fixed-order sums of the per-tile partials, spread over the lanes then combined in lane order
+  double q = 0.0, t = 0.0;
+  const int nq = mtiles * ksplit;
+  for (int mt = lane; mt < nq; mt += 32) q += colpart[((size_t)b * nq + mt) * ldp + k];
+  for (int mt = lane; mt < mtiles; mt += 32) t += tpart[((size_t)b * mtiles + mt) * ldp + k];
+  q = warp_sum(q);
   t = warp_sum(t);
-  u = warp_sum(u);
   if (lane == 0) {
-    double q = 0.0;
-    for (int mt = 0; mt < mtiles; mt++) q += colpart[((size_t)b * mtiles + mt) * ldp + k];
     double* o = qtu + (size_t)b * 3 * ldp;
     o[k] = q;
     o[ldp + k] = t;
