@@ -5,7 +5,7 @@
     python bench.py --gpus N --steps K --warmup W            # our CUDA path
     python bench.py --impl reference --steps K --warmup W    # the reference algorithm on host cores
 
-One "step" = one pass of the hot path over one BATCH of independent fits: `--batch` (default 32)
+One "step" = one pass of the hot path over one BATCH of independent fits: `--batch` (default 64)
 C2-shaped GPS3/ARD fits (distinct synthetic data sets and start hyper-parameters — restarts /
 CV folds / repetitions, which north_star batches per GPU) each get one evaluation of
 ForOptimisationLog + OptimisationGradientLog (NLML and its gradient w.r.t. all 22
@@ -84,12 +84,14 @@ def config_dict(B, world, n, d, nhyp):
 def measured_traffic(B):
     """DRAM bytes of one step from the committed ncu capture of the same workload (bench.py cannot run
     under ncu itself); None when no capture exists for this batch size."""
-    path = os.path.join(ROOT, "profiles", "r1c_traffic_c2_batch32.json")
-    try:
-        t = json.load(open(path))
-        return float(t["traffic_bytes_per_step"]) if int(t["fits_per_step"]) == int(B) else None
-    except (OSError, ValueError, KeyError):
-        return None
+    for name in ("r1d_traffic_c2_batch64.json", "r1c_traffic_c2_batch32.json"):
+        try:
+            t = json.load(open(os.path.join(ROOT, "profiles", name)))
+            if int(t["fits_per_step"]) == int(B):
+                return float(t["traffic_bytes_per_step"]), name
+        except (OSError, ValueError, KeyError):
+            continue
+    return None, None
 
 
 def algorithmic_flops(n, d, ard=True):
@@ -297,6 +299,19 @@ def run_gpu(args):
         stages = fit.time_stages()
         gemm_ms = fit.bench_gemm(8192, 8192, 8192, 3)
         achieved = B * flops / (ms_per_step * 1e-3) / 1e12
+        traffic, traffic_file = measured_traffic(B)
+        n3 = float(n) ** 3 / 3.0
+
+        def tf(fl, ms):
+            return B * fl / (ms * 1e-3) / 1e12 if ms > 0 else None
+        # per-stage algorithmic rates of the same step (CUDA events between the stages, gps_time_stages)
+        stage_rates = {
+            "gram (dmma + covariance epilogue; n^2 d)": tf(float(n) * n * d, stages[0]),
+            "cholesky (panel_kernel + dmma trailing updates; n^3/3)": tf(n3, stages[1]),
+            "triangular inverse (dmma, U and Linv; n^3/3)": tf(n3, stages[2]),
+            "Kinv = U U' (dmma_ws_kernel, the longest launch; n^3/3)": tf(n3, stages[3]),
+            "W o K + gradient contraction (2 n^2 (d+1))": tf(2.0 * n * n * (d + 1), stages[4]),
+        }
         # a lone fit (latency-bound): same workload, batch of one
         one = gp.Fit(local)
         one.set_options(CFG.cov_form, "Zero", CFG.noise_corr, "intended")
@@ -348,9 +363,13 @@ def run_gpu(args):
             "gpu_launches": int(launches),
             "clocks": clocks,
             "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s",
-                         "frac": achieved / peak_tf if peak_tf else None, "traffic": measured_traffic(B),
-                         "traffic_source": "profiles/r1c_traffic_c2_batch32.json: ncu dram__bytes_read.sum + dram__bytes_write.sum "
-                                           "summed over the 85 launches of one step (bytes)",
+                         "frac": achieved / peak_tf if peak_tf else None, "traffic": traffic,
+                         "traffic_source": ("profiles/%s: ncu dram__bytes_read.sum + dram__bytes_write.sum summed over "
+                                            "the launches of one step (bytes)" % traffic_file) if traffic_file else None,
+                         "stage_tflops": stage_rates,
+                         "dmma_issue_peak": {"tflops": 37.1, "frac": achieved / 37.1,
+                                             "source": "register-only mma.sync.m8n8k4.f64 issue rate measured on B200 "
+                                                       "(lab/dmma_lab.cu, profiles/r1d_dmma_lab.log); cublasDgemm reaches 35.9"},
                          "kernel": "evaluation graph (1 launch = %d NLML+gradient evaluations, %d kernel nodes)"
                                    % (B, launches // max(K, 1)),
                          "algorithmic_flops_per_launch": B * flops,
