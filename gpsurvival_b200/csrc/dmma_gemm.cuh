@@ -362,20 +362,27 @@ struct EpiCov {
 #pragma unroll
       for (int i = 0; i < Cfg::FM; i++) {
         int m = a.m_base + 8 * i;
+        if (m >= p.M) continue;
+        double kk[2], ky[2];
 #pragma unroll
         for (int e = 0; e < 2; e++) {
           int mm = m + e;
-          if (mm >= p.M) continue;
-          double r2 = fmax(0.0, nA[mm] + sn - 2.0 * a.v[i][j][e]);
-          double k = cov_kernel_fn(kind, r2, s2);
-          double ky = k;
+          double r2 = (mm < p.M) ? fmax(0.0, nA[mm] + sn - 2.0 * a.v[i][j][e]) : 0.0;
+          kk[e] = cov_kernel_fn(kind, r2, s2);
+          ky[e] = kk[e];
           if (sym && mm == n) {
-            k = s2;
-            ky = nd ? s2 + nd[mm] : s2;
+            kk[e] = s2;
+            ky[e] = nd ? s2 + nd[mm] : s2;
           }
-          size_t off = (size_t)mm + (size_t)n * ldk;
-          if (Kb) Kb[off] = k;
-          if (Kyb) Kyb[off] = ky;
+        }
+        // the thread's two values are consecutive rows of one column: one 16-byte store per matrix
+        size_t off = (size_t)m + (size_t)n * ldk;
+        if (m + 1 < p.M) {
+          if (Kb) *reinterpret_cast<double2*>(Kb + off) = make_double2(kk[0], kk[1]);
+          if (Kyb) *reinterpret_cast<double2*>(Kyb + off) = make_double2(ky[0], ky[1]);
+        } else {
+          if (Kb) Kb[off] = kk[0];
+          if (Kyb) Kyb[off] = ky[0];
         }
       }
     }
