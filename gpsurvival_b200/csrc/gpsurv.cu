@@ -81,6 +81,8 @@ struct gps_handle_s {
   double* wsc = nullptr;         // [batch][ldmu] k-weights 1/ell_k^2 of the weighted Gram product (hyp_prep_kernel)
   int num_sms = 148;
   int ws_enabled = 1;            // GPS_WS=0: never use the warp-specialised 128 x 128 kernel
+  int nbig = 256;                // GPS_NBIG: diagonal block of the two-level Cholesky (64 = one-level recursion)
+  bool nbig_forced = false;
   int ws_min_tiles = 296;        // GPS_WS_MIN: minimum number of 128 x 128 tiles in a launch
   int ws_min_n = 3072;           // GPS_WS_MIN_N: smallest problem (rows of the covariance) that uses it.  Measured on
                                  // B200: its tiles run at 34.5 TF/s against 30 for the 64 x 64 kernel, but 128-wide tiles
@@ -457,20 +459,21 @@ void launch_panel(H* h, int e0, int nb, int M, long long* dbg) {
 // ---------------------------------------------------------------------------------------
 // Recursive blocked Cholesky over block columns [j0, j1) (units of NB).  Precondition: all
 // updates from columns < j0*NB are already applied to Ky[:, j0*NB : j1*NB].  Rows run to
-// naug, i.e. the appended right-hand-side rows are carried along (forward solve for free).
+// row_end: naug in the one-level scheme (the appended right-hand-side rows are carried along: forward
+// solve for free), the end of the diagonal block in the two-level scheme (potrf_big).
 // ---------------------------------------------------------------------------------------
-void potrf_range(H* h, int j0, int j1) {
+void potrf_range(H* h, int j0, int j1, int row_end) {
   const int ld = h->ld;
   const long long sM = h->strideM;
   if (j1 - j0 == 1) {
     int e0 = j0 * NB, nb = (h->ne - e0 < NB) ? h->ne - e0 : NB;
     // fused: L11 = chol(A11), X11 = L11^-1, L[e1:, e0:e1] = Ky[e1:, e0:e1] * X11'
-    int e1 = e0 + nb, M = h->naug - e1;
+    int e1 = e0 + nb, M = row_end - e1;
     launch_panel(h, e0, nb, M, nullptr);
     return;
   }
   int mid = j0 + (j1 - j0 + 1) / 2;
-  potrf_range(h, j0, mid);
+  potrf_range(h, j0, mid, row_end);
   int r0 = mid * NB, c0 = j0 * NB, c1 = (j1 * NB < h->ne) ? j1 * NB : h->ne;
   // Ky[r0:naug, r0:c1] -= L[r0:naug, c0:r0] * L[r0:c1, c0:r0]'
   // Optional look-ahead (GPS_LOOKAHEAD=1, default off): the next panel only needs block column r0 of this
@@ -481,24 +484,24 @@ void potrf_range(H* h, int j0, int j1) {
   // latency of the graph cost more than the 18 us panel they hide.
   const int K = r0 - c0, ncols = c1 - r0;
   if (h->lookahead && ncols > NB) {
-    GemmParams pa = gp(h->L + r0 + (size_t)c0 * ld, ld, sM, h->L + r0 + (size_t)c0 * ld, ld, sM, h->naug - r0, NB, K);
+    GemmParams pa = gp(h->L + r0 + (size_t)c0 * ld, ld, sM, h->L + r0 + (size_t)c0 * ld, ld, sM, row_end - r0, NB, K);
     pa.lower = 1;
     gemm<false, false>(h, pa, plain(h->Ky + r0 + (size_t)r0 * ld, ld, sM, -1.0, 1.0));
     CKV(h, cudaEventRecord(h->ev_fork, h->st));
     CKV(h, cudaStreamWaitEvent(h->st2, h->ev_fork, 0));
     const int r1 = r0 + NB;
-    GemmParams pb = gp(h->L + r1 + (size_t)c0 * ld, ld, sM, h->L + r1 + (size_t)c0 * ld, ld, sM, h->naug - r1, c1 - r1, K);
+    GemmParams pb = gp(h->L + r1 + (size_t)c0 * ld, ld, sM, h->L + r1 + (size_t)c0 * ld, ld, sM, row_end - r1, c1 - r1, K);
     pb.lower = 1;
     h->cur = h->st2;
     gemm<false, false>(h, pb, plain(h->Ky + r1 + (size_t)r1 * ld, ld, sM, -1.0, 1.0));
     h->cur = h->st;
     h->pending_join = true;
   } else {
-    GemmParams p = gp(h->L + r0 + (size_t)c0 * ld, ld, sM, h->L + r0 + (size_t)c0 * ld, ld, sM, h->naug - r0, ncols, K);
+    GemmParams p = gp(h->L + r0 + (size_t)c0 * ld, ld, sM, h->L + r0 + (size_t)c0 * ld, ld, sM, row_end - r0, ncols, K);
     p.lower = 1;
     gemm<false, false>(h, p, plain(h->Ky + r0 + (size_t)r0 * ld, ld, sM, -1.0, 1.0));
   }
-  potrf_range(h, mid, j1);
+  potrf_range(h, mid, j1, row_end);
 }
 
 // Inverse of the lower-triangular factor, kept in both orientations: Linv = L^-1 (lower) and U = Linv'
@@ -511,15 +514,17 @@ void potrf_range(H* h, int j0, int j1) {
 // makes every product an "NT" GEMM — each operand row is a long contiguous run in memory, which is what the
 // bulk-copy producer of the warp-specialised kernel streams best — and Kinv = U U' likewise.
 // All nodes of a level are independent and share the two launches.  Kinv is the temporary for T.
-void trtri_levels(H* h) {
-  const int ld = h->ld, ne = h->ne;
+// Levels bs = bs_from, 2 bs_from, ... (< bs_to) of that merge tree on the diagonal sub-matrix [lo, hi).
+void trtri_range(H* h, int lo, int hi, int bs_from, int bs_to) {
+  const int ld = h->ld, ne = hi - lo;
   const long long sM = h->strideM;
-  for (int bs = NB; bs < ne; bs *= 2) {
+  const size_t base = (size_t)lo * (1 + (size_t)ld);
+  for (int bs = bs_from; bs < ne && bs < bs_to; bs *= 2) {
     const int nodes = ceil_div(ne, 2 * bs);
     const long long nstride = (long long)2 * bs * (1 + (long long)ld);
-    const size_t off12 = (size_t)bs * ld, off21 = (size_t)bs, off22 = (size_t)bs + (size_t)bs * ld;
+    const size_t off12 = base + (size_t)bs * ld, off21 = base + (size_t)bs, off22 = base + (size_t)bs + (size_t)bs * ld;
     {  // T = U11 * L21'
-      GemmParams p = gp(h->U, ld, sM, h->L + off21, ld, sM, bs, bs, bs);
+      GemmParams p = gp(h->U + base, ld, sM, h->L + off21, ld, sM, bs, bs, bs);
       p.klo_m = 1;
       p.nodes = nodes; p.nodeStrideA = nstride; p.nodeStrideB = nstride;
       p.clip_total = ne - bs; p.clip_step = 2 * bs; p.k_eq_m = 0; p.clip_n = 1;
@@ -538,6 +543,48 @@ void trtri_levels(H* h) {
       gemm<false, false>(h, p, e);
     }
   }
+}
+
+// Two-level Cholesky (h->nbig > NB): the one-level recursion drags every panel solve and every K = 64 / 128
+// update over ALL rows below the diagonal — short-k products that run at a third of the long-k rate.  Here the
+// 64-column recursion (panel kernels, K <= 128 updates) is confined to the nbig x nbig DIAGONAL block; that
+// block's inverse is finished right away (the first levels of the triangular-inverse tree, needed later
+// anyway), and the rows below are solved by ONE product with K = nbig:  L21 = A21 * L11^-T = A21 * U11, an
+// "NT" GEMM reading Linv11 transposed.  Trailing updates then start at K = nbig.
+void potrf_big(H* h, int J0, int J1) {
+  const int ld = h->ld, nbig = h->nbig;
+  const long long sM = h->strideM;
+  if (J1 - J0 == 1) {
+    const int c0 = J0 * nbig, c1 = std::min(c0 + nbig, h->ne);
+    potrf_range(h, c0 / NB, ceil_div(c1, NB), c1);
+    trtri_range(h, c0, c1, NB, nbig);
+    const int M = h->naug - c1;
+    if (M > 0) {
+      GemmParams p = gp(h->Ky + c1 + (size_t)c0 * ld, ld, sM, h->Linv + c0 + (size_t)c0 * ld, ld, sM, M, c1 - c0, c1 - c0);
+      p.khi_n = 1;   // Linv11 lower: (L11^-T)[k, n] = Linv11[n, k] = 0 for k > n
+      gemm<false, false>(h, p, plain(h->L + c1 + (size_t)c0 * ld, ld, sM, 1.0, 0.0));
+    }
+    return;
+  }
+  const int mid = J0 + (J1 - J0 + 1) / 2;
+  potrf_big(h, J0, mid);
+  const int r0 = mid * nbig, c0 = J0 * nbig, c1 = std::min(J1 * nbig, h->ne);
+  GemmParams p = gp(h->L + r0 + (size_t)c0 * ld, ld, sM, h->L + r0 + (size_t)c0 * ld, ld, sM, h->naug - r0, c1 - r0, r0 - c0);
+  p.lower = 1;
+  gemm<false, false>(h, p, plain(h->Ky + r0 + (size_t)r0 * ld, ld, sM, -1.0, 1.0));
+  potrf_big(h, mid, J1);
+}
+
+// Two-level only for batches: measured on B200, C2 x 64 fits 22.31 -> 22.00 ms (Cholesky stage 9.1 -> 8.1 ms), but a
+// lone fit gets SLOWER (C2 1.84 -> 2.22 ms, n = 8192 Cholesky 10.8 -> 12.5 ms): its launches are latency-bound and
+// the scheme trades wide short-k products for more, smaller launches.  GPS_NBIG=64 turns it off everywhere.
+inline bool two_level(const H* h) { return h->nbig > NB && h->ne > h->nbig && (h->batch >= 8 || h->nbig_forced); }
+void enqueue_potrf(H* h) {   // whole factorisation (+ the inverse levels below nbig in the two-level scheme)
+  if (two_level(h)) potrf_big(h, 0, ceil_div(h->ne, h->nbig));
+  else potrf_range(h, 0, ceil_div(h->ne, NB), h->naug);
+}
+void trtri_levels(H* h) {    // what is left of the triangular inverse after enqueue_potrf
+  trtri_range(h, 0, h->ne, two_level(h) ? h->nbig : NB, 1 << 30);
 }
 
 // ---------------------------------------------------------------------------------------
@@ -601,7 +648,7 @@ void enqueue_factor(H* h) {
       h->Xaug, n, h->ne, h->d, h->ldx, h->strideX, h->meanw, h->ldmu, h->o.mean_form == 1, h->y, h->ld, h->meanv, h->Ky,
       h->ld, h->strideM, h->nrhs);
   LAUNCHED(h);
-  potrf_range(h, 0, ceil_div(h->ne, NB));
+  enqueue_potrf(h);
   nlml_finish_kernel<<<h->batch, 256, 0, h->st>>>(h->L, n, h->ne, h->ld, h->strideM, h->nrhs, h->zvec, h->ld, h->d_nlml,
                                                    h->d_logdet);
   LAUNCHED(h);
@@ -919,6 +966,13 @@ int gps_create_batch(int device, int batch, gps_handle* out) {
   if (const char* ev = getenv("GPS_WS")) h->ws_enabled = atoi(ev) != 0;
   if (const char* ev = getenv("GPS_WS_MIN")) h->ws_min_tiles = atoi(ev);
   if (const char* ev = getenv("GPS_WS_MIN_N")) h->ws_min_n = atoi(ev);
+  if (const char* ev = getenv("GPS_NBIG")) {
+    const int v = atoi(ev);
+    if (v == 64 || v == 128 || v == 256 || v == 512) {
+      h->nbig = v;
+      h->nbig_forced = true;
+    }
+  }
   h->num_sms = prop.multiProcessorCount;
   h->device = device;
   h->batch = batch;
@@ -1771,7 +1825,7 @@ int gps_time_stages(gps_handle h, double* ms_out) {
       h->Xaug, n, h->ne, h->d, h->ldx, h->strideX, h->meanw, h->ldmu, h->o.mean_form == 1, h->y, h->ld, h->meanv, h->Ky,
       h->ld, h->strideM, h->nrhs);
   CK(h, cudaEventRecord(ev[1], h->st));
-  potrf_range(h, 0, ceil_div(h->ne, NB));
+  enqueue_potrf(h);
   nlml_finish_kernel<<<h->batch, 256, 0, h->st>>>(h->L, n, h->ne, h->ld, h->strideM, h->nrhs, h->zvec, h->ld, h->d_nlml,
                                                    h->d_logdet);
   CK(h, cudaEventRecord(ev[2], h->st));

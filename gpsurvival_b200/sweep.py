@@ -28,6 +28,8 @@ def main(argv=None):
     ap.add_argument("--method", default="BFGS", choices=["BFGS", "Nelder-Mead"])
     ap.add_argument("--rounds", type=int, default=6)
     ap.add_argument("--distinct", type=int, default=4, help="distinct synthetic data sets generated per rank")
+    ap.add_argument("--driver", default="c", choices=["c", "python"],
+                    help="c: whole fits behind the C ABI (gps_fit_batch); python: the lock-step host driver (batchfit)")
     args = ap.parse_args(argv)
 
     import torch
@@ -70,10 +72,23 @@ def main(argv=None):
             fit = gp.Fit(local, batch=len(idx))
         probs = [base[i % len(base)] for i in idx]
         starts = [synth.start_log_hyp(d, cfg.cov_form, rng) for _ in idx]
-        res = batchfit.apply_gp_batch(probs, dict(params, logHypStart=starts), fit=fit)
-        for i, r in zip(idx, res):
-            results[i] = {"objective": r["objective"], "logMarLik": r["logMarLik"], "rounds": r["count"],
-                          "pred_mean": float(np.mean(r["funcMeanPred"]))}
+        if args.driver == "python":
+            res = batchfit.apply_gp_batch(probs, dict(params, logHypStart=starts), fit=fit)
+            for i, r in zip(idx, res):
+                results[i] = {"objective": r["objective"], "logMarLik": r["logMarLik"], "rounds": r["count"],
+                              "pred_mean": float(np.mean(r["funcMeanPred"]))}
+        else:
+            fit.set_options(cfg.cov_form, "Zero", cfg.noise_corr, "intended")
+            X = np.stack([p["trainingData"] for p in probs])
+            y = np.stack([np.log(p["trainingTargets"]) for p in probs])
+            ev = np.stack([p["events"] for p in probs])
+            Xt = np.stack([p["testData"] for p in probs])
+            par0 = np.stack([gp._flatten(s0, d, "Zero", cfg.noise_corr, None) for s0 in starts])
+            rr = fit.fit_batch(X, y, ev, par0, Xt, method=args.method, maxit=10, tolerance=1e300, max_count=args.rounds,
+                               survival=True)
+            for k, i in enumerate(idx):
+                results[i] = {"objective": float(rr["objective"][k]), "logMarLik": float(rr["logMarLik"][k]),
+                              "rounds": int(rr["count"][k]), "pred_mean": float(np.mean(rr["funcMeanPred"][k]))}
     torch.cuda.synchronize(local)
     mine_s = time.perf_counter() - t0
     barrier()
@@ -89,7 +104,8 @@ def main(argv=None):
                           "fits": args.fits, "seconds": mine_s, "seconds_incl_gather": total_s,
                           "config": {"workload": f"{args.config}: n={cfg.n} d={cfg.d} c={cfg.c} {cfg.cov_form} "
                                                  f"{cfg.noise_corr}; {args.rounds} GPS rounds x optim({args.method}, maxit 10) "
-                                                 f"+ test/train predictions; {args.batch} fits in lock-step per GPU",
+                                                 f"+ test/train predictions; {args.batch} fits in lock-step per GPU; "
+                                                 f"driver: {'gps_fit_batch (C ABI)' if args.driver == 'c' else 'batchfit (Python)'}",
                                      "partition": f"{args.fits} independent fits over {world} GPUs, no collective"},
                           "mean_objective": float(np.mean([v["objective"] for v in full.values()]))}), flush=True)
     if fit is not None:
