@@ -330,6 +330,17 @@ __device__ __forceinline__ double cov_kernel_fn(int kind, double r2, double s2) 
   return s2 * (1.0 + a + (5.0 * (r * r)) / 3.0) * exp(-a);
 }
 
+// Kd = -sf2 f'(r)/r for K = sf2 f(r): dK_ij / dlog(ell_k) = Kd_ij (x_ik - x_jk)^2 / ell_k^2.  SqExp: Kd = K (never
+// asked for).  Matern gradients are derived here — the reference has none (OptimisationGradientLog.R:6).
+// At r = 0 the distance factor vanishes; nu = 1/2 (1/r) is defined as 0 there.
+__device__ __forceinline__ double cov_deriv_fn(int kind, double r2, double s2) {
+  if (kind == 0) return s2 * exp(-0.5 * r2);
+  const double r = sqrt(r2);
+  if (kind == 1) return r > 0.0 ? s2 * exp(-r) / r : 0.0;
+  if (kind == 3) return 3.0 * s2 * exp(-1.7320508075688772 * r);
+  return (5.0 / 3.0) * s2 * (1.0 + 2.23606797749979 * r) * exp(-2.23606797749979 * r);
+}
+
 // Covariance epilogue (CovFunc.R:33-39 on the Gram form):
 //   r2 = max(0, sA[m] + sB[n] - 2*G[m,n]);  K = sf2 * exp(-r2/2);
 // symmetric case (sym != 0): the diagonal is written as exactly sf2 and Ky additionally gets
@@ -342,6 +353,7 @@ struct EpiCov {
   const double* noise_diag;   // [batch][ldn] or nullptr
   double* Kout;            // noise-free covariance (may be nullptr)
   double* Kyout;           // covariance + noise on the diagonal (may be nullptr)
+  double* Kdout;           // derivative factor Kd (Matern gradients; usually nullptr)
   int ldk, ldn, ldnB;      // ldn / ldnB: per-batch strides of normA (and noise_diag) / normB
   long long strideK;
   int sym;
@@ -354,6 +366,7 @@ struct EpiCov {
     const double* nd = noise_diag ? noise_diag + (size_t)a.batch * ldn : nullptr;
     double* Kb = Kout ? Kout + (size_t)a.batch * strideK : nullptr;
     double* Kyb = Kyout ? Kyout + (size_t)a.batch * strideK : nullptr;
+    double* Kdb = Kdout ? Kdout + (size_t)a.batch * strideK : nullptr;
 #pragma unroll
     for (int j = 0; j < Cfg::FN; j++) {
       int n = a.n_base + 8 * j;
@@ -363,13 +376,15 @@ struct EpiCov {
       for (int i = 0; i < Cfg::FM; i++) {
         int m = a.m_base + 8 * i;
         if (m >= p.M) continue;
-        double kk[2], ky[2];
+        double kk[2], ky[2], kd[2] = {0.0, 0.0};
 #pragma unroll
         for (int e = 0; e < 2; e++) {
           int mm = m + e;
           double r2 = (mm < p.M) ? fmax(0.0, nA[mm] + sn - 2.0 * a.v[i][j][e]) : 0.0;
+          if (sym && mm == n) r2 = 0.0;
           kk[e] = cov_kernel_fn(kind, r2, s2);
           ky[e] = kk[e];
+          if (Kdb) kd[e] = cov_deriv_fn(kind, r2, s2);
           if (sym && mm == n) {
             kk[e] = s2;
             ky[e] = nd ? s2 + nd[mm] : s2;
@@ -380,9 +395,11 @@ struct EpiCov {
         if (m + 1 < p.M) {
           if (Kb) *reinterpret_cast<double2*>(Kb + off) = make_double2(kk[0], kk[1]);
           if (Kyb) *reinterpret_cast<double2*>(Kyb + off) = make_double2(ky[0], ky[1]);
+          if (Kdb) *reinterpret_cast<double2*>(Kdb + off) = make_double2(kd[0], kd[1]);
         } else {
           if (Kb) Kb[off] = kk[0];
           if (Kyb) Kyb[off] = ky[0];
+          if (Kdb) Kdb[off] = kd[0];
         }
       }
     }

@@ -78,6 +78,7 @@ struct gps_handle_s {
   // matrices (work set)
   double *K = nullptr, *Ky = nullptr, *L = nullptr, *Linv = nullptr, *Kinv = nullptr, *gsplit = nullptr;
   double* U = nullptr;           // U = Linv' (upper triangular), built next to Linv by trtri_levels
+  double *Kd = nullptr, *rsK_part = nullptr, *rsK = nullptr;   // Matern gradients: derivative factor, row sums of W o K
   double* wsc = nullptr;         // [batch][ldmu] k-weights 1/ell_k^2 of the weighted Gram product (hyp_prep_kernel)
   int num_sms = 148;
   int ws_enabled = 1;            // GPS_WS=0: never use the warp-specialised 128 x 128 kernel
@@ -197,7 +198,7 @@ void free_data(H* h) {
   dfree(h->rnpart); dfree(h->rnorm); dfree(h->meanv); dfree(h->zvec); dfree(h->alpha);
   dfree(h->wdiag); dfree(h->rs); dfree(h->rs_part); dfree(h->colpart); dfree(h->tpart); dfree(h->qtu); dfree(h->d_nlml); dfree(h->d_logdet);
   dfree(h->d_grad); dfree(h->info);
-  dfree(h->K); dfree(h->Ky); dfree(h->L); dfree(h->Linv); dfree(h->Kinv); dfree(h->gsplit); dfree(h->U); dfree(h->XaugT); dfree(h->wsc);
+  dfree(h->K); dfree(h->Ky); dfree(h->L); dfree(h->Linv); dfree(h->Kinv); dfree(h->gsplit); dfree(h->U); dfree(h->XaugT); dfree(h->wsc); dfree(h->Kd); dfree(h->rsK_part); dfree(h->rsK);
   dfree(h->mL); dfree(h->mLinv); dfree(h->m_alpha); dfree(h->m_hyp); dfree(h->m_ell); dfree(h->m_meanw);
   dfree(h->Xs); dfree(h->Zs); dfree(h->snorm); dfree(h->snpart); dfree(h->Ks); dfree(h->V); dfree(h->mstar);
   dfree(h->pout);
@@ -216,6 +217,18 @@ void drop_graphs(H* h) {
   if (h->g_full) cudaGraphExecDestroy(h->g_full);
   h->g_factor = h->g_inverse = h->g_grad = h->g_full = nullptr;
   h->warm_factor = h->warm_inverse = h->warm_grad = h->warm_full = 0;
+}
+
+// Buffers only the Matern gradient needs (derivative factor Kd, row sums of W o K): allocated on first need.
+int ensure_matern_buffers(H* h) {
+  if (h->o.cov_form < GPS_COV_MATERN1 || h->Kd || h->n == 0) return GPS_OK;
+  g_alloc_stream = h->st;
+  const size_t vecB = (size_t)h->ld * h->batch;
+  CK(h, dalloc(&h->Kd, (size_t)h->strideM * h->batch));
+  CK(h, dalloc(&h->rsK_part, vecB * ceil_div(h->n, 32)));
+  CK(h, dalloc(&h->rsK, vecB));
+  CK(h, cudaStreamSynchronize(h->st));
+  return GPS_OK;
 }
 
 int expected_len(const H* h) {
@@ -404,12 +417,12 @@ inline bool cov_form_ok(int f) { return f >= GPS_COV_SQEXP && f <= GPS_COV_MATER
 void enqueue_cov(H* h, const double* Za, int n1, int lda, long long sA, const double* normA, const double* Zb,
                  int n2, int ldb, long long sB, const double* normB, int d, const double* hyp,
                  const double* noise_diag, double* Kout, double* Kyout, int ldk, long long sK, bool sym, int ksplit,
-                 int kind) {
+                 int kind, double* Kdout = nullptr) {
   GemmParams p = gp(Za, lda, sA, Zb, ldb, sB, n1, n2, d);
   p.lower = sym ? 1 : 0;
   if (ksplit <= 1) {
     EpiCov e;
-    e.normA = normA; e.normB = normB; e.hyp = hyp; e.noise_diag = noise_diag; e.Kout = Kout; e.Kyout = Kyout;
+    e.normA = normA; e.normB = normB; e.hyp = hyp; e.noise_diag = noise_diag; e.Kout = Kout; e.Kyout = Kyout; e.Kdout = Kdout;
     e.ldk = ldk; e.ldn = h->ld; e.ldnB = h->ld; e.strideK = sK; e.sym = sym ? 1 : 0; e.kind = kind;
     gemm<false, false>(h, p, e);
   } else {
@@ -419,7 +432,7 @@ void enqueue_cov(H* h, const double* Za, int n1, int lda, long long sA, const do
     gemm<false, false>(h, p, e);
     dim3 grid(ceil_div(n1, 32), ceil_div(n2, 8), h->batch), block(32, 8);
     cov_finish_kernel<<<grid, block, 0, h->st>>>(h->gsplit, n1, n2, ldk, sK, (long long)ksplit * sK, ksplit, normA,
-                                                  normB, h->ld, hyp, noise_diag, Kout, Kyout, ldk, sK, sym ? 1 : 0, kind);
+                                                  normB, h->ld, hyp, noise_diag, Kout, Kyout, ldk, sK, sym ? 1 : 0, kind, Kdout);
     LAUNCHED(h);
   }
 }
@@ -614,6 +627,7 @@ void enqueue_gram_train(H* h) {
   p.lower = 1;
   p.ksplit = std::max(1, h->gram_ksplit);
   const bool as_written = (h->o.ard_mode == 1 && h->p > 1);
+  double* kd = (h->o.cov_form >= GPS_COV_MATERN1) ? h->Kd : nullptr;   // derivative factor, Matern gradients only
   if (h->wsc && h->gsplit && !as_written && pick_nt_tile(h, p) != 0) {
     const int ks = p.ksplit;
     p.kscale = h->wsc;
@@ -627,13 +641,13 @@ void enqueue_gram_train(H* h) {
     dim3 grid(ceil_div(n, 32), ceil_div(n, 8), h->batch), block(32, 8);
     cov_finish_kernel<<<grid, block, 0, h->st>>>(h->gsplit, n, n, h->ld, h->strideM, (long long)ks * h->strideM, ks, h->rnorm,
                                                   h->rnorm, h->ld, h->hyp, h->noise_diag, h->K, h->Ky, h->ld, h->strideM, 1,
-                                                  cov_kind(h->o.cov_form));
+                                                  cov_kind(h->o.cov_form), kd);
     LAUNCHED(h);
     return;
   }
   enqueue_prescale_train(h, h->ell, 1);
   enqueue_cov(h, h->Z, n, h->ldx, h->strideX, h->rnorm, h->Z, n, h->ldx, h->strideX, h->rnorm, h->d, h->hyp,
-              h->noise_diag, h->K, h->Ky, h->ld, h->strideM, true, h->gram_ksplit, cov_kind(h->o.cov_form));
+              h->noise_diag, h->K, h->Ky, h->ld, h->strideM, true, h->gram_ksplit, cov_kind(h->o.cov_form), kd);
 }
 
 void enqueue_factor(H* h) {
@@ -675,9 +689,14 @@ void enqueue_grad(H* h) {
   // M = (a a' - Kinv) o K  into the (now free) Ky buffer, with its row sums as per-column-block partials
   const double* aw = h->alpha + (h->nrhs == 2 ? h->ld : 0);
   const int nt32 = ceil_div(n, 32);
+  const bool matern = (h->o.cov_form >= GPS_COV_MATERN1);
   wk_kernel<<<dim3(nt32, nt32, h->batch), dim3(32, 8), 0, h->st>>>(h->Kinv, h->K, n, ld, sM, aw, h->ld, h->Ky, h->wdiag,
-                                                                   h->rs_part, nt32);
+                                                                   h->rs_part, nt32, matern ? h->Kd : nullptr, h->rsK_part);
   LAUNCHED(h);
+  if (matern) {
+    rs_reduce_kernel<<<dim3(ceil_div(n, 256), h->batch), 256, 0, h->st>>>(h->rsK_part, n, h->ld, nt32, h->rsK);
+    LAUNCHED(h);
+  }
   rs_reduce_kernel<<<dim3(ceil_div(n, 256), h->batch), 256, 0, h->st>>>(h->rs_part, n, h->ld, nt32, h->rs);
   LAUNCHED(h);
   int mtiles = 1;
@@ -698,7 +717,8 @@ void enqueue_grad(H* h) {
       h->ell, h->ldmu, h->o.cov_form == 1 ? 1 : 0, h->o.mean_form == 1 ? 1 : 0, h->par_cap, h->d_grad);
   LAUNCHED(h);
   grad_finish_kernel<<<h->batch, 256, 0, h->st>>>(h->qtu, h->ldmu, n, h->d, h->p, h->o, h->wdiag, h->cens_rank, h->ld,
-                                                   h->hyp, h->ell, h->ldmu, h->mu, h->ldmu, h->par_cap, h->d_grad);
+                                                   h->hyp, h->ell, h->ldmu, h->mu, h->ldmu, h->par_cap, h->d_grad,
+                                                   matern ? h->rsK : nullptr);
   LAUNCHED(h);
 }
 
@@ -738,7 +758,8 @@ void make_view(const H* h, int g0, int cnt, cudaStream_t st, H* v) {
   adv(v->hyp, g * 4);
   adv(v->d_nlml, g); adv(v->d_logdet, g); adv(v->info, g); adv(v->d_ncens, g);
   adv(v->K, g * h->strideM); adv(v->Ky, g * h->strideM); adv(v->L, g * h->strideM); adv(v->Linv, g * h->strideM);
-  adv(v->Kinv, g * h->strideM); adv(v->U, g * h->strideM);
+  adv(v->Kinv, g * h->strideM); adv(v->U, g * h->strideM); adv(v->Kd, g * h->strideM);
+  adv(v->rsK_part, g * h->ld * ceil_div(h->n, 32)); adv(v->rsK, g * h->ld);
   adv(v->gsplit, g * std::max(1, h->gram_ksplit) * h->strideM);
 }
 
@@ -1066,6 +1087,8 @@ int gps_set_options(gps_handle h, int cov_form, int mean_form, int noise_corr, i
       int nrhs = (mean_form == GPS_MEAN_LINEAR) ? 2 : 1;
       h->nrhs = nrhs;
       h->naug = h->ne + nrhs;
+      rc = ensure_matern_buffers(h);
+      if (rc) return rc;
     }
     drop_graphs(h);
     h->fact_level = 0;
@@ -1153,6 +1176,7 @@ int gps_set_data(gps_handle h, const double* X, int n, int d, const double* y, c
   h->gsplit_elems = mat * std::max(1, h->gram_ksplit);   // raw Gram slices (>= 1: the weighted-Gram path always goes through it)
   CK(h, dalloc(&h->gsplit, h->gsplit_elems, false));
   CK(h, dalloc(&h->wsc, (size_t)h->ldmu * B));
+
   CK(h, dalloc(&h->m_alpha, vecB * 2));
   CK(h, dalloc(&h->m_hyp, (size_t)4 * B));
   CK(h, dalloc(&h->m_ell, (size_t)h->ldmu * B));
@@ -1160,6 +1184,8 @@ int gps_set_data(gps_handle h, const double* X, int n, int d, const double* y, c
   }
   h->model_valid = false;
   h->fact_level = 0;
+  rc = ensure_matern_buffers(h);
+  if (rc) return rc;
   // upload (host arrays are [batch][n x d] column-major, [batch][n])
   for (int b = 0; b < B; b++) {
     CK(h, cudaMemcpy2DAsync(h->Xaug + (size_t)b * h->strideX, (size_t)h->ldx * sizeof(double), X + (size_t)b * n * d,
@@ -1259,10 +1285,9 @@ int gps_nlml_grad(gps_handle h, const double* par, int len, double* nlml_out, do
   int rc = check_handle(h);
   if (rc) return rc;
   if (!grad_out) return fail(h, GPS_ERR_ARG, "grad_out is NULL");
-  if (h->o.cov_form >= GPS_COV_MATERN1)
-    return fail(h, GPS_ERR_UNSUPPORTED,
-                "no gradient for the Matern covariances: the reference has none either "
-                "(OptimisationGradientLog.R:6 'NOT YET WORKING FOR Matern'); use optimType = 'Nelder-Mead'");
+  if (h->o.cov_form >= GPS_COV_MATERN1 && h->have_data && !h->Kd)
+    return fail(h, GPS_ERR_STATE, "Matern gradient: call gps_set_options before gps_set_data (the derivative-factor buffer "
+                                  "is allocated with the data)");
   if (h->have_data && h->o.cov_form == GPS_COV_ARD && h->o.ard_mode == GPS_ARD_AS_WRITTEN && h->d > 1)
     return fail(h, GPS_ERR_UNSUPPORTED,
                 "the analytic ARD gradient is defined for ard_mode = INTENDED only (the reference's as-written ARD "
@@ -1428,7 +1453,7 @@ int gps_predict(gps_handle h, const double* par, int len, int reuse_model, const
   {  // K* = cov(X, X*)  (n x m).  snorm uses leading dimension lds, so the epilogue gets its own ldn
     GemmParams p = gp(h->Z, h->ldx, h->strideX, h->Zs, lds, sXs, n, m, d);
     EpiCov e;
-    e.normA = h->rnorm; e.normB = h->snorm; e.hyp = h->m_hyp; e.noise_diag = nullptr; e.Kout = h->Ks; e.Kyout = nullptr;
+    e.normA = h->rnorm; e.normB = h->snorm; e.hyp = h->m_hyp; e.noise_diag = nullptr; e.Kout = h->Ks; e.Kyout = nullptr; e.Kdout = nullptr;
     e.ldk = h->ld; e.ldn = h->ld; e.strideK = sKs; e.sym = 0; e.kind = cov_kind(h->o.cov_form);
     e.ldnB = lds;
     gemm<false, false>(h, p, e);
@@ -1635,8 +1660,7 @@ int gps_fit_batch(gps_handle h, const double* X, int n, int d, const double* y_l
   rc = gps_set_data(h, X, n, d, y_log, events);
   if (rc) return rc;
   if (len != expected_len(h)) return fail(h, GPS_ERR_ARG, "gps_fit_batch: par_start has the wrong length for these options");
-  if (method == 1 && h->o.cov_form >= GPS_COV_MATERN1)
-    return fail(h, GPS_ERR_UNSUPPORTED, "gps_fit_batch: BFGS needs a gradient, the Matern covariances have none");
+
   const int B = h->batch, p = h->p;
   const int nc = survival ? h->o.noise_corr : GPS_NC_NONE;
   if (!survival && h->o.noise_corr != GPS_NC_NONE)

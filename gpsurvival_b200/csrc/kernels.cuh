@@ -221,7 +221,8 @@ __global__ void cov_finish_kernel(const double* __restrict__ Gpart, int n1, int 
                                   long long strideG, int ksplit, const double* __restrict__ normA,
                                   const double* __restrict__ normB, int ldn, const double* __restrict__ hyp,
                                   const double* __restrict__ noise_diag, double* __restrict__ Kout,
-                                  double* __restrict__ Kyout, int ldk, long long strideK, int sym, int kind) {
+                                  double* __restrict__ Kyout, int ldk, long long strideK, int sym, int kind,
+                                  double* __restrict__ Kdout) {
   int i = blockIdx.x * 32 + threadIdx.x, j = blockIdx.y * 8 + threadIdx.y, b = blockIdx.z;
   if (i >= n1 || j >= n2) return;
   if (sym && i < j) return;   // lower triangle only, like the fused path
@@ -230,6 +231,7 @@ __global__ void cov_finish_kernel(const double* __restrict__ Gpart, int n1, int 
     gsum += Gpart[(size_t)b * strideG + (size_t)s * strideSplit + (size_t)i + (size_t)j * ldg];
   double s2 = hyp[b * 4 + 1];
   double r2 = fmax(0.0, normA[(size_t)b * ldn + i] + normB[(size_t)b * ldn + j] - 2.0 * gsum);
+  if (sym && i == j) r2 = 0.0;
   double k = cov_kernel_fn(kind, r2, s2), ky = k;
   if (sym && i == j) {
     k = s2;
@@ -238,6 +240,7 @@ __global__ void cov_finish_kernel(const double* __restrict__ Gpart, int n1, int 
   size_t off = (size_t)b * strideK + (size_t)i + (size_t)j * ldk;
   if (Kout) Kout[off] = k;
   if (Kyout) Kyout[off] = ky;
+  if (Kdout) Kdout[off] = cov_deriv_fn(kind, r2, s2);
 }
 
 // ---------------------------------------------------------------------------------------
@@ -655,8 +658,13 @@ __global__ void alpha_kernel(const double* __restrict__ Linv, int n, int ld, lon
 // ---------------------------------------------------------------------------------------
 __global__ void wk_kernel(const double* __restrict__ Kinv, const double* __restrict__ K, int n, int ld,
                           long long stride, const double* __restrict__ alpha_w, int ldn,
-                          double* __restrict__ M, double* __restrict__ wdiag, double* __restrict__ rs_part, int nt32) {
+                          double* __restrict__ M, double* __restrict__ wdiag, double* __restrict__ rs_part, int nt32,
+                          const double* __restrict__ Kd, double* __restrict__ rsK_part) {
+  // Kd != nullptr (Matern): M = W o Kd feeds the length-scale contraction, and the row sums of W o K (needed for
+  // d/dlog sf2 = -1/2 sum(W o K)) go to rsK_part; for SqExp / ARD Kd = K and sum(M) serves both.
   __shared__ double tile[32][33];
+  __shared__ double tileK[32][33];
+  const double* Kdb = Kd ? Kd + (size_t)blockIdx.z * stride : nullptr;
   int ti = blockIdx.x, tj = blockIdx.y, b = blockIdx.z;
   if (ti < tj) return;
   const double* Ki = Kinv + (size_t)b * stride;
@@ -674,12 +682,36 @@ __global__ void wk_kernel(const double* __restrict__ Kinv, const double* __restr
       size_t off = (size_t)ii + (size_t)jj * ld;
       double w = a[ii] * a[jj] - Ki[off];
       m = w * Kb[off];
+      if (Kdb) {
+        tileK[jl][threadIdx.x] = m;
+        m = w * Kdb[off];
+      }
       Mb[(size_t)i + (size_t)j * ld] = m;
       if (i == j) wdiag[(size_t)b * ldn + i] = w;
+    } else if (Kdb) {
+      tileK[jl][threadIdx.x] = 0.0;
     }
     tile[jl][threadIdx.x] = m;
   }
   __syncthreads();
+  if (Kdb) {   // the same partial row sums for W o K
+    double* rk = rsK_part + (size_t)b * nt32 * ldn;
+    if (threadIdx.y == 2 && i < n) {
+      double sum = 0.0;
+#pragma unroll 8
+      for (int jl = 0; jl < 32; jl++) sum += tileK[jl][threadIdx.x];
+      rk[(size_t)tj * ldn + i] = sum;
+    }
+    if (ti != tj && threadIdx.y == 3) {
+      int jo = tj * 32 + threadIdx.x;
+      if (jo < n) {
+        double sum = 0.0;
+#pragma unroll 8
+        for (int il = 0; il < 32; il++) sum += tileK[threadIdx.x][il];
+        rk[(size_t)ti * ldn + jo] = sum;
+      }
+    }
+  }
   // partial row sums of M over this tile's 32 columns (fixed order): rs_part[b][tj][i]; the mirrored block
   // gives rs_part[b][ti][j].  Every (row block, column block) pair is written exactly once.
   double* rp = rs_part + (size_t)b * nt32 * ldn;
@@ -764,10 +796,15 @@ __global__ void grad_finish_kernel(const double* __restrict__ qtu, int ldp, int 
                                    const double* __restrict__ wdiag, const int* __restrict__ cens_rank,
                                    int ldn, const double* __restrict__ hyp, const double* __restrict__ ell,
                                    int ldell, const double* __restrict__ mu, int ldmu, int len,
-                                   double* __restrict__ grad) {
+                                   double* __restrict__ grad, const double* __restrict__ rsK) {
   __shared__ double sh[256];
   int b = blockIdx.x, tid = threadIdx.x;
   const double* q = qtu + (size_t)b * 3 * ldp;
+  double sumWK = 0.0;   // sum(W o K): q[d] unless the contraction ran on W o Kd (Matern), then from its own row sums
+  if (rsK) {
+    for (int i = tid; i < n; i += blockDim.x) sumWK += rsK[(size_t)b * ldn + i];
+    sumWK = block_sum(sumWK, sh);
+  }
   const double* t = q + ldp;
   const double* u = q + 2 * ldp;
   double* g = grad + (size_t)b * len;
@@ -795,7 +832,7 @@ __global__ void grad_finish_kernel(const double* __restrict__ qtu, int ldp, int 
   }
   if (tid == 0) {
     g[0] = -0.5 * tr * hyp[b * 4 + 0];
-    g[1] = -0.5 * q[d];
+    g[1] = -0.5 * (rsK ? sumWK : q[d]);
     if (o.noise_corr == 1) g[len - 1] = -0.5 * trc * hyp[b * 4 + 2];
   }
 }

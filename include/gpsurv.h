@@ -33,7 +33,7 @@ typedef enum {
   GPS_ERR_ARG = 1,          /* bad argument (NULL, size, NaN/Inf in par) */
   GPS_ERR_CUDA = 2,         /* CUDA runtime failure or no sm_100 device */
   GPS_ERR_NOT_PD = 3,       /* Ky not positive definite; gps_last_pivot() = failing column (1-based) */
-  GPS_ERR_UNSUPPORTED = 4,  /* RF / InformedARD covariance, Matern or as-written-ARD gradient */
+  GPS_ERR_UNSUPPORTED = 4,  /* RF / InformedARD covariance, as-written-ARD gradient */
   GPS_ERR_STATE = 5         /* call order (e.g. predict before finalize) */
 } gps_status;
 
@@ -42,7 +42,7 @@ typedef enum {            /* covFuncForm (+ extraParam = maternParam for 'Matern
   GPS_COV_MATERN1 = 2,    /* 'Matern', extraParam 1: sf2 exp(-r)                                   */
   GPS_COV_MATERN3 = 3,    /* 'Matern', extraParam 3: sf2 (1 + sqrt3 r) exp(-sqrt3 r)              */
   GPS_COV_MATERN5 = 4     /* 'Matern', extraParam 5: sf2 (1 + sqrt5 r + 5 r^2/3) exp(-sqrt5 r)    */
-} gps_cov_form;           /* Matern: NLML / cov / finalize / predict only — the reference has no Matern gradient */
+} gps_cov_form;           /* Matern gradients are derived here (dK/dlog ell = -sf2 f'(r)/r * r^2): the reference has none */
 typedef enum { GPS_MEAN_ZERO = 0, GPS_MEAN_LINEAR = 1 } gps_mean_form;     /* meanFuncForm */
 typedef enum {
   GPS_NC_NONE = 0,      /* noiseCorr FALSE / 'none'      (GPR, GPS1) */

@@ -187,8 +187,22 @@ def nlml(par, X, y, events, cov_form="SqExp", mean_form="Zero", noise_corr=False
 # --------------------------------------------------------------------------------------
 # OptimisationGradientLog.R
 # --------------------------------------------------------------------------------------
+def matern_deriv_factor(distance, sf2, flag):
+    """Kd = -sf2 f'(r)/r for K = sf2 f(r): dK_ij/dlog(ell) = Kd_ij * r_ij^2 (one shared length-scale, CovFunc.R:33-37).
+    Derived, not restated: the reference has no Matern gradient (OptimisationGradientLog.R:6)."""
+    r = np.asarray(distance, dtype=np.float64)
+    if flag == "1":
+        with np.errstate(divide="ignore", invalid="ignore"):
+            return np.where(r > 0, float(sf2) * np.exp(-r) / r, 0.0)
+    if flag == "3":
+        return 3.0 * float(sf2) * np.exp(-(math.sqrt(3) * r))
+    if flag == "5":
+        return (5.0 / 3.0) * float(sf2) * (1 + math.sqrt(5) * r) * np.exp(-(math.sqrt(5) * r))
+    raise ValueError(f"maternParam {flag!r}")
+
+
 def nlml_grad(par, X, y, events, cov_form="SqExp", mean_form="Zero", noise_corr=False,
-              log_hyp_noise_corr=None, ard_mode="intended", grad_mode="analytic"):
+              log_hyp_noise_corr=None, ard_mode="intended", grad_mode="analytic", extra_param=None):
     """Gradient of the NLML w.r.t. ``par`` (OptimisationGradientLog.R:1-94).
 
     SqExp: the reference branch (:50-57), restated operation by operation — it is the
@@ -209,7 +223,7 @@ def nlml_grad(par, X, y, events, cov_form="SqExp", mean_form="Zero", noise_corr=
     sn2, sf2, ell = math.exp(log_sn2), math.exp(log_sf2), np.exp(log_ell)
     m = mean_func(mean_hyp, X, mean_form)                                    # :35
     r = rdist(X, X)                                                          # :36 (dist)
-    K = cov_func(X, X, sf2, ell, cov_form, ard_mode)                         # :37
+    K = cov_func(X, X, sf2, ell, cov_form, ard_mode, extra_param)            # :37
     Ky = K + np.diag(_noise_diag(n, log_sn2, events, noise_corr, lnc))       # :39-46
     Kinv = np.linalg.solve(Ky, np.eye(n))                                    # solve(Ky)
     cens = (np.asarray(events).ravel() == 0).astype(np.float64)
@@ -238,6 +252,18 @@ def nlml_grad(par, X, y, events, cov_form="SqExp", mean_form="Zero", noise_corr=
         if ard_mode != "intended":
             raise NotImplementedError("analytic ARD gradient is defined for ard_mode='intended'")
         dl = -(1.0 / ell ** 2) * ((rs[:, None] * X ** 2).sum(axis=0) - (X * (M @ X)).sum(axis=0))
+        if noise_corr == "noiseCorrLearned":
+            dcorr = -0.5 * float(np.sum(np.diag(W) * cens)) * math.exp(float(np.ravel(lnc)[0]))
+    elif cov_form == "Matern":
+        # derived (no reference branch): W-form with Kd = -sf2 f'(r)/r in the length-scale term
+        a = Kinv @ y
+        W = np.outer(a, a) - Kinv
+        l = float(ell[0])
+        rs_ = rdist(X / l, X / l)
+        Kd = matern_deriv_factor(rs_, sf2, str(int(extra_param)))
+        dnoise = -0.5 * float(np.trace(W)) * sn2
+        dfunc = -0.5 * float(np.sum(W * K))
+        dl = np.array([-0.5 * float(np.sum(W * Kd * rs_ ** 2))])
         if noise_corr == "noiseCorrLearned":
             dcorr = -0.5 * float(np.sum(np.diag(W) * cens)) * math.exp(float(np.ravel(lnc)[0]))
     elif cov_form == "ARD" and grad_mode == "as_written":
@@ -718,7 +744,7 @@ def gp_regression(log_hyp, params, data, log_hyp_noise_corr, ard_mode="intended"
     kw = dict(cov_form=cov_form, mean_form=mean_form, noise_corr=noise_corr,
               log_hyp_noise_corr=log_hyp_noise_corr, ard_mode=ard_mode)
     fn = lambda p: nlml(p, X, y, events, as_written_ops=as_written_ops, extra_param=extra, **kw)
-    gr = lambda p: nlml_grad(p, X, y, events, **kw)
+    gr = lambda p: nlml_grad(p, X, y, events, extra_param=extra, **kw)
     method = params["optimType"]
     if method == "Nelder-Mead":                                                                  # :28-31
         opt = nelder_mead(fn, vec, maxit=maxit)

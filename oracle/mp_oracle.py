@@ -40,8 +40,33 @@ def _cov(x1, x2, sf2, ell):
     return K
 
 
+def _cov_d(x, sf2, ell):
+    """Kd_ij = -sf2 f'(r)/r, the factor in dK_ij / dlog(ell_k) = Kd_ij * (x_ik - x_jk)^2 / ell_k^2 for
+    K = sf2 f(r), r = |x_i/ell - x_j/ell|.  Derived here (the reference has no Matern gradient,
+    OptimisationGradientLog.R:6): SqExp f = exp(-r^2/2) gives Kd = K; Matern 1/2: sf2 exp(-r)/r (0 at r = 0,
+    where the distance factor vanishes); 3/2: 3 sf2 exp(-sqrt3 r); 5/2: 5/3 sf2 (1 + sqrt5 r) exp(-sqrt5 r)."""
+    n, d = len(x), len(x[0])
+    Kd = mp.zeros(n, n)
+    for i in range(n):
+        for j in range(n):
+            r2 = mp.mpf(0)
+            for k in range(d):
+                lk = ell[k] if len(ell) > 1 else ell[0]
+                r2 += ((mp.mpf(x[i][k]) - mp.mpf(x[j][k])) / lk) ** 2
+            r = mp.sqrt(r2)
+            if MATERN is None:
+                Kd[i, j] = sf2 * mp.exp(-r2 / 2)
+            elif MATERN == 1:
+                Kd[i, j] = sf2 * mp.exp(-r) / r if r > 0 else mp.mpf(0)
+            elif MATERN == 3:
+                Kd[i, j] = 3 * sf2 * mp.exp(-mp.sqrt(3) * r)
+            else:
+                Kd[i, j] = mp.mpf(5) / 3 * sf2 * (1 + mp.sqrt(5) * r) * mp.exp(-mp.sqrt(5) * r)
+    return Kd
+
+
 def _unpack(par, d, ard, linear_mean, gps2):
-    par = [mp.mpf(float(p)) for p in par]
+    par = [p if isinstance(p, mp.mpf) else mp.mpf(float(p)) for p in par]
     sc2 = None
     if gps2:
         sc2 = mp.exp(par[-1])
@@ -98,6 +123,7 @@ def nlml_grad(par, X, y, events, ard=False, linear_mean=False, gps2=False, log_s
     g = [-(sum(W[i, i] for i in range(n))) * sn2 / 2,
          -sum(W[i, j] * K[i, j] for i in range(n) for j in range(n)) / 2]
     p = d if ard else 1
+    Kd = K if MATERN is None else _cov_d(X, sf2, ell)
     for k in range(p):
         s = mp.mpf(0)
         for i in range(n):
@@ -106,7 +132,7 @@ def nlml_grad(par, X, y, events, ard=False, linear_mean=False, gps2=False, log_s
                     r2 = ((mp.mpf(X[i][k]) - mp.mpf(X[j][k])) / ell[k]) ** 2
                 else:
                     r2 = sum(((mp.mpf(X[i][q]) - mp.mpf(X[j][q])) / ell[0]) ** 2 for q in range(d))
-                s += W[i, j] * K[i, j] * r2
+                s += W[i, j] * Kd[i, j] * r2
         g.append(-s / 2)
     if linear_mean:
         m = _mean(w, X)

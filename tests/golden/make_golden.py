@@ -56,8 +56,20 @@ def main():
             cov = "Matern"
         mpo.MATERN = extra
         nl = float(mpo.nlml(par, Xl, y, ev, **kw))
-        # the reference has no Matern gradient (OptimisationGradientLog.R:6): none is pinned
-        gr = [float(v) for v in mpo.nlml_grad(par, Xl, y, ev, **kw)] if extra is None else None
+        # the reference has no Matern gradient (OptimisationGradientLog.R:6); ours is derived (mp_oracle._cov_d)
+        # and checked here against a 50-digit central difference of the mpmath NLML before it is pinned
+        grm = mpo.nlml_grad(par, Xl, y, ev, **kw)
+        if extra is not None:
+            import mpmath as mp
+            hstep = mp.mpf(10) ** -20
+            for q in range(len(par)):
+                pp = [mp.mpf(float(v)) for v in par]
+                pm = list(pp)
+                pp[q] += hstep
+                pm[q] -= hstep
+                fd = (mpo.nlml(pp, Xl, y, ev, **kw) - mpo.nlml(pm, Xl, y, ev, **kw)) / (2 * hstep)
+                assert abs(fd - grm[q]) <= mp.mpf(10) ** -25 * max(1, abs(fd)), (name, q, fd, grm[q])
+        gr = [float(v) for v in grm]
         mu, vf, vd = mpo.predict(par, Xl, y, ev, Xs.tolist(), **kw)
         mpo.MATERN = None
         out["cases"].append({

@@ -36,7 +36,7 @@ def test_oracle_matches_mpmath_golden(c):
         f = orc.nlml(par, X, y, ev, as_written_ops=as_written, **kw, **_extra(c))
         assert abs(f - c["nlml"]) <= 1e-11 * abs(c["nlml"])
     if c["grad"] is not None:
-        g = orc.nlml_grad(par, X, y, ev, **kw)
+        g = orc.nlml_grad(par, X, y, ev, **kw, **_extra(c))
         assert np.max(np.abs(g - np.array(c["grad"]))) <= 1e-10 * np.max(np.abs(c["grad"]))
     reg = orc.regress_finalize(par, X, y, ev, **kw, **_extra(c))
     assert abs(reg["logMarLik"] + c["nlml"]) <= 1e-11 * abs(c["nlml"])
