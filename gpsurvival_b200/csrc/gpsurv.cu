@@ -89,7 +89,9 @@ struct gps_handle_s {
                                  // B200: its tiles run at 34.5 TF/s against 30 for the 64 x 64 kernel, but 128-wide tiles
                                  // over-compute a triangular n = 2000 matrix by 20 % (64-wide: 10 %), and one 288-thread
                                  // CTA per SM leaves no room for another stream group's panel kernels
-  int* ws_sched = nullptr;       // tile counters of the persistent kernel: WS_SLOTS x 2 ints, one slot per launch in turn
+  int* ws_sched = nullptr;       // tile counters of the persistent kernel: per stream group WS_SLOTS x 2 ints, one slot per
+                                 // launch in turn (kernels that may run at the same time never share a slot: launches of one
+                                 // group are ordered by its stream, different groups use different regions)
   unsigned ws_seq = 0;
   size_t gsplit_elems = 0;
   // resident model (after gps_regress_finalize)
@@ -779,9 +781,8 @@ void enqueue_grouped(H* h, SeqFn fn) {
     if (g > 0) CKV(h, cudaStreamWaitEvent(sg, h->ev_gfork, 0));
     H v;
     make_view(h, g0, g1 - g0, sg, &v);
-    v.ws_seq = h->ws_seq;
+    v.ws_sched = h->ws_sched + (size_t)g * 2 * WS_SLOTS;   // this group's own counters
     fn(&v);
-    h->ws_seq = v.ws_seq;
     launched += v.seq_launches;
     if (v.cu_err != cudaSuccess && h->cu_err == cudaSuccess) {
       h->cu_err = v.cu_err;
@@ -1015,8 +1016,8 @@ int gps_create_batch(int device, int batch, gps_handle* out) {
     return fail(nullptr, GPS_ERR_CUDA, std::string("gps_create: ") + cudaGetErrorString(e));
   }
   h->cur = h->st;
-  if (cudaMalloc((void**)&h->ws_sched, sizeof(int) * 2 * WS_SLOTS) != cudaSuccess ||
-      cudaMemsetAsync(h->ws_sched, 0, sizeof(int) * 2 * WS_SLOTS, h->st) != cudaSuccess ||
+  if (cudaMalloc((void**)&h->ws_sched, sizeof(int) * 2 * WS_SLOTS * H::MAX_GROUPS) != cudaSuccess ||
+      cudaMemsetAsync(h->ws_sched, 0, sizeof(int) * 2 * WS_SLOTS * H::MAX_GROUPS, h->st) != cudaSuccess ||
       cudaStreamSynchronize(h->st) != cudaSuccess) {
     std::string m = cudaGetErrorString(cudaGetLastError());
     delete h;
@@ -1186,27 +1187,33 @@ int gps_set_data(gps_handle h, const double* X, int n, int d, const double* y, c
   h->fact_level = 0;
   rc = ensure_matern_buffers(h);
   if (rc) return rc;
-  // upload (host arrays are [batch][n x d] column-major, [batch][n])
-  for (int b = 0; b < B; b++) {
-    CK(h, cudaMemcpy2DAsync(h->Xaug + (size_t)b * h->strideX, (size_t)h->ldx * sizeof(double), X + (size_t)b * n * d,
-                            (size_t)n * sizeof(double), (size_t)n * sizeof(double), d, cudaMemcpyHostToDevice, h->st));
-    CK(h, cudaMemcpyAsync(h->y + (size_t)b * h->ld, y + (size_t)b * n, (size_t)n * sizeof(double), cudaMemcpyHostToDevice,
-                          h->st));
-    if (events) {
-      CK(h, cudaMemcpyAsync(h->events + (size_t)b * h->ld, events + (size_t)b * n, (size_t)n * sizeof(double),
-                            cudaMemcpyHostToDevice, h->st));
-    } else {
-      std::vector<double> ones(n, 1.0);
-      CK(h, cudaMemcpyAsync(h->events + (size_t)b * h->ld, ones.data(), (size_t)n * sizeof(double), cudaMemcpyHostToDevice,
-                            h->st));
-      CK(h, cudaStreamSynchronize(h->st));   // `ones` goes out of scope
-    }
+  // upload (host arrays are [batch][n x d] column-major, [batch][n]).  A fit's X is one contiguous run on both sides
+  // when n needs no row padding, so the whole batch goes in ONE strided copy per array instead of one per fit
+  // (64 fits: 3 copies instead of 192 — each pageable-memory copy is staged synchronously by the driver).
+  if (h->ldx == n) {
+    CK(h, cudaMemcpy2DAsync(h->Xaug, (size_t)h->strideX * sizeof(double), X, (size_t)n * d * sizeof(double),
+                            (size_t)n * d * sizeof(double), B, cudaMemcpyHostToDevice, h->st));
+  } else {
+    for (int b = 0; b < B; b++)
+      CK(h, cudaMemcpy2DAsync(h->Xaug + (size_t)b * h->strideX, (size_t)h->ldx * sizeof(double), X + (size_t)b * n * d,
+                              (size_t)n * sizeof(double), (size_t)n * sizeof(double), d, cudaMemcpyHostToDevice, h->st));
+  }
+  CK(h, cudaMemcpy2DAsync(h->y, (size_t)h->ld * sizeof(double), y, (size_t)n * sizeof(double), (size_t)n * sizeof(double), B,
+                          cudaMemcpyHostToDevice, h->st));
+  if (events) {
+    CK(h, cudaMemcpy2DAsync(h->events, (size_t)h->ld * sizeof(double), events, (size_t)n * sizeof(double),
+                            (size_t)n * sizeof(double), B, cudaMemcpyHostToDevice, h->st));
+  } else {
+    std::vector<double> ones((size_t)n * B, 1.0);
+    CK(h, cudaMemcpy2DAsync(h->events, (size_t)h->ld * sizeof(double), ones.data(), (size_t)n * sizeof(double),
+                            (size_t)n * sizeof(double), B, cudaMemcpyHostToDevice, h->st));
+    CK(h, cudaStreamSynchronize(h->st));   // `ones` goes out of scope
   }
   colmean_kernel<<<dim3(ceil_div(d, 8), B), 256, 0, h->st>>>(h->Xaug, n, d, h->ldx, h->strideX, h->mu, h->ldmu);
   center_kernel<<<dim3(ceil_div(n, 256), d + 1, B), 256, 0, h->st>>>(h->Xaug, n, d, h->ldx, h->strideX, h->mu, h->ldmu);
   transpose_kernel<<<dim3(ceil_div(n, 32), ceil_div(d + 1, 32), B), dim3(32, 8), 0, h->st>>>(
       h->Xaug, n, d + 1, h->ldx, h->strideX, h->XaugT, h->ldxt, h->strideXT);
-  cens_rank_kernel<<<ceil_div(B, 64), 64, 0, h->st>>>(h->events, n, h->ld, h->cens_rank, h->d_ncens, B);
+  cens_rank_kernel<<<B, 32, 0, h->st>>>(h->events, n, h->ld, h->cens_rank, h->d_ncens, B);
   h->launches += 4;
   CK(h, cudaGetLastError());
   h->ncens.assign(B, 0);

@@ -66,19 +66,21 @@ __global__ void center_kernel(double* __restrict__ X, int n, int d, int ldx, lon
   else *x = 1.0;
 }
 
-// cens_rank[i] = index of row i among the censored rows (events == 0), else -1. One thread
-// per batch entry (n is small enough; runs once per gps_set_data).
+// cens_rank[i] = index of row i among the censored rows (events == 0), else -1 (once per gps_set_data).
 __global__ void cens_rank_kernel(const double* __restrict__ events, int n, int ldn, int* __restrict__ rank,
                                  int* __restrict__ ncens, int batch) {
-  int b = blockIdx.x * blockDim.x + threadIdx.x;
+  // one warp per fit: 32 rows per step, ranks by ballot + popcount (grid = batch, block = 32)
+  const int b = blockIdx.x, lane = threadIdx.x;
   if (b >= batch) return;
   int c = 0;
-  for (int i = 0; i < n; i++) {
-    bool cens = events[(size_t)b * ldn + i] == 0.0;
-    rank[(size_t)b * ldn + i] = cens ? c : -1;
-    c += cens ? 1 : 0;
+  for (int i0 = 0; i0 < n; i0 += 32) {
+    const int i = i0 + lane;
+    const bool cens = (i < n) && events[(size_t)b * ldn + i] == 0.0;
+    const unsigned mask = __ballot_sync(0xffffffffu, cens);
+    if (i < n) rank[(size_t)b * ldn + i] = cens ? c + __popc(mask & ((1u << lane) - 1u)) : -1;
+    c += __popc(mask);
   }
-  ncens[b] = c;
+  if (lane == 0) ncens[b] = c;
 }
 
 // ---------------------------------------------------------------------------------------
