@@ -330,6 +330,7 @@ __device__ __forceinline__ double cov_kernel_fn(int kind, double r2, double s2) 
   return s2 * (1.0 + a + (5.0 * (r * r)) / 3.0) * exp(-a);
 }
 
+// (used by cov_finish_kernel only: the fused epilogue below stays lean)
 // Kd = -sf2 f'(r)/r for K = sf2 f(r): dK_ij / dlog(ell_k) = Kd_ij (x_ik - x_jk)^2 / ell_k^2.  SqExp: Kd = K (never
 // asked for).  Matern gradients are derived here — the reference has none (OptimisationGradientLog.R:6).
 // At r = 0 the distance factor vanishes; nu = 1/2 (1/r) is defined as 0 there.
@@ -353,7 +354,6 @@ struct EpiCov {
   const double* noise_diag;   // [batch][ldn] or nullptr
   double* Kout;            // noise-free covariance (may be nullptr)
   double* Kyout;           // covariance + noise on the diagonal (may be nullptr)
-  double* Kdout;           // derivative factor Kd (Matern gradients; usually nullptr)
   int ldk, ldn, ldnB;      // ldn / ldnB: per-batch strides of normA (and noise_diag) / normB
   long long strideK;
   int sym;
@@ -366,7 +366,6 @@ struct EpiCov {
     const double* nd = noise_diag ? noise_diag + (size_t)a.batch * ldn : nullptr;
     double* Kb = Kout ? Kout + (size_t)a.batch * strideK : nullptr;
     double* Kyb = Kyout ? Kyout + (size_t)a.batch * strideK : nullptr;
-    double* Kdb = Kdout ? Kdout + (size_t)a.batch * strideK : nullptr;
 #pragma unroll
     for (int j = 0; j < Cfg::FN; j++) {
       int n = a.n_base + 8 * j;
@@ -376,15 +375,13 @@ struct EpiCov {
       for (int i = 0; i < Cfg::FM; i++) {
         int m = a.m_base + 8 * i;
         if (m >= p.M) continue;
-        double kk[2], ky[2], kd[2] = {0.0, 0.0};
+        double kk[2], ky[2];
 #pragma unroll
         for (int e = 0; e < 2; e++) {
           int mm = m + e;
           double r2 = (mm < p.M) ? fmax(0.0, nA[mm] + sn - 2.0 * a.v[i][j][e]) : 0.0;
-          if (sym && mm == n) r2 = 0.0;
           kk[e] = cov_kernel_fn(kind, r2, s2);
           ky[e] = kk[e];
-          if (Kdb) kd[e] = cov_deriv_fn(kind, r2, s2);
           if (sym && mm == n) {
             kk[e] = s2;
             ky[e] = nd ? s2 + nd[mm] : s2;
@@ -395,11 +392,9 @@ struct EpiCov {
         if (m + 1 < p.M) {
           if (Kb) *reinterpret_cast<double2*>(Kb + off) = make_double2(kk[0], kk[1]);
           if (Kyb) *reinterpret_cast<double2*>(Kyb + off) = make_double2(ky[0], ky[1]);
-          if (Kdb) *reinterpret_cast<double2*>(Kdb + off) = make_double2(kd[0], kd[1]);
         } else {
           if (Kb) Kb[off] = kk[0];
           if (Kyb) Kyb[off] = ky[0];
-          if (Kdb) Kdb[off] = kd[0];
         }
       }
     }

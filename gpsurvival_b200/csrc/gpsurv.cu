@@ -422,9 +422,12 @@ void enqueue_cov(H* h, const double* Za, int n1, int lda, long long sA, const do
                  int kind, double* Kdout = nullptr) {
   GemmParams p = gp(Za, lda, sA, Zb, ldb, sB, n1, n2, d);
   p.lower = sym ? 1 : 0;
-  if (ksplit <= 1) {
+  // Kdout (the Matern derivative factor, training Gram only) is written by the finishing pass: that route then
+  // also serves ksplit = 1, so the fused epilogue never carries the extra code and registers
+  if (Kdout && ksplit < 1) ksplit = 1;
+  if (ksplit <= 1 && !Kdout) {
     EpiCov e;
-    e.normA = normA; e.normB = normB; e.hyp = hyp; e.noise_diag = noise_diag; e.Kout = Kout; e.Kyout = Kyout; e.Kdout = Kdout;
+    e.normA = normA; e.normB = normB; e.hyp = hyp; e.noise_diag = noise_diag; e.Kout = Kout; e.Kyout = Kyout;
     e.ldk = ldk; e.ldn = h->ld; e.ldnB = h->ld; e.strideK = sK; e.sym = sym ? 1 : 0; e.kind = kind;
     gemm<false, false>(h, p, e);
   } else {
@@ -1460,7 +1463,7 @@ int gps_predict(gps_handle h, const double* par, int len, int reuse_model, const
   {  // K* = cov(X, X*)  (n x m).  snorm uses leading dimension lds, so the epilogue gets its own ldn
     GemmParams p = gp(h->Z, h->ldx, h->strideX, h->Zs, lds, sXs, n, m, d);
     EpiCov e;
-    e.normA = h->rnorm; e.normB = h->snorm; e.hyp = h->m_hyp; e.noise_diag = nullptr; e.Kout = h->Ks; e.Kyout = nullptr; e.Kdout = nullptr;
+    e.normA = h->rnorm; e.normB = h->snorm; e.hyp = h->m_hyp; e.noise_diag = nullptr; e.Kout = h->Ks; e.Kyout = nullptr;
     e.ldk = h->ld; e.ldn = h->ld; e.strideK = sKs; e.sym = 0; e.kind = cov_kind(h->o.cov_form);
     e.ldnB = lds;
     gemm<false, false>(h, p, e);
