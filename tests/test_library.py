@@ -77,3 +77,27 @@ def test_host_logic_flatten_and_options():
     pb = synth.make_config_problem(cfg, scale=0.05)
     assert pb["trainingData"].shape == (100, 20) and int(np.sum(pb["events"] == 0)) == 50
     assert abs(pb["trainingData"].mean()) < 1e-12 and np.allclose(pb["trainingData"].std(axis=0, ddof=1), 1.0)
+
+
+def test_r_glue_type_checks_against_the_abi():
+    """R is not installed here, so r/gpsurv_glue.c can never be run; it can still be TYPE-CHECKED:
+    gcc -fsyntax-only against a stub of the few R C-API declarations it uses (tests/r_stub) and the real
+    include/gpsurv.h — every gps_* call in the glue must match the ABI's argument list, and the .Call
+    registration table must state each wrapper's true argument count."""
+    import re
+    import shutil
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    glue = os.path.join(root, "r", "gpsurv_glue.c")
+    gcc = shutil.which("gcc")
+    assert gcc, "gcc is part of the build image"
+    res = subprocess.run([gcc, "-fsyntax-only", "-std=c11", "-Wall", "-Werror=implicit-function-declaration",
+                          "-Werror=incompatible-pointer-types", "-Werror=int-conversion", "-Wno-cast-function-type",
+                          "-I", os.path.join(root, "tests", "r_stub"), glue], capture_output=True, text=True)
+    assert res.returncode == 0, res.stderr
+    src = open(glue).read()
+    defs = {m.group(1): m.group(2).count("SEXP") for m in re.finditer(r"^SEXP (gps_r_\w+)\(([^)]*)\)", src, re.M)}
+    table = re.findall(r'\{"(gps_r_\w+)", \(DL_FUNC\)&(gps_r_\w+), (\d+)\}', src)
+    assert table and len(table) == len(defs)
+    for name, fn, nargs in table:
+        assert name == fn and defs[fn] == int(nargs), (name, defs.get(fn), nargs)
