@@ -319,6 +319,21 @@ __device__ __forceinline__ void dmma_acc(double& d0, double& d1, double a_mma, d
                : "d"(a_mma), "d"(b_mma));
 }
 
+// Branch-free 1/sqrt(d) for the pivot chain: hardware seed (rsqrt.approx.f64, 2^-26) + two Newton steps
+// y <- y + y (1/2 - (d/2) y^2) -> ~1 ulp, like rsqrt().  The library routine carries special-case branches, i.e.
+// basic-block boundaries the scheduler cannot move the rank-1 update's independent DFMAs across; this one is
+// straight-line code, so they interleave with its dependent chain.  d <= 0 / NaN give NaN (the caller flags it).
+__device__ __forceinline__ double pivot_rsqrt(double d) {
+  double y;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(d));
+  const double hd = 0.5 * d;
+  double e = fma(-hd * y, y, 0.5);
+  y = fma(y, e, y);
+  e = fma(-hd * y, y, 0.5);
+  y = fma(y, e, y);
+  return y;
+}
+
 // Sub-panel Q (columns 16Q..16Q+15) of the 64 x 64 block in S, executed by warp 0.
 // SLOTS = 2: rows lane and lane+32 are both live (Q < 2); SLOTS = 1: only rows lane+32 (Q >= 2).
 template <int Q>
@@ -331,11 +346,11 @@ __device__ __forceinline__ void potf2_subpanel(double* S, double* invd, int lane
 #pragma unroll
     for (int i = 0; i < 16; i++) p[s][i] = S[(16 * Q + i) * PS + lane + 32 * s];
   double d = __shfl_sync(0xffffffffu, p[PSLOT][0], (16 * Q) & 31);
+  double rs = pivot_rsqrt(d);
 #pragma unroll 1
   for (int jj = 0; jj < 16; jj++) {
     const int j = 16 * Q + jj;
     if (!(d > 0.0) && bad == 0) bad = j + 1;
-    const double rs = rsqrt(d);
     double lr[2];
 #pragma unroll
     for (int s = S0; s < 2; s++) {
@@ -345,14 +360,20 @@ __device__ __forceinline__ void potf2_subpanel(double* S, double* invd, int lane
     }
     if (Q >= 2) S[j * PS + lane] = 0.0;          // rows above the sub-panel: zeros above the diagonal
     if (lane == 0) invd[j] = rs;
-    // next pivot = a_{j+1,j+1} - l_{j+1,j}^2, straight from the owner's registers
+    // next pivot = a_{j+1,j+1} - l_{j+1,j}^2, straight from the owner's registers — and its rsqrt is issued
+    // HERE, ahead of this column's rank-1 update in program order: a warp issues in order, so started after
+    // the update's 30 DFMAs the ~120-cycle rsqrt chain would sit fully exposed behind them (measured 280
+    // cycles per pivot); started first, the update's independent DFMAs fill its latency.
     {
       const int o = (j + 1) & 31;
       double a11 = __shfl_sync(0xffffffffu, p[PSLOT][1], o);
       double l10 = __shfl_sync(0xffffffffu, lr[PSLOT], o);
       d = a11 - l10 * l10;
+      rs = pivot_rsqrt(d);
     }
     __syncwarp();
+    // (the L[j+i][j] broadcasts stay in shared memory: fetching them by warp shuffle from the owners' registers
+    //  was measured SLOWER — 7.2 K vs 5.0 K cycles per 16-column sub-panel: two SHFL.32 + a select per value)
     const double* col = S + j * PS + j;
 #pragma unroll
     for (int i = 1; i < 16; i++) {
