@@ -82,6 +82,7 @@ struct gps_handle_s {
   double* wsc = nullptr;         // [batch][ldmu] k-weights 1/ell_k^2 of the weighted Gram product (hyp_prep_kernel)
   int num_sms = 148;
   int ws_enabled = 1;            // GPS_WS=0: never use the warp-specialised 128 x 128 kernel
+  int front_fused = 1;           // GPS_FRONT=0: never use the fused small-d front end (small_front_kernel)
   int nbig = 256;                // GPS_NBIG: diagonal block of the two-level Cholesky (64 = one-level recursion)
   bool nbig_forced = false;
   int ws_min_tiles = 296;        // GPS_WS_MIN: minimum number of 128 x 128 tiles in a launch
@@ -655,8 +656,21 @@ void enqueue_gram_train(H* h) {
               h->noise_diag, h->K, h->Ky, h->ld, h->strideM, true, h->gram_ksplit, cov_kind(h->o.cov_form), kd);
 }
 
-void enqueue_factor(H* h) {
+// Everything before the factorisation: hyper-parameters, K / Ky, mean, augmented right-hand-side rows.
+void enqueue_front(H* h) {
   const int n = h->n;
+  // few features and a small problem: one fused launch, covariance by direct differences.  Measured on B200: lone
+  // n = 60 / 100 / 200 / 500 evaluations 43 -> 27, 68 -> 55, 121 -> 111, 249 -> 242 us; break-even near
+  // batch * n^2 * d = 4e7 (a lone C2 fit), beyond which the DMMA Gram route wins (C2 x 64: 1.0 vs 2.0 ms)
+  if (h->front_fused && h->d <= FRONT_DMAX && (double)h->batch * h->n * h->n * h->d <= 4.0e7) {
+    const int nt = ceil_div(h->ne, 32);
+    small_front_kernel<<<dim3(nt, nt, h->batch), dim3(32, 8), 0, h->st>>>(
+        h->par, h->par_cap, h->o, n, h->ne, h->d, h->p, h->nrhs, h->Xaug, h->ldx, h->strideX, h->mu, h->ldmu, h->events,
+        h->cens_rank, h->lsc, h->ldc, h->ld, h->y, h->hyp, h->ell, h->meanw, h->noise_diag, h->meanv, h->K, h->Ky,
+        (h->o.cov_form >= GPS_COV_MATERN1) ? h->Kd : nullptr, h->ld, h->strideM, h->info, cov_kind(h->o.cov_form));
+    LAUNCHED(h);
+    return;
+  }
   CKV(h, cudaMemsetAsync(h->info, 0, sizeof(int) * h->batch, h->st));
   hyp_prep_kernel<<<h->batch, 256, 0, h->st>>>(h->par, h->par_cap, h->o, n, h->d, h->p, h->events, h->cens_rank, h->lsc,
                                                 h->ldc, h->ld, h->mu, h->ldmu, h->hyp, h->ell, h->ldmu, h->meanw,
@@ -667,6 +681,11 @@ void enqueue_factor(H* h) {
       h->Xaug, n, h->ne, h->d, h->ldx, h->strideX, h->meanw, h->ldmu, h->o.mean_form == 1, h->y, h->ld, h->meanv, h->Ky,
       h->ld, h->strideM, h->nrhs);
   LAUNCHED(h);
+}
+
+void enqueue_factor(H* h) {
+  const int n = h->n;
+  enqueue_front(h);
   enqueue_potrf(h);
   nlml_finish_kernel<<<h->batch, 256, 0, h->st>>>(h->L, n, h->ne, h->ld, h->strideM, h->nrhs, h->zvec, h->ld, h->d_nlml,
                                                    h->d_logdet);
@@ -991,6 +1010,7 @@ int gps_create_batch(int device, int batch, gps_handle* out) {
   if (const char* ev = getenv("GPS_WS")) h->ws_enabled = atoi(ev) != 0;
   if (const char* ev = getenv("GPS_WS_MIN")) h->ws_min_tiles = atoi(ev);
   if (const char* ev = getenv("GPS_WS_MIN_N")) h->ws_min_n = atoi(ev);
+  if (const char* ev = getenv("GPS_FRONT")) h->front_fused = atoi(ev) != 0;
   if (const char* ev = getenv("GPS_NBIG")) {
     const int v = atoi(ev);
     if (v == 64 || v == 128 || v == 256 || v == 512) {
@@ -1850,14 +1870,7 @@ int gps_time_stages(gps_handle h, double* ms_out) {
   h->seq_launches = 0;
   CK(h, cudaStreamSynchronize(h->st));
   CK(h, cudaEventRecord(ev[0], h->st));
-  CKV(h, cudaMemsetAsync(h->info, 0, sizeof(int) * h->batch, h->st));
-  hyp_prep_kernel<<<h->batch, 256, 0, h->st>>>(h->par, h->par_cap, h->o, n, h->d, h->p, h->events, h->cens_rank, h->lsc,
-                                                h->ldc, h->ld, h->mu, h->ldmu, h->hyp, h->ell, h->ldmu, h->meanw,
-                                                h->noise_diag, h->wsc);
-  enqueue_gram_train(h);
-  fill_aug_kernel<<<dim3(ceil_div(h->ne, 128), h->batch), 128, 0, h->st>>>(
-      h->Xaug, n, h->ne, h->d, h->ldx, h->strideX, h->meanw, h->ldmu, h->o.mean_form == 1, h->y, h->ld, h->meanv, h->Ky,
-      h->ld, h->strideM, h->nrhs);
+  enqueue_front(h);
   CK(h, cudaEventRecord(ev[1], h->st));
   enqueue_potrf(h);
   nlml_finish_kernel<<<h->batch, 256, 0, h->st>>>(h->L, n, h->ne, h->ld, h->strideM, h->nrhs, h->zvec, h->ld, h->d_nlml,

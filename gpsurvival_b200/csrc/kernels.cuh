@@ -280,6 +280,134 @@ __global__ void fill_aug_kernel(const double* __restrict__ X, int n, int ne, int
 }
 
 // ---------------------------------------------------------------------------------------
+// Fused front end for few features (d <= FRONT_DMAX): hyper-parameter preparation, covariance by DIRECT
+// differences, noise diagonal, mean function and the augmented right-hand-side rows in ONE launch
+// (replaces memset + hyp_prep + prescale + rownorm + Gram GEMM + fill_aug).  With d of a few dozen the
+// Gram GEMM has a 2-step k-loop and its traffic is all epilogue; here each thread forms
+//   r2 = sum_k ((x_ik - x_jk) / ell_k)^2      (the reference's own order of operations: rdist of the scaled
+//                                              inputs, CovFunc.R:25-29 — no Gram-trick cancellation at all)
+// from rows staged in shared memory.  The reference's drivers all live here (n = 100..500, d <= 6), where it
+// removes five of the nine launches of an evaluation.
+// grid (ceil(ne/32), ceil(ne/32), batch), block (32, 8); tiles above the diagonal exit.
+// ---------------------------------------------------------------------------------------
+constexpr int FRONT_DMAX = 32;
+__global__ void __launch_bounds__(256) small_front_kernel(
+    const double* __restrict__ par, int len, ModelOpts o, int n, int ne, int d, int p, int nrhs,
+    const double* __restrict__ X, int ldx, long long strideX, const double* __restrict__ mu, int ldmu,
+    const double* __restrict__ events, const int* __restrict__ cens_rank, const double* __restrict__ log_sc2_vec,
+    int ldc, int ldn, const double* __restrict__ y, double* __restrict__ hyp, double* __restrict__ ell,
+    double* __restrict__ meanw, double* __restrict__ noise_diag, double* __restrict__ meanv, double* __restrict__ K,
+    double* __restrict__ Ky, double* __restrict__ Kd, int ld, long long strideK, int* __restrict__ info, int kind) {
+  const int ti = blockIdx.x, tj = blockIdx.y, b = blockIdx.z;
+  if (ti < tj) return;
+  __shared__ double zi[32][FRONT_DMAX + 1], zj[32][FRONT_DMAX + 1];
+  __shared__ double s_ell[FRONT_DMAX], s_w[FRONT_DMAX + 1];
+  const int tx = threadIdx.x, ty = threadIdx.y, tid = ty * 32 + tx;
+  const double* pr = par + (size_t)b * len;
+  const int plen = len - (o.noise_corr == 1 ? 1 : 0);
+  const double sn2 = exp(pr[0]), s2 = exp(pr[1]);
+  const double sc2 = (o.noise_corr == 1) ? exp(pr[len - 1]) : 0.0;
+  const bool as_written = (o.ard_mode == 1 && p > 1);
+  if (tid < d) s_ell[tid] = exp(pr[2 + (p == 1 ? 0 : tid)]);
+  if (tid <= d) {
+    double w = 0.0;
+    if (o.mean_form == 1) {
+      const double* wp = pr + (plen - d - 1);
+      w = wp[tid];
+      if (tid == d)   // stored X is centred: b' = b + mu . w
+        for (int k = 0; k < d; k++) w += wp[k] * mu[(size_t)b * ldmu + k];
+    }
+    s_w[tid] = w;
+  }
+  __syncthreads();
+  const double* Xb = X + (size_t)b * strideX;
+  // stage the scaled rows of both tiles: z = x / ell (intended) or (x + mu) / ell[(i + k n) mod p] (as written)
+  for (int c = tid; c < 32 * d; c += 256) {
+    const int r = c & 31, k = c >> 5;
+    const int i = ti * 32 + r, j = tj * 32 + r;
+    double vi = 0.0, vj = 0.0;
+    if (i < n) {
+      const double xv = Xb[(size_t)i + (size_t)k * ldx];
+      vi = as_written ? (xv + mu[(size_t)b * ldmu + k]) / s_ell[(int)(((long long)i + (long long)k * n) % p)] : xv / s_ell[k];
+    }
+    if (j < n) {
+      const double xv = Xb[(size_t)j + (size_t)k * ldx];
+      vj = as_written ? (xv + mu[(size_t)b * ldmu + k]) / s_ell[(int)(((long long)j + (long long)k * n) % p)] : xv / s_ell[k];
+    }
+    zi[r][k] = vi;
+    zj[r][k] = vj;
+  }
+  __syncthreads();
+  double* Kb = K + (size_t)b * strideK;
+  double* Kyb = Ky + (size_t)b * strideK;
+  double* Kdb = Kd ? Kd + (size_t)b * strideK : nullptr;
+  const int i = ti * 32 + tx;
+  const bool mirror = (ti != tj) && ((ti >> 1) == (tj >> 1));   // upper half of a diagonal 64-block: kept symmetric
+  double nd_i = sn2;
+  if (i < n) {
+    const int r = cens_rank[(size_t)b * ldn + i];
+    if (r >= 0) nd_i += (o.noise_corr == 1) ? sc2 : (o.noise_corr == 2 ? exp(log_sc2_vec[(size_t)b * ldc + r]) : 0.0);
+  }
+#pragma unroll
+  for (int rr = 0; rr < 4; rr++) {
+    const int jl = ty + 8 * rr, j = tj * 32 + jl;
+    if (i >= n || j >= n) continue;
+    double r2 = 0.0;
+    for (int k = 0; k < d; k++) {
+      const double df = zi[tx][k] - zj[jl][k];
+      r2 = fma(df, df, r2);
+    }
+    double kv = cov_kernel_fn(kind, r2, s2), kyv = kv;
+    if (i == j) {
+      r2 = 0.0;
+      kv = s2;
+      kyv = s2 + nd_i;
+    }
+    const size_t off = (size_t)i + (size_t)j * ld, offt = (size_t)j + (size_t)i * ld;
+    Kb[off] = kv;
+    Kyb[off] = kyv;
+    if (Kdb) Kdb[off] = cov_deriv_fn(kind, r2, s2);
+    if (mirror || (ti == tj && i != j)) {
+      Kb[offt] = kv;
+      Kyb[offt] = kyv;
+      if (Kdb) Kdb[offt] = cov_deriv_fn(kind, r2, s2);
+    }
+  }
+  if (tj != 0) return;
+  // ---- per-row work, once per row block (tiles of the first block column) --------------------------------
+  if (ty == 0 && i < ne) {
+    double* col = Kyb + (size_t)i * ld;
+    if (i >= n) {   // identity padding column (n odd)
+      for (int r = 0; r < ne + nrhs; r++) col[r] = (r == i) ? 1.0 : 0.0;
+      Kb[(size_t)i + (size_t)i * ld] = 1.0;
+    } else {
+      double m = 0.0;
+      if (o.mean_form == 1) {
+        for (int k = 0; k < d; k++) m += Xb[(size_t)i + (size_t)k * ldx] * s_w[k];
+        m += s_w[d];
+      }
+      meanv[(size_t)b * ldn + i] = m;
+      noise_diag[(size_t)b * ldn + i] = nd_i;
+      const double yi = y[(size_t)b * ldn + i];
+      for (int r = n; r < ne; r++) col[r] = 0.0;   // padding row
+      col[ne] = yi - m;
+      if (nrhs == 2) col[ne + 1] = yi;
+    }
+  }
+  if (ti == 0) {   // once per fit
+    if (tid == 0) {
+      hyp[b * 4 + 0] = sn2;
+      hyp[b * 4 + 1] = s2;
+      hyp[b * 4 + 2] = sc2;
+      hyp[b * 4 + 3] = 0.0;
+      info[b] = 0;
+    }
+    if (tid < p) ell[(size_t)b * ldmu + tid] = s_ell[tid];
+    if (tid <= d) meanw[(size_t)b * ldmu + tid] = s_w[tid];
+  }
+}
+
+// ---------------------------------------------------------------------------------------
 // Fused panel kernel of the blocked Cholesky (chol(): ForOptimisationLog.R:41-42): for the
 // block column [e0, e0+nb) it
 //   (1) factors the NB x NB diagonal block          L11 = chol(A11)
