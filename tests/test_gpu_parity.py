@@ -756,3 +756,17 @@ def test_stream_groups_are_bitwise_neutral():
     assert np.array_equal(a[4], b[4]) and np.array_equal(a[5], b[5])
     c = _batched_eval(520, 60, 40, 9, {"GPS_GROUPS": "4", "GPS_NBIG": "64"})      # one-level Cholesky: rounding only
     assert relmax(c[4], a[4]) <= 1e-12 and relmax(c[5], a[5]) <= 1e-10
+
+
+def test_fused_front_end_agrees_with_gram_route():
+    """Few features: small_front_kernel (direct differences, one launch) against the DMMA Gram route
+    (pre-scale + Gram trick + fused covariance epilogue + fill_aug) — rounding-level agreement, both vs the oracle."""
+    a = _batched_eval(300, 7, 6, 3, {"GPS_FRONT": "1"})
+    b = _batched_eval(300, 7, 6, 3, {"GPS_FRONT": "0"})
+    assert relmax(a[4], b[4]) <= 1e-12 and relmax(a[5], b[5]) <= 1e-10 and relmax(a[6], b[6]) <= 1e-12
+    X, y, ev, par, f, g, _ = a
+    lnc = np.full(int(np.sum(ev[0] == 0)), np.log(0.3))
+    kw = dict(cov_form="ARD", noise_corr="noiseCorrVec", log_hyp_noise_corr=lnc)
+    fo = orc.nlml(par[0], X[0], y[0], ev[0], **kw)
+    assert abs(f[0] - fo) <= TOL_NLML * abs(fo)
+    assert relmax(g[0], orc.nlml_grad(par[0], X[0], y[0], ev[0], **kw)) <= TOL_GRAD
