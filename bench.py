@@ -308,6 +308,7 @@ def run_gpu(args):
 
     line = None
     if rank == 0:
+        fit.time_stages()                 # first pass pays one-time costs of kernel variants only this (ungrouped) path uses
         stages = fit.time_stages()
         gemm_ms = fit.bench_gemm(8192, 8192, 8192, 3)
         achieved = B * flops / (ms_per_step * 1e-3) / 1e12
