@@ -72,13 +72,18 @@ def step_pars(par0, count, seed):
     return par0[None, :] + 0.05 * rng.standard_normal((count, par0.size))
 
 
+CONFIG_NOTES = {"C2": "BASELINE.json configs[1]", "C3": "BASELINE.json configs[2], Tothill shape",
+                "C4": "BASELINE.json configs[3], Yuan shape"}
+
+
 def config_dict(B, world, n, d, nhyp):
-    return {"workload": "C2: GPS3 ARD NLML+gradient, n=2000 d=20 c=1000 (BASELINE.json configs[1]); one step = "
-                        "one evaluation of each of %d independent fits batched per GPU" % B,
+    return {"workload": "%s: GPS3 ARD NLML+gradient, n=%d d=%d c=%d (%s); one step = "
+                        "one evaluation of each of %d independent fits batched per GPU"
+                        % (CFG.name, n, d, CFG.c, CONFIG_NOTES.get(CFG.name, ""), B),
             "n": int(n), "d": int(d), "hyperparameters": int(nhyp), "fits_per_gpu": int(B),
             "partition": f"independent fits, {B} per GPU x {world} GPUs, no collective",
-            "l2": "per-step working set %d fits x 5 n x n FP64 matrices = %.1f GB >> 126 MB L2 (no flush needed)"
-                  % (B, B * 5 * n * n * 8 / 1e9)}
+            "l2": "per-step working set %d fits x (5 n x n matrices + X and X') = %.1f GB >> 126 MB L2 (no flush needed)"
+                  % (B, B * (5 * n * n + 2 * n * d) * 8 / 1e9)}
 
 
 def measured_traffic(B):
@@ -343,7 +348,8 @@ def run_gpu(args):
             starts = [synth.start_log_hyp(d, CFG.cov_form, rs) for _ in range(B)]
             par_start = np.stack([gp._flatten(s0, d, "Zero", CFG.noise_corr, None) for s0 in starts])
             Xtest = X[:, :500, :]
-            for method in ("Nelder-Mead", "BFGS"):
+            # Nelder-Mead needs one evaluation per simplex vertex (hyper-parameters + 1) before it moves: only sensible at d = 20
+            for method in (("Nelder-Mead", "BFGS") if CFG.name == "C2" else ("BFGS",)):
                 tt = time.perf_counter()
                 rr = fit.fit_batch(X, y, ev, par_start, Xtest, method=method, maxit=10, tolerance=1e300, max_count=6,
                                    survival=True)                      # whole fits behind the C ABI (gps_fit_batch)
@@ -416,8 +422,15 @@ def main():
     ap.add_argument("--steps", type=int, default=30)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--batch", type=int, default=64, help="independent fits evaluated per step on each GPU")
+    ap.add_argument("--batch", type=int, default=0, help="independent fits evaluated per step on each GPU "
+                                                         "(default: 64 for C2, 32 for C3, 256 for C4)")
+    ap.add_argument("--config", default="C2", choices=["C2", "C3", "C4"],
+                    help="workload shape; the default C2 is the configuration BASELINE.json's metric is quoted on")
     args = ap.parse_args()
+    global CFG
+    CFG = synth.CONFIGS[args.config]
+    if args.batch <= 0:
+        args.batch = {"C2": 64, "C3": 32, "C4": 256}[args.config]
     if args.impl == "reference":
         return run_reference(args)
     return run_gpu(args)
