@@ -82,6 +82,7 @@ struct gps_handle_s {
   double* wsc = nullptr;         // [batch][ldmu] k-weights 1/ell_k^2 of the weighted Gram product (hyp_prep_kernel)
   int num_sms = 148;
   int ws_enabled = 1;            // GPS_WS=0: never use the warp-specialised 128 x 128 kernel
+  int ws_kmin = 128;             // GPS_WS_KMIN: shortest k-loop given to the persistent kernel
   int front_fused = 1;           // GPS_FRONT=0: never use the fused small-d front end (small_front_kernel)
   int nbig = 256;                // GPS_NBIG: diagonal block of the two-level Cholesky (64 = one-level recursion)
   bool nbig_forced = false;
@@ -262,7 +263,7 @@ bool use_ws128(const H* h, const GemmParams& p) {
 // tile, 32 = its 128 x 32 tile for narrow outputs (dmma_ws.cuh), 0 = the 64 x 64 cp.async kernel (short k-loops: K < 128, where a persistent tile's
 // un-overlapped epilogue dominates; and every developer override).
 int pick_nt_tile(const H* h, const GemmParams& p) {
-  if (h->force_tile >= 0 || !h->ws_enabled || !h->ws_sched || p.K < 128) return 0;
+  if (h->force_tile >= 0 || !h->ws_enabled || !h->ws_sched || p.K < h->ws_kmin) return 0;
   if (use_ws128(h, p)) return 128;
   if (p.N <= 32 && !p.lower && (long long)ceil_div(p.M, 128) * h->batch * p.nodes * p.ksplit >= h->num_sms) return 32;
   {   // a launch that cannot even fill the persistent grid once (a lone mid-size fit) is latency-bound: the plain
@@ -1011,6 +1012,7 @@ int gps_create_batch(int device, int batch, gps_handle* out) {
   if (const char* ev = getenv("GPS_WS_MIN")) h->ws_min_tiles = atoi(ev);
   if (const char* ev = getenv("GPS_WS_MIN_N")) h->ws_min_n = atoi(ev);
   if (const char* ev = getenv("GPS_FRONT")) h->front_fused = atoi(ev) != 0;
+  if (const char* ev = getenv("GPS_WS_KMIN")) h->ws_kmin = atoi(ev);
   if (const char* ev = getenv("GPS_NBIG")) {
     const int v = atoi(ev);
     if (v == 64 || v == 128 || v == 256 || v == 512) {
