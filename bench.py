@@ -15,9 +15,9 @@ A lone fit is latency-bound by the sequential pivot chain of its Cholesky; `sing
 * value  : evaluations/s, inputs resident in HBM, device-timed with CUDA events on the
            library's stream (gps_time_eval: K back-to-back graph replays; nothing is cached
            between replays: each recomputes Gram, Cholesky, inverse and gradient), max over ranks.
-* e2e    : the same metric through the public API with HOST buffers: every step uploads X, y,
-           events, the GPS3 noise-correction vectors and par for the whole batch, evaluates, and
-           reads all NLMLs and gradients back.
+* e2e    : the same metric through the public API with HOST buffers (pinned, X column-major per fit
+           as the ABI and R store it): every step uploads X, y, events, the GPS3 noise-correction
+           vectors and par for the whole batch, evaluates, and reads all NLMLs and gradients back.
 * roofline: the evaluation graph (one launch = `batch` evaluations, each 3 n^2 d + n^3
            algorithmic FP64 flops) against the FP64 tensor (DMMA) peak measured in
            this run with cublasDgemm 8192^3 (MEASURED_PEAKS.json carries no FP64 figure).
@@ -298,12 +298,21 @@ def run_gpu(args):
     value = world * B * K / (dev_ms * 1e-3)
 
     # ---- end to end through the public API with host buffers --------------------------------------
+    # inputs live in PINNED host memory, X in the layout the C ABI (and R) uses: every fit column-major
+    def pinned(a):
+        t = torch.empty(a.shape, dtype=torch.float64, pin_memory=True)
+        v = t.numpy()
+        v[...] = a
+        return t, v
+    keep = [pinned(np.ascontiguousarray(np.transpose(X, (0, 2, 1)))), pinned(y), pinned(ev), pinned(lnc), pinned(pars)]
+    Xp, yp, evp, lncp, parsp = (k[1] for k in keep)
+    fit.set_data(Xp, yp, evp, colmajor=True)          # untimed: registers nothing, only warms the path
     barrier()
     t0 = time.perf_counter()
     for s in range(K):
-        fit.set_data(X, y, ev)
-        fit.set_noise_corr(lnc)
-        f, g = fit.nlml_grad(pars[W + s])
+        fit.set_data(Xp, yp, evp, colmajor=True)
+        fit.set_noise_corr(lncp)
+        f, g = fit.nlml_grad(parsp[W + s])
     torch.cuda.synchronize(device)
     e2e_s = max_over_ranks(time.perf_counter() - t0)
     barrier()

@@ -58,10 +58,15 @@ class Fit:
         self.opts = (cov_form, mean_form, noise_corr, ard_mode) if cov_form != "Matern" else \
             (cov_form, mean_form, noise_corr, ard_mode, int(extra_param))
 
-    def set_data(self, X, y, events=None):
+    def set_data(self, X, y, events=None, colmajor=False):
+        """gps_set_data.  X: n x d (one fit) or [batch, n, d]; with colmajor=True a batch is given the way the ABI
+        (and R) stores it, [batch, d, n] C-contiguous = each fit column-major, and is passed through untouched."""
         if np.ndim(X) == 2:
             X = f64(X)
             n, d = X.shape
+        elif colmajor:
+            X = np.ascontiguousarray(np.asarray(X, dtype=np.float64))
+            _, d, n = X.shape
         else:   # [batch, n, d] -> each problem column-major
             X = np.asarray(X, dtype=np.float64)
             _, n, d = X.shape
