@@ -82,6 +82,7 @@ struct gps_handle_s {
   double* wsc = nullptr;         // [batch][ldmu] k-weights 1/ell_k^2 of the weighted Gram product (hyp_prep_kernel)
   int num_sms = 148;
   int ws_enabled = 1;            // GPS_WS=0: never use the warp-specialised 128 x 128 kernel
+  int fuse_k64 = 1;              // GPS_FUSE64=0: separate K = 64 GEMM between the panels of a leaf pair
   int ws_kmin = 128;             // GPS_WS_KMIN: shortest k-loop given to the persistent kernel
   int front_fused = 1;           // GPS_FRONT=0: never use the fused small-d front end (small_front_kernel)
   int nbig = 256;                // GPS_NBIG: diagonal block of the two-level Cholesky (64 = one-level recursion)
@@ -448,14 +449,14 @@ void enqueue_cov(H* h, const double* Za, int n1, int lda, long long sA, const do
 // latency.  A small cost model (measured: chain ~17 us, panel solve ~1.4 us per 32-row tile and
 // ~5.2 us per 128-row tile, one CTA per SM) picks the tile height RT and the tiles per CTA T that
 // minimise  waves * (chain + T * tile).  +1 CTA per fit publishes L11 / X11.
-void launch_panel(H* h, int e0, int nb, int M, long long* dbg) {
+void launch_panel(H* h, int e0, int nb, int M, long long* dbg, int kprev = 0) {
   const int B = h->batch;
   const int Mr = M > 0 ? M : 1;
   double best = 1e300;
   int best_rt = 32, best_T = 1;
-  for (int rt = 32; rt <= 128; rt += 96) {
+  for (int rt = 32; rt <= (kprev ? 32 : 128); rt += 96) {   // the fused rank-64 pre-update exists for 32-row tiles only
     const int tiles = ceil_div(Mr, rt);
-    const double t_tile = (rt == 32) ? 1.4 : 5.2;
+    const double t_tile = (rt == 32) ? (kprev ? 2.0 : 1.4) : 5.2;
     for (int T = 1; T <= tiles; T++) {
       const long long ctas = (long long)(ceil_div(tiles, T) + 1) * B;
       const double cost = (double)ceil_div((int)ctas, 148) * (17.0 + T * t_tile);
@@ -465,9 +466,11 @@ void launch_panel(H* h, int e0, int nb, int M, long long* dbg) {
   const int tiles = ceil_div(Mr, best_rt);
   dim3 grid(ceil_div(tiles, best_T) + 1, B);
   if (best_rt == 32)
-    panel_kernel<32><<<grid, 256, PANEL_SMEM, h->st>>>(h->Ky, h->L, h->Linv, h->U, h->ld, h->strideM, e0, nb, M, best_T, h->info, dbg);
+    panel_kernel<32><<<grid, 256, kprev ? PANEL_SMEM_FUSED : PANEL_SMEM, h->st>>>(h->Ky, h->L, h->Linv, h->U, h->ld, h->strideM, e0, nb,
+                                                                                    M, best_T, h->info, dbg, kprev);
   else
-    panel_kernel<128><<<grid, 256, PANEL_SMEM, h->st>>>(h->Ky, h->L, h->Linv, h->U, h->ld, h->strideM, e0, nb, M, best_T, h->info, dbg);
+    panel_kernel<128><<<grid, 256, PANEL_SMEM, h->st>>>(h->Ky, h->L, h->Linv, h->U, h->ld, h->strideM, e0, nb, M, best_T, h->info,
+                                                         dbg, 0);
   LAUNCHED(h);
   if (h->pending_join) {   // look-ahead: the rest of the previous trailing update ran beside this panel
     CKV(h, cudaEventRecord(h->ev_join, h->st2));
@@ -490,6 +493,15 @@ void potrf_range(H* h, int j0, int j1, int row_end) {
     // fused: L11 = chol(A11), X11 = L11^-1, L[e1:, e0:e1] = Ky[e1:, e0:e1] * X11'
     int e1 = e0 + nb, M = row_end - e1;
     launch_panel(h, e0, nb, M, nullptr);
+    return;
+  }
+  if (j1 - j0 == 2 && h->fuse_k64 && !h->lookahead && (h->batch < 8 || row_end < h->naug)) {
+    // leaf pair: the second panel applies the first one's rank-64 update itself (panel_kernel, kprev = 64) —
+    // one launch less per pair; for lone fits and inside the diagonal blocks of the two-level scheme, where the
+    // 32-row panel tiles it needs are what the cost model picks anyway
+    potrf_range(h, j0, j0 + 1, row_end);
+    const int e0 = (j0 + 1) * NB, nb = (h->ne - e0 < NB) ? h->ne - e0 : NB;
+    launch_panel(h, e0, nb, row_end - (e0 + nb), nullptr, NB);
     return;
   }
   int mid = j0 + (j1 - j0 + 1) / 2;
@@ -1013,6 +1025,7 @@ int gps_create_batch(int device, int batch, gps_handle* out) {
   if (const char* ev = getenv("GPS_WS_MIN_N")) h->ws_min_n = atoi(ev);
   if (const char* ev = getenv("GPS_FRONT")) h->front_fused = atoi(ev) != 0;
   if (const char* ev = getenv("GPS_WS_KMIN")) h->ws_kmin = atoi(ev);
+  if (const char* ev = getenv("GPS_FUSE64")) h->fuse_k64 = atoi(ev) != 0;
   if (const char* ev = getenv("GPS_NBIG")) {
     const int v = atoi(ev);
     if (v == 64 || v == 128 || v == 256 || v == 512) {
@@ -1033,7 +1046,7 @@ int gps_create_batch(int device, int batch, gps_handle* out) {
     delete h;
     return fail(nullptr, GPS_ERR_CUDA, "gps_create: " + m);
   }
-  e = cudaFuncSetAttribute(panel_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PANEL_SMEM);
+  e = cudaFuncSetAttribute(panel_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PANEL_SMEM_FUSED);
   if (e == cudaSuccess)
     e = cudaFuncSetAttribute(panel_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PANEL_SMEM);
   if (e != cudaSuccess) {

@@ -440,6 +440,8 @@ constexpr int PX = NB + 4;     // sX row-major:    sX[k*PX + c] = X11[k][c]
 constexpr int PA = 128 + 4;    // sA: sA[k*PA + m] = A21[m][k]
 constexpr int PT = 32 + 4;     // sT column-major: sT[n*PT + m]
 constexpr size_t PANEL_SMEM = (size_t)(NB * PS + NB * PX + NB * PA + 32 * PT + NB) * sizeof(double);
+// + the 64 x 64 block of the previous block column, for the fused rank-64 pre-update (panel_kernel<32>, kprev = 64)
+constexpr size_t PANEL_SMEM_FUSED = PANEL_SMEM + (size_t)(NB * PS) * sizeof(double);
 
 __device__ __forceinline__ void dmma_acc(double& d0, double& d1, double a_mma, double b_mma) {
   asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
@@ -572,7 +574,11 @@ __global__ void __launch_bounds__(256) panel_kernel(const double* __restrict__ A
                                                     double* __restrict__ Linv, double* __restrict__ Uinv, int ld,
                                                     long long stride, int e0,
                                                     int nb, int M, int T, int* __restrict__ info,
-                                                    long long* __restrict__ dbg) {
+                                                    long long* __restrict__ dbg, int kprev) {
+  // kprev = 64 (RT = 32 only): the rank-64 update from the PREVIOUS block column is still pending for this one
+  // (the second leaf of a leaf pair of the recursion).  It is applied here — to the diagonal block and to every
+  // row tile, on DMMA from shared memory, before they are used — instead of by a separate K = 64 GEMM launch
+  // over the same rows: a lone fit's launches are latency-bound and this removes one in four of its Cholesky's.
   extern __shared__ __align__(16) double panel_smem[];
   int dbg_i = 0;
 #define PANEL_STAMP() do { if (dbg && threadIdx.x == 0 && blockIdx.x == 0 && blockIdx.y == 0) dbg[dbg_i++] = clock64(); } while (0)
@@ -582,9 +588,12 @@ __global__ void __launch_bounds__(256) panel_kernel(const double* __restrict__ A
   double* sA = sX + NB * PX;
   double* sT = sA + NB * PA;
   double* invd = sT + 32 * PT;
+  double* sLd = invd + NB;                       // [k][r] = L[e0 + r][e0 - 64 + k]   (kprev only; PS stride)
+  double* sLt = sA + 64;                         // [k][m] = L[row0 + m][e0 - 64 + k], beside the A21 tile in sA's rows (RT = 32)
   const int tid = threadIdx.x, cta = blockIdx.x, b = blockIdx.y;
   const int warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
   const double* Ab = A + (size_t)b * stride;
+  const double* Lprev = L + (size_t)b * stride + (size_t)(e0 - kprev) * ld;   // columns e0-64 .. e0-1 of L (kprev only)
   const int e1 = e0 + nb;
   const bool publisher = (cta == (int)gridDim.x - 1);
   int row0 = e1 + cta * T * RT;                 // first panel row of this CTA
@@ -598,6 +607,15 @@ __global__ void __launch_bounds__(256) panel_kernel(const double* __restrict__ A
     unsigned dst = (unsigned)__cvta_generic_to_shared(S + col * PS + rc);
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(dst), "l"(src), "r"(valid * 8));
   }
+  if (RT == 32 && kprev) {
+    for (int c = tid; c < NB * 32; c += 256) {
+      int k = c >> 5, rc = (c & 31) * 2;
+      int valid = min(max(nb - rc, 0), 2);
+      const double* src = valid ? (Lprev + (size_t)(e0 + rc) + (size_t)k * ld) : Lprev;
+      unsigned dst = (unsigned)__cvta_generic_to_shared(sLd + k * PS + rc);
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(dst), "l"(src), "r"(valid * 8));
+    }
+  }
   asm volatile("cp.async.commit_group;\n" ::);
   auto load_a21 = [&]() {
     for (int c = tid; c < NB * (RT / 2); c += 256) {
@@ -606,6 +624,12 @@ __global__ void __launch_bounds__(256) panel_kernel(const double* __restrict__ A
       const double* src = valid ? (Ab + (size_t)(row0 + mc) + (size_t)(e0 + k) * ld) : Ab;
       unsigned dst = (unsigned)__cvta_generic_to_shared(sA + k * PA + mc);
       asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(dst), "l"(src), "r"(valid * 8));
+      if (RT == 32 && kprev) {   // the same rows of the previous block column (all 64 columns exist)
+        int v2 = min(max(rows - mc, 0), 2);
+        const double* src2 = v2 ? (Lprev + (size_t)(row0 + mc) + (size_t)k * ld) : Lprev;
+        unsigned dst2 = (unsigned)__cvta_generic_to_shared(sLt + k * PA + mc);
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(dst2), "l"(src2), "r"(v2 * 8));
+      }
     }
     asm volatile("cp.async.commit_group;\n" ::);
   };
@@ -613,6 +637,24 @@ __global__ void __launch_bounds__(256) panel_kernel(const double* __restrict__ A
   for (int i = tid; i < NB * PX; i += 256) sX[i] = 0.0;
   asm volatile("cp.async.wait_group 1;\n" ::);     // A11 has landed (A21 may still be in flight)
   __syncthreads();
+  if (RT == 32 && kprev) {   // A11 -= Ld Ld'  (lower 8 x 8 tiles over the 8 warps; rows >= nb of Ld are zero)
+    int tile = 0;
+#pragma unroll 1
+    for (int mi = 0; mi < NB / 8; mi++)
+#pragma unroll 1
+      for (int ni = 0; ni <= mi; ni++, tile++) {
+        if ((tile & 7) != warp) continue;
+        const int m0 = 8 * mi, n0 = 8 * ni;
+        double2 c = *reinterpret_cast<double2*>(S + (n0 + g) * PS + m0 + 2 * t);
+#pragma unroll
+        for (int ks = 0; ks < NB / 4; ks++) {
+          const int k = 4 * ks + t;
+          dmma_acc(c.x, c.y, -sLd[k * PS + n0 + g], sLd[k * PS + m0 + g]);
+        }
+        *reinterpret_cast<double2*>(S + (n0 + g) * PS + m0 + 2 * t) = c;
+      }
+    __syncthreads();
+  }
   if (tid >= nb && tid < NB) S[tid * PS + tid] = 1.0;   // identity padding of a partial block
   __syncthreads();
   PANEL_STAMP();
@@ -702,6 +744,20 @@ __global__ void __launch_bounds__(256) panel_kernel(const double* __restrict__ A
       __syncthreads();
     } else if (rows <= 0) {
       break;
+    }
+    if (RT == 32 && kprev) {   // A21 tile -= Lt Ld'  (32 x 64 outputs = 32 8 x 8 tiles, four per warp)
+#pragma unroll 1
+      for (int q = 0; q < 4; q++) {
+        const int tl = warp * 4 + q, m0 = 8 * (tl & 3), n0 = 8 * (tl >> 2);
+        double2 c = *reinterpret_cast<double2*>(sA + (n0 + g) * PA + m0 + 2 * t);
+#pragma unroll
+        for (int ks = 0; ks < NB / 4; ks++) {
+          const int k = 4 * ks + t;
+          dmma_acc(c.x, c.y, -sLd[k * PS + n0 + g], sLt[k * PA + m0 + g]);
+        }
+        *reinterpret_cast<double2*>(sA + (n0 + g) * PA + m0 + 2 * t) = c;
+      }
+      __syncthreads();
     }
     double acc[FMT][4][2];
 #pragma unroll
