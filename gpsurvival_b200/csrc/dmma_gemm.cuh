@@ -494,6 +494,10 @@ struct EpiColDot {
 // kept behind GPS_TILE=2 / GPS_LARGE_MIN_DIM for experiments only.
 using CfgLarge = TileCfg<128, 128, 16, 2, 4, 4>;
 using CfgS3 = TileCfg<64, 64, 16, 2, 2, 3>;
+// covariance from very few features (K <= 32, e.g. C2's d = 20): the k-loop is two steps and the kernel is all epilogue
+// (exp per element), latency-bound at the 16 warps/SM the 64 x 64 tile's 124 registers allow; 32 x 32 tiles of four
+// 16 x 16 warps need ~60 registers and run 8+ CTAs per SM
+using CfgTiny = TileCfg<32, 32, 16, 2, 2, 2>;
 
 template <class Cfg, bool A_KC, bool B_KC, class Epi>
 cudaError_t launch_gemm(const GemmParams& p, const Epi& epi, int batch, cudaStream_t st) {

@@ -384,7 +384,8 @@ using WsCfg64 = WsCfg<64, 64, 16, 2, 2, 3, 3>;        // 4 consumer warps of 32 
 using WsCfg80 = WsCfg<80, 80, 16, 2, 2, 4, 2>;        // 4 consumer warps of 40 x 40, 4 stages, 86 KB smem
 using WsCfg96 = WsCfg<96, 96, 16, 2, 4, 6, 1>;         // 8 consumer warps of 48 x 24: row counts just under a multiple of 96 (n = 285)
 using WsCfg96x64 = WsCfg<96, 64, 16, 2, 2, 3, 3>;     // 4 consumer warps of 48 x 32, 3 CTAs/SM: the same rows against a wide N (M * Xaug, d = 10^4)
-using WsCfgN32 = WsCfg<128, 32, 16, 4, 1, 4, 3>;      // narrow outputs (N <= 32, e.g. M * Xaug with d = 20): 4 warps of 32 x 32
+using WsCfgN32 = WsCfg<128, 32, 16, 4, 1, 4, 3>;      // narrow outputs (N <= 32): 4 warps of 32 x 32
+using WsCfgN24 = WsCfg<128, 24, 16, 4, 1, 4, 3>;      // N <= 24 (M * Xaug with d = 20: 21 columns): 4 warps of 32 x 24
 
 // `sched`: two ints in device memory, zero before the first launch that uses them (the kernel re-arms them);
 // launches that may overlap in time must not share them.

@@ -24,6 +24,7 @@
 #include <algorithm>
 #include <cmath>
 #include <string>
+#include <type_traits>
 #include <vector>
 
 #include "dmma_gemm.cuh"
@@ -82,6 +83,7 @@ struct gps_handle_s {
   double* wsc = nullptr;         // [batch][ldmu] k-weights 1/ell_k^2 of the weighted Gram product (hyp_prep_kernel)
   int num_sms = 148;
   int ws_enabled = 1;            // GPS_WS=0: never use the warp-specialised 128 x 128 kernel
+  int tiny_cov = 1;              // GPS_TINYCOV=0: 64 x 64 tiles for the K <= 32 covariance too
   int fuse_k64 = 1;              // GPS_FUSE64=0: separate K = 64 GEMM between the panels of a leaf pair
   int ws_kmin = 128;             // GPS_WS_KMIN: shortest k-loop given to the persistent kernel
   int front_fused = 1;           // GPS_FRONT=0: never use the fused small-d front end (small_front_kernel)
@@ -261,12 +263,12 @@ bool use_ws128(const H* h, const GemmParams& p) {
 }
 
 // Tile configuration of an "NT" GEMM: 128 / 80 / 64 = warp-specialised persistent kernel with that square
-// tile, 32 = its 128 x 32 tile for narrow outputs (dmma_ws.cuh), 0 = the 64 x 64 cp.async kernel (short k-loops: K < 128, where a persistent tile's
+// tile, 32 / 24 = its 128 x 32 / 128 x 24 tiles for narrow outputs (dmma_ws.cuh), 0 = the 64 x 64 cp.async kernel (short k-loops: K < 128, where a persistent tile's
 // un-overlapped epilogue dominates; and every developer override).
 int pick_nt_tile(const H* h, const GemmParams& p) {
   if (h->force_tile >= 0 || !h->ws_enabled || !h->ws_sched || p.K < h->ws_kmin) return 0;
   if (use_ws128(h, p)) return 128;
-  if (p.N <= 32 && !p.lower && (long long)ceil_div(p.M, 128) * h->batch * p.nodes * p.ksplit >= h->num_sms) return 32;
+  if (p.N <= 32 && !p.lower && (long long)ceil_div(p.M, 128) * h->batch * p.nodes * p.ksplit >= h->num_sms) return p.N <= 24 ? 24 : 32;
   {   // a launch that cannot even fill the persistent grid once (a lone mid-size fit) is latency-bound: the plain
       // kernel starts faster (no barrier set-up, no scheduler round trip) — measured 1.87 vs 2.02 ms on a lone C2 fit
     ws::TileEnum te;
@@ -293,7 +295,7 @@ int pick_nt_tile(const H* h, const GemmParams& p) {
   return 64;
 }
 inline int tile_bm(const H* h, int code) {   // rows of the tile a pick_nt_tile() code stands for
-  return code == 128 || code == 32 ? 128 : code == 80 ? 80 : code == 96 || code == 97 ? 96 : code == 64 ? 64
+  return code == 128 || code == 32 || code == 24 ? 128 : code == 80 ? 80 : code == 96 || code == 97 ? 96 : code == 64 ? 64
          : (h->force_tile == 2 ? 128 : 64);
 }
 
@@ -310,6 +312,8 @@ void gemm(H* h, const GemmParams& p, const Epi& epi) {
         e = launch_gemm_ws<WsCfg80, false, false, Epi>(p, epi, h->batch, h->num_sms, sched, h->cur);
       else if (tile == 32)
         e = launch_gemm_ws<WsCfgN32, false, false, Epi>(p, epi, h->batch, h->num_sms, sched, h->cur);
+      else if (tile == 24)
+        e = launch_gemm_ws<WsCfgN24, false, false, Epi>(p, epi, h->batch, h->num_sms, sched, h->cur);
       else if (tile == 96)
         e = launch_gemm_ws<WsCfg96, false, false, Epi>(p, epi, h->batch, h->num_sms, sched, h->cur);
       else if (tile == 97)
@@ -330,7 +334,12 @@ void gemm(H* h, const GemmParams& p, const Epi& epi) {
   // 64 x 64 x 16 tile, 4 warps, 3-stage cp.async pipeline (4 CTAs/SM); CfgLarge only by developer override
   int choice = (tl >= need && p.N >= 96 && p.M >= h->large_min_dim && p.N >= h->large_min_dim) ? 2 : 3;
   if (h->force_tile >= 0) choice = h->force_tile;
-  if (choice == 2)
+  bool tiny = false;
+  if constexpr (std::is_same<Epi, EpiCov>::value && !A_KC && !B_KC) tiny = (p.K <= 32 && h->force_tile < 0 && h->tiny_cov);
+  if (tiny) {
+    if constexpr (std::is_same<Epi, EpiCov>::value && !A_KC && !B_KC)
+      e = launch_gemm<CfgTiny, A_KC, B_KC, Epi>(p, epi, h->batch, h->cur);
+  } else if (choice == 2)
     e = launch_gemm<CfgLarge, A_KC, B_KC, Epi>(p, epi, h->batch, h->cur);
   else
     e = launch_gemm<CfgS3, A_KC, B_KC, Epi>(p, epi, h->batch, h->cur);
@@ -351,7 +360,7 @@ void gemm_ks(H* h, const GemmParams& p, const EpiPlain& epi) {
     e = launch_gemm_ws<WsCfg96, false, false, EpiPlain, true>(p, epi, h->batch, h->num_sms, sched, h->cur);
   else if (tile == 97)
     e = launch_gemm_ws<WsCfg96x64, false, false, EpiPlain, true>(p, epi, h->batch, h->num_sms, sched, h->cur);
-  else if (tile == 32)
+  else if (tile == 32 || tile == 24)
     e = launch_gemm_ws<WsCfgN32, false, false, EpiPlain, true>(p, epi, h->batch, h->num_sms, sched, h->cur);
   else
     e = launch_gemm_ws<WsCfg64, false, false, EpiPlain, true>(p, epi, h->batch, h->num_sms, sched, h->cur);
@@ -395,8 +404,8 @@ int pick_gram_ksplit(const H* h, int n1, int n2, int d, bool sym) {
   H hv = *h;
   hv.batch = per_launch;
   const int code = pick_nt_tile(&hv, probe);
-  const int bm = tile_bm(h, code), bn = (code == 97) ? 64 : (code == 32 ? 32 : bm);
-  const int cps = (code == 64 || code == 97 || code == 32) ? 3 : (code == 80 ? 2 : (code == 0 ? 4 : 1));
+  const int bm = tile_bm(h, code), bn = (code == 97) ? 64 : (code == 32 ? 32 : (code == 24 ? 24 : bm));
+  const int cps = (code == 64 || code == 97 || code == 32 || code == 24) ? 3 : (code == 80 ? 2 : (code == 0 ? 4 : 1));
   ws::TileEnum te;
   te.init(n1, n2, bm, bn, (sym && bm == bn) ? 1 : 0, 0);
   const long long tiles = (long long)te.per_z * per_launch;
@@ -1026,6 +1035,7 @@ int gps_create_batch(int device, int batch, gps_handle* out) {
   if (const char* ev = getenv("GPS_FRONT")) h->front_fused = atoi(ev) != 0;
   if (const char* ev = getenv("GPS_WS_KMIN")) h->ws_kmin = atoi(ev);
   if (const char* ev = getenv("GPS_FUSE64")) h->fuse_k64 = atoi(ev) != 0;
+  if (const char* ev = getenv("GPS_TINYCOV")) h->tiny_cov = atoi(ev) != 0;
   if (const char* ev = getenv("GPS_NBIG")) {
     const int v = atoi(ev);
     if (v == 64 || v == 128 || v == 256 || v == 512) {
