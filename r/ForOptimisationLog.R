@@ -8,8 +8,10 @@ ForOptimisationLog <- function(logHyp,trainingData,trainingTargets,trainingEvent
   logMarLik <- tryCatch(.Call('gps_r_nlml', h, as.double(logHyp)),
     error = function(e){
       if(!grepl('^gps_not_pd', conditionMessage(e))) stop(e)
-      # Reference fallback (ForOptimisationLog.R:43-51): nearest positive-definite matrix, on the host.
-      stop('Error: Covariance matrix is not positive definite. Generation of nearby p.d. matrix failed.')
+      # Reference fallback (ForOptimisationLog.R:43-51): nearest positive-definite matrix.  Rare, so it stays on the
+      # host in R (Matrix::nearPD = repeated symmetric eigen-decompositions); the covariance still comes from the GPU.
+      GpsNlmlNearPD(logHyp,trainingData,trainingTargets,trainingEvents,meanFuncForm,dimension,extraParam,covFuncForm,
+                    nSamples,noiseCorr,logHypNoiseCorrection)
     })
   return(logMarLik)
 }

@@ -39,3 +39,34 @@ GpsBind <- function(trainingData, trainingTargets, trainingEvents, covFuncForm, 
   }
   .gps$handle
 }
+
+#-------------------------------------------------------------------------------------------------#
+# GpsNlmlNearPD — what ForOptimisationLog.R:43-51,54-63 does when chol() fails: Matrix::nearPD on the
+# covariance (+ noise), Cholesky of the nearby matrix, the two triangular solves, the likelihood.
+# Called only after libgpsurv reported GPS_ERR_NOT_PD for this logHyp.  NOT RUN IN THE BUILD IMAGE.
+#-------------------------------------------------------------------------------------------------#
+GpsNlmlNearPD <- function(logHyp,trainingData,trainingTargets,trainingEvents,meanFuncForm,dimension,extraParam,covFuncForm,
+                          nSamples,noiseCorr,logHypNoiseCorrection){
+  library(Matrix)
+  logHyp <- as.matrix(logHyp)
+  if(noiseCorr=='noiseCorrLearned'){                                     # ForOptimisationLog.R:9-12: last entry is log sc2
+    logHypNoiseCorrection <- logHyp[nrow(logHyp),1]
+    logHyp                <- logHyp[-nrow(logHyp),,drop=FALSE]
+  }
+  nLength <- if(covFuncForm=='ARD') dimension else 1
+  sn2     <- exp(logHyp[1,1]); sf2 <- exp(logHyp[2,1]); ell <- exp(logHyp[3:(2+nLength),1])
+  meanHyp <- if(meanFuncForm=='Zero') rep(0,dimension+1) else logHyp[(nrow(logHyp)-dimension):nrow(logHyp),1]
+  m       <- MeanFunc(meanHyp,trainingData,meanFuncForm,nSamples)
+  Ky      <- CovFunc(trainingData,trainingData,trainingData,trainingTargets,extraParam,sf2,ell,covFuncForm) + diag(sn2,nSamples,nSamples)
+  if(noiseCorr=='noiseCorrVec'|noiseCorr=='noiseCorrLearned'){
+    corr                    <- rep(0,nSamples)
+    corr[trainingEvents==0] <- exp(logHypNoiseCorrection)
+    Ky                      <- Ky + diag(corr,nSamples,nSamples)
+  }
+  near <- try(nearPD(Ky),silent=TRUE)
+  if(inherits(near,'try-error') || !near$converged) stop('Error: Covariance matrix is not positive definite. Generation of nearby p.d. matrix failed.')
+  L     <- t(chol(as.matrix(near$mat)))
+  r     <- as.numeric(trainingTargets) - as.numeric(m)
+  alpha <- backsolve(t(L), forwardsolve(L, r))
+  matrix(0.5*sum(r*alpha) + sum(log(diag(L))) + (nSamples/2)*log(2*pi), 1, 1)
+}
