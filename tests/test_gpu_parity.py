@@ -770,3 +770,27 @@ def test_fused_front_end_agrees_with_gram_route():
     fo = orc.nlml(par[0], X[0], y[0], ev[0], **kw)
     assert abs(f[0] - fo) <= TOL_NLML * abs(fo)
     assert relmax(g[0], orc.nlml_grad(par[0], X[0], y[0], ev[0], **kw)) <= TOL_GRAD
+
+
+def test_bench_line_carries_the_contract_keys():
+    """python bench.py (small batch, few steps): one JSON line on stdout with every key of the measurement contract."""
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    res = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--steps", "3", "--warmup", "3", "--batch", "4"],
+                         capture_output=True, text=True, timeout=900)
+    assert res.returncode == 0, res.stderr[-2000:]
+    lines = [ln for ln in res.stdout.strip().splitlines() if ln.startswith("{")]
+    assert len(lines) == 1
+    b = json.loads(lines[0])
+    for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline",
+              "dtype", "data", "config", "e2e", "gpu_launches", "clocks", "roofline", "cpu_baseline"):
+        assert k in b, k
+    assert b["n_gpus"] == 1 and b["steps"] == 3 and b["dtype"] == "f64" and b["scaling"] == "weak" and b["vs_baseline"] is None
+    assert b["gpu_launches"] > 0 and b["value"] > 0 and b["e2e"]["value"] > 0
+    assert b["e2e"]["h2d_bytes_per_step"] > 0 and b["e2e"]["d2h_bytes_per_step"] > 0
+    for k in ("bound", "achieved", "peak", "unit", "frac", "traffic"):
+        assert k in b["roofline"], k
+    for k in ("value", "unit", "cores", "kind", "sample"):
+        assert k in b["cpu_baseline"], k
+    assert b["parity_vs_oracle"]["nlml_rel"] <= TOL_NLML and b["parity_vs_oracle"]["grad_rel"] <= TOL_GRAD

@@ -101,3 +101,23 @@ def test_r_glue_type_checks_against_the_abi():
     assert table and len(table) == len(defs)
     for name, fn, nargs in table:
         assert name == fn and defs[fn] == int(nargs), (name, defs.get(fn), nargs)
+
+
+def test_reference_arm_prints_the_contract_line():
+    """bench.py --impl reference: the reference algorithm (numpy restatement) on the host cores, one JSON line with
+    the keys the driver reads."""
+    import json
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    res = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "1"],
+                         capture_output=True, text=True, timeout=600)
+    assert res.returncode == 0, res.stderr[-2000:]
+    lines = [ln for ln in res.stdout.strip().splitlines() if ln.startswith("{")]
+    assert len(lines) == 1
+    line = json.loads(lines[0])
+    assert line["impl"] == "reference" and line["metric"] == "gp_logml_grad_evals_per_sec" and line["unit"] == "evals/s"
+    assert line["value"] > 0 and line["higher_is_better"] is True and line["dtype"] == "f64"
+    assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
+    assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["d2h_bytes_per_step"] == 0
+    assert "workload" in line["config"]
