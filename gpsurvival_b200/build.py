@@ -13,8 +13,15 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libgpsurv.so")
 SOURCES = [os.path.join(CSRC, "gpsurv.cu")]
-DEPS = SOURCES + [os.path.join(CSRC, f) for f in ("dmma_gemm.cuh", "kernels.cuh")] + [
-    os.path.join(os.path.dirname(HERE), "include", "gpsurv.h")]
+
+
+def deps():
+    """Everything the library is built from: every file under csrc/ (gpsurv.cu includes all the .cuh files) and
+    the public header — a stale .so must never travel to the GPU box."""
+    out = [os.path.join(os.path.dirname(HERE), "include", "gpsurv.h"), os.path.abspath(__file__)]
+    for root, _, files in os.walk(CSRC):
+        out += [os.path.join(root, f) for f in files if f.endswith((".cu", ".cuh", ".h", ".cpp"))]
+    return out
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
@@ -26,7 +33,7 @@ def needs_build() -> bool:
     if not os.path.exists(LIB):
         return True
     t = os.path.getmtime(LIB)
-    return any(os.path.getmtime(f) > t for f in DEPS if os.path.exists(f))
+    return any(os.path.getmtime(f) > t for f in deps() if os.path.exists(f))
 
 
 def build_lib(force: bool = False, verbose: bool = False) -> str:

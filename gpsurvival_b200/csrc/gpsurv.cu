@@ -1021,7 +1021,7 @@ int gps_create_batch(int device, int batch, gps_handle* out) {
   cudaDeviceProp prop;
   e = cudaGetDeviceProperties(&prop, device);
   if (e != cudaSuccess) return fail(nullptr, GPS_ERR_CUDA, cudaGetErrorString(e));
-  if (prop.major != 10) {
+  if (prop.major != 10 || prop.minor != 0) {   // sm_100a code is arch-specific: no PTX fallback for sm_103 and later
     char b[256];
     snprintf(b, sizeof b, "device %d is sm_%d%d; libgpsurv is built for sm_100a only", device, prop.major, prop.minor);
     return fail(nullptr, GPS_ERR_CUDA, b);
@@ -1053,14 +1053,14 @@ int gps_create_batch(int device, int batch, gps_handle* out) {
       cudaEventCreate(&h->ev0) != cudaSuccess || cudaEventCreate(&h->ev1) != cudaSuccess ||
       cudaMallocHost((void**)&h->pin_info, sizeof(int) * batch) != cudaSuccess) {
     std::string m = cudaGetErrorString(cudaGetLastError());
-    delete h;
+    gps_destroy(h);
     return fail(nullptr, GPS_ERR_CUDA, "gps_create: " + m);
   }
   e = cudaFuncSetAttribute(panel_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PANEL_SMEM_FUSED);
   if (e == cudaSuccess)
     e = cudaFuncSetAttribute(panel_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PANEL_SMEM);
   if (e != cudaSuccess) {
-    delete h;
+    gps_destroy(h);
     return fail(nullptr, GPS_ERR_CUDA, std::string("gps_create: ") + cudaGetErrorString(e));
   }
   h->cur = h->st;
@@ -1068,7 +1068,7 @@ int gps_create_batch(int device, int batch, gps_handle* out) {
       cudaMemsetAsync(h->ws_sched, 0, sizeof(int) * 2 * WS_SLOTS * H::MAX_GROUPS, h->st) != cudaSuccess ||
       cudaStreamSynchronize(h->st) != cudaSuccess) {
     std::string m = cudaGetErrorString(cudaGetLastError());
-    delete h;
+    gps_destroy(h);
     return fail(nullptr, GPS_ERR_CUDA, "gps_create: " + m);
   }
   if (const char* ev = getenv("GPS_LOOKAHEAD")) h->lookahead = atoi(ev) != 0;
@@ -1084,7 +1084,7 @@ int gps_create_batch(int device, int batch, gps_handle* out) {
           cudaEventCreateWithFlags(&h->ev_gjoin[g], cudaEventDisableTiming) == cudaSuccess;
   if (!okg) {
     std::string m = cudaGetErrorString(cudaGetLastError());
-    delete h;
+    gps_destroy(h);
     return fail(nullptr, GPS_ERR_CUDA, "gps_create: " + m);
   }
   *out = h;
