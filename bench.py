@@ -275,7 +275,7 @@ def run_reference(args):
     X, y, ev, lnc, par0 = workload(0)
     cores = host_cores()
     blas = pin_blas_threads(cores)
-    pars = step_pars(par0, args.steps + args.warmup + 1, 7)
+    pars = step_pars(par0, max(args.steps, 3) + args.warmup + 1, 7)
     t_w = time.perf_counter()
     for w in range(max(args.warmup, 1)):
         cpu_eval(pars[w], X, y, ev, lnc)

@@ -485,6 +485,100 @@ struct EpiColDot {
   }
 };
 
+// W o K fused into the epilogue of Kinv = U U' (OptimisationGradientLog.R:51-53 in W-form; north_star item 4):
+//   W = a a' - Kinv,  M = W o K,  wdiag = diag(W),  rowsum(M) as fixed-order per-column-block partials.
+// Kinv itself is never written (it was only ever re-read to form M): one n x n write, one n x n read and one launch
+// per evaluation less than the separate wk_kernel pass.  The product runs over LOWER tiles only (BM == BN):
+//   * an off-diagonal tile (m0 > n0) holds M[m, n] for its rows/columns and, by symmetry, M[n, m]: both are stored,
+//     its row sums go to rs_part[col block][m] and its column sums to rs_part[row block][n];
+//   * a diagonal tile was computed in full (both halves): every entry is stored once, row sums only.
+// Every (row block, column block) pair of rs_part is therefore written exactly once, without atomics.
+struct EpiWK {
+  const double* K;        // noise-free covariance, lower triangle valid, ld = ldk
+  double* Mout;           // full symmetric M (both halves), same layout
+  int ldk;
+  long long strideK;
+  const double* alpha;    // [batch][2 * ldn]: the right-hand side the reference's quadratic forms use
+  double* wdiag;          // [batch][ldn]
+  double* rs_part;        // [batch][nblk][ldn]
+  int ldn, nblk, nvalid;  // nvalid = n (rows/columns >= n are identity padding and are skipped)
+  template <class Cfg>
+  __device__ __forceinline__ void operator()(const GemmParams& p, AccTile<Cfg>& a, double* smem) const {
+    // (lower-tile products only ever run on square tiles; the non-square configurations merely have to compile)
+    const double* __restrict__ Kb = K + (size_t)a.batch * strideK;
+    double* __restrict__ Mb = Mout + (size_t)a.batch * strideK;
+    const double* __restrict__ al = alpha + (size_t)a.batch * 2 * ldn;
+    const bool diag = (a.m0 == a.n0);
+    double rsum[Cfg::FM][2], csum[Cfg::FN];
+#pragma unroll
+    for (int i = 0; i < Cfg::FM; i++) rsum[i][0] = rsum[i][1] = 0.0;
+#pragma unroll
+    for (int j = 0; j < Cfg::FN; j++) {
+      const int n = a.n_base + 8 * j;
+      const double an = (n < nvalid) ? al[n] : 0.0;
+      double cs = 0.0;
+#pragma unroll
+      for (int i = 0; i < Cfg::FM; i++) {
+#pragma unroll
+        for (int e = 0; e < 2; e++) {
+          const int m = a.m_base + 8 * i + e;
+          if (m >= nvalid || n >= nvalid) continue;
+          const int r = m > n ? m : n, c = m > n ? n : m;
+          const double w = al[m] * an - a.v[i][j][e];
+          const double mv = w * Kb[(size_t)r + (size_t)c * ldk];
+          Mb[(size_t)m + (size_t)n * ldk] = mv;
+          if (!diag) Mb[(size_t)n + (size_t)m * ldk] = mv;
+          if (m == n) wdiag[(size_t)a.batch * ldn + m] = w;
+          rsum[i][e] += mv;
+          cs += mv;
+        }
+      }
+      csum[j] = cs;
+    }
+    // row sums: over the 8 lanes (g) that hold the other columns of the same rows, then over the WARPS_N warps
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int wmi = warp % Cfg::WARPS_M, wni = warp / Cfg::WARPS_M;
+    double* rowp = smem;                               // [WARPS_N][BM]
+    double* colp = smem + Cfg::WARPS_N * Cfg::BM;      // [WARPS_M][BN]
+#pragma unroll
+    for (int i = 0; i < Cfg::FM; i++)
+#pragma unroll
+      for (int e = 0; e < 2; e++) {
+        double v = rsum[i][e];
+        v += __shfl_xor_sync(0xffffffffu, v, 4);
+        v += __shfl_xor_sync(0xffffffffu, v, 8);
+        v += __shfl_xor_sync(0xffffffffu, v, 16);
+        if ((lane >> 2) == 0) rowp[wni * Cfg::BM + wmi * Cfg::WM + 8 * i + 2 * (lane & 3) + e] = v;
+      }
+#pragma unroll
+    for (int j = 0; j < Cfg::FN; j++) {
+      double v = csum[j];
+      v += __shfl_xor_sync(0xffffffffu, v, 1);
+      v += __shfl_xor_sync(0xffffffffu, v, 2);
+      if ((lane & 3) == 0) colp[wmi * Cfg::BN + wni * Cfg::WN + 8 * j + (lane >> 2)] = v;
+    }
+    Cfg::sync();
+    double* rp = rs_part + (size_t)a.batch * nblk * ldn;
+    const int ti = a.m0 / Cfg::BM, tj = a.n0 / Cfg::BN;
+    for (int c = threadIdx.x; c < Cfg::BM; c += Cfg::NT) {
+      const int m = a.m0 + c;
+      if (m < nvalid) {
+        double sr = 0.0;
+#pragma unroll
+        for (int w = 0; w < Cfg::WARPS_N; w++) sr += rowp[w * Cfg::BM + c];
+        rp[(size_t)tj * ldn + m] = sr;
+      }
+      const int n = a.n0 + c;
+      if (!diag && n < nvalid) {
+        double sc = 0.0;
+#pragma unroll
+        for (int w = 0; w < Cfg::WARPS_M; w++) sc += colp[w * Cfg::BN + c];
+        rp[(size_t)ti * ldn + n] = sc;
+      }
+    }
+  }
+};
+
 // ---------------------------------------------------------------------------------------
 // Launch helper
 // ---------------------------------------------------------------------------------------

@@ -164,7 +164,9 @@ struct WsSmem {
   static constexpr int B_ROWS = B_KC ? Cfg::BN : Cfg::BK;
   static constexpr int A_STAGE = A_ROWS * LDA;
   static constexpr int B_STAGE = B_ROWS * LDB;
-  static constexpr int SCRATCH = 2 * Cfg::WARPS_M * Cfg::BN;   // doubles, for epilogues (EpiColDot: two [WARPS_M][BN] arrays)
+  // doubles, for epilogues (EpiColDot: two [WARPS_M][BN] arrays; EpiWK: [WARPS_N][BM] + [WARPS_M][BN])
+  static constexpr int SCRATCH_A = 2 * Cfg::WARPS_M * Cfg::BN, SCRATCH_B = Cfg::WARPS_N * Cfg::BM + Cfg::WARPS_M * Cfg::BN;
+  static constexpr int SCRATCH = SCRATCH_A > SCRATCH_B ? SCRATCH_A : SCRATCH_B;
   static constexpr int WSC = Cfg::STAGES * Cfg::BK;        // doubles, per-stage k-weights (KS kernels)
   static constexpr size_t BYTES = ((size_t)Cfg::STAGES * (A_STAGE + B_STAGE) + SCRATCH + WSC) * sizeof(double) +
                                   2 * Cfg::STAGES * 8 + Cfg::STAGES * sizeof(int);

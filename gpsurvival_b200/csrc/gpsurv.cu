@@ -87,6 +87,7 @@ struct gps_handle_s {
   int fuse_k64 = 1;              // GPS_FUSE64=0: separate K = 64 GEMM between the panels of a leaf pair
   int ws_kmin = 128;             // GPS_WS_KMIN: shortest k-loop given to the persistent kernel
   int front_fused = 1;           // GPS_FRONT=0: never use the fused small-d front end (small_front_kernel)
+  int fuse_wk = 1;               // GPS_FUSEWK=0: separate wk_kernel pass after Kinv = U U' (always so for Matern gradients)
   int nbig = 256;                // GPS_NBIG: diagonal block of the two-level Cholesky (64 = one-level recursion)
   bool nbig_forced = false;
   int ws_min_tiles = 296;        // GPS_WS_MIN: minimum number of 128 x 128 tiles in a launch
@@ -139,6 +140,9 @@ struct gps_handle_s {
   double last_ms = 0.0;
   int last_pivot = 0;
   std::vector<int> pivots;      // per-fit failing pivot of the last evaluation (0 = factorised)
+  bool tolerate_not_pd = false; // inside gps_fit_batch: a fit that fails to factorise is dropped (NaN outputs, per-fit status),
+                                // the others go on — what the reference loses on such a fit is that one fit
+  std::vector<int> fit_status;  // per-fit status of the last gps_fit_batch (GPS_OK / GPS_ERR_NOT_PD)
   int force_tile = -1;          // developer override of the GEMM tile config (GPS_TILE=2: 128 x 128, else 64 x 64)
   int large_min_dim = 1 << 30;  // 128 x 128 tiles only when both M and N reach this (GPS_LARGE_MIN_DIM); measured:
                                 // the 4-warp 64 x 64 tile (3 CTAs/SM) wins at every size up to 8192^3, alone and batched
@@ -731,19 +735,33 @@ void enqueue_kinv(H* h) {   // Kinv = Linv' * Linv = U * U'  (lower tiles; k >= 
 void enqueue_grad(H* h) {
   const int n = h->n, ld = h->ld;
   const long long sM = h->strideM;
-  enqueue_kinv(h);
   // M = (a a' - Kinv) o K  into the (now free) Ky buffer, with its row sums as per-column-block partials
   const double* aw = h->alpha + (h->nrhs == 2 ? h->ld : 0);
   const int nt32 = ceil_div(n, 32);
   const bool matern = (h->o.cov_form >= GPS_COV_MATERN1);
-  wk_kernel<<<dim3(nt32, nt32, h->batch), dim3(32, 8), 0, h->st>>>(h->Kinv, h->K, n, ld, sM, aw, h->ld, h->Ky, h->wdiag,
-                                                                   h->rs_part, nt32, matern ? h->Kd : nullptr, h->rsK_part);
-  LAUNCHED(h);
-  if (matern) {
-    rs_reduce_kernel<<<dim3(ceil_div(n, 256), h->batch), 256, 0, h->st>>>(h->rsK_part, n, h->ld, nt32, h->rsK);
+  int nblk = nt32;
+  if (h->fuse_wk && !matern) {
+    // fused: M, diag(W) and the row-sum partials come out of the epilogue of Kinv = U U'; Kinv is never stored
+    GemmParams p = gp(h->U, ld, sM, h->U, ld, sM, h->ne, h->ne, h->ne);
+    p.lower = 1;
+    p.klo_m = 1;
+    EpiWK e;
+    e.K = h->K; e.Mout = h->Ky; e.ldk = ld; e.strideK = sM; e.alpha = aw; e.wdiag = h->wdiag; e.rs_part = h->rs_part;
+    e.ldn = h->ld; e.nvalid = n;
+    const int tile = pick_nt_tile(h, p);
+    e.nblk = nblk = ceil_div(h->ne, tile_bm(h, tile));
+    gemm<false, false>(h, p, e);
+  } else {
+    enqueue_kinv(h);
+    wk_kernel<<<dim3(nt32, nt32, h->batch), dim3(32, 8), 0, h->st>>>(h->Kinv, h->K, n, ld, sM, aw, h->ld, h->Ky, h->wdiag,
+                                                                     h->rs_part, nt32, matern ? h->Kd : nullptr, h->rsK_part);
     LAUNCHED(h);
+    if (matern) {
+      rs_reduce_kernel<<<dim3(ceil_div(n, 256), h->batch), 256, 0, h->st>>>(h->rsK_part, n, h->ld, nt32, h->rsK);
+      LAUNCHED(h);
+    }
   }
-  rs_reduce_kernel<<<dim3(ceil_div(n, 256), h->batch), 256, 0, h->st>>>(h->rs_part, n, h->ld, nt32, h->rs);
+  rs_reduce_kernel<<<dim3(ceil_div(n, 256), h->batch), 256, 0, h->st>>>(h->rs_part, n, h->ld, nblk, h->rs);
   LAUNCHED(h);
   int mtiles = 1;
   {  // (M Xaug) contracted with Xaug column by column in the epilogue, together with rowsum(M) . Xaug^2.  With few
@@ -1036,6 +1054,7 @@ int gps_create_batch(int device, int batch, gps_handle* out) {
   if (const char* ev = getenv("GPS_WS_KMIN")) h->ws_kmin = atoi(ev);
   if (const char* ev = getenv("GPS_FUSE64")) h->fuse_k64 = atoi(ev) != 0;
   if (const char* ev = getenv("GPS_TINYCOV")) h->tiny_cov = atoi(ev) != 0;
+  if (const char* ev = getenv("GPS_FUSEWK")) h->fuse_wk = atoi(ev) != 0;
   if (const char* ev = getenv("GPS_NBIG")) {
     const int v = atoi(ev);
     if (v == 64 || v == 128 || v == 256 || v == 512) {
@@ -1405,11 +1424,20 @@ int gps_regress_finalize(gps_handle h, const double* par, int len, double* K_out
   CK(h, cudaMemcpy2DAsync(h->pin + B + (size_t)B * n, (size_t)n * sizeof(double), h->meanv, (size_t)h->ld * sizeof(double),
                           (size_t)n * sizeof(double), B, cudaMemcpyDeviceToHost, h->st));
   rc = fetch_info(h);
-  if (rc) return rc;
+  if (rc && !(rc == GPS_ERR_NOT_PD && h->tolerate_not_pd)) return rc;
   if (logmarlik_out)
     for (int b = 0; b < B; b++) logmarlik_out[b] = -h->pin[b];   // GPRegression.R:71 (positive sign)
   if (alpha_out) memcpy(alpha_out, h->pin + B, sizeof(double) * B * n);
   if (mean_out) memcpy(mean_out, h->pin + B + (size_t)B * n, sizeof(double) * B * n);
+  if (rc == GPS_ERR_NOT_PD)    // tolerated (gps_fit_batch): the failed fits' outputs are NaN, the model of the others is kept
+    for (int b = 0; b < B; b++)
+      if (h->pivots[b] != 0) {
+        if (logmarlik_out) logmarlik_out[b] = NAN;
+        for (int i = 0; i < n; i++) {
+          if (alpha_out) alpha_out[(size_t)b * n + i] = NAN;
+          if (mean_out) mean_out[(size_t)b * n + i] = NAN;
+        }
+      }
   if (K_out) {
     symmetrize_kernel<<<dim3(ceil_div(n, 32), ceil_div(n, 32), B), dim3(32, 8), 0, h->st>>>(h->K, n, h->ld, h->strideM);
     h->launches++;
@@ -1703,13 +1731,12 @@ int gps_chol_matvec(gps_handle h, const double* par, int len, const double* v, d
 }
 
 // ApplyGP.R:136-282 for every fit of the batch, in lock-step (C++ twin of batchfit.apply_gp_batch).
-int gps_fit_batch(gps_handle h, const double* X, int n, int d, const double* y_log, const double* events,
+static int fit_batch_impl(gps_handle h, const double* X, int n, int d, const double* y_log, const double* events,
                   const double* par_start, int len, int method, int maxit, double tolerance, int max_count, int survival,
                   const double* Xtest, int m, double* par_out, double* objective_out, double* logmarlik_out,
                   int* rounds_out, double* targets_learned_out, double* test_mean, double* test_varf, double* test_vard,
                   double* train_mean, long long* evaluations_out) {
-  int rc = check_handle(h);
-  if (rc) return rc;
+  int rc = GPS_OK;
   if (!X || !y_log || !events || !par_start || !Xtest || n < 1 || d < 1 || m < 1 || (method != 0 && method != 1))
     return fail(h, GPS_ERR_ARG, "gps_fit_batch: bad arguments");
   rc = gps_set_data(h, X, n, d, y_log, events);
@@ -1743,6 +1770,12 @@ int gps_fit_batch(gps_handle h, const double* X, int n, int d, const double* y_l
       mean_tmp((size_t)B * n);
   std::vector<int> count(B, 0);
   std::vector<OptResult> res;
+  std::vector<int>& status = h->fit_status;
+  status.assign(B, GPS_OK);
+  auto mark_failed = [&]() {
+    for (int b = 0; b < B; b++)
+      if (b < (int)h->pivots.size() && h->pivots[b] != 0) status[b] = GPS_ERR_NOT_PD;
+  };
   if (survival) {
     std::vector<double> a_start((size_t)B * c), lnc((size_t)B * (c > 0 ? c : 1)), used_lnc(lnc.size()), used_targets(learned),
         Xc((size_t)B * (c > 0 ? c : 1) * d), mu((size_t)B * (c > 0 ? c : 1)), vf(mu.size()), vd(mu.size()), em(mu.size()), evr(mu.size()),
@@ -1758,7 +1791,7 @@ int gps_fit_batch(gps_handle h, const double* X, int n, int d, const double* y_l
     for (;;) {
       bool any = false;
       for (int b = 0; b < B; b++) {
-        active[b] = ((change[b] > tolerance && count[b] < max_count) || count[b] <= 5) ? 1 : 0;   // :162
+        active[b] = (!status[b] && ((change[b] > tolerance && count[b] < max_count) || count[b] <= 5)) ? 1 : 0;   // :162
         any |= active[b] != 0;
       }
       if (!any) break;
@@ -1779,6 +1812,7 @@ int gps_fit_batch(gps_handle h, const double* X, int n, int d, const double* y_l
         if (active[b]) std::copy(res[b].par.begin(), res[b].par.end(), &vecs[(size_t)b * len]);
       rc = gps_regress_finalize(h, vecs.data(), len, nullptr, nullptr, alpha_tmp.data(), mean_tmp.data(), lml.data());
       if (rc) return rc;
+      mark_failed();   // a fit whose Ky does not factorise at the point optim returned is lost; the others go on
       for (int b = 0; b < B; b++) {
         std::vector<double> v(&vecs[(size_t)b * len], &vecs[(size_t)b * len] + len);
         chosen_vec(v, &pars_pred[(size_t)b * len]);
@@ -1790,7 +1824,7 @@ int gps_fit_batch(gps_handle h, const double* X, int n, int d, const double* y_l
         if (rc) return rc;
       }
       for (int b = 0; b < B; b++) {
-        if (!active[b]) continue;
+        if (!active[b] || status[b]) continue;
         std::copy(&pars_pred[(size_t)b * len], &pars_pred[(size_t)b * len] + len, &cur[(size_t)b * len]);    // :185
         change[b] = fabs(objective[b] - res[b].value);                                                        // :195
         objective[b] = res[b].value;
@@ -1825,6 +1859,7 @@ int gps_fit_batch(gps_handle h, const double* X, int n, int d, const double* y_l
     }
     rc = gps_regress_finalize(h, vecs.data(), len, nullptr, nullptr, alpha_tmp.data(), mean_tmp.data(), lml.data());
     if (rc) return rc;
+    mark_failed();
     for (int b = 0; b < B; b++) {
       std::vector<double> v(&vecs[(size_t)b * len], &vecs[(size_t)b * len] + len);
       chosen_vec(v, &cur[(size_t)b * len]);
@@ -1849,6 +1884,39 @@ int gps_fit_batch(gps_handle h, const double* X, int n, int d, const double* y_l
   if (rounds_out) std::copy(count.begin(), count.end(), rounds_out);
   if (targets_learned_out) std::copy(learned.begin(), learned.end(), targets_learned_out);
   if (evaluations_out) *evaluations_out = ev.ticks;
+  mark_failed();   // the final predictions may have rebuilt the model (GPS2 / GPS3)
+  for (int b = 0; b < B; b++) {
+    if (!status[b]) continue;      // lost fit: every numeric output is NaN, gps_fit_batch_status says why
+    if (objective_out) objective_out[b] = NAN;
+    if (logmarlik_out) logmarlik_out[b] = NAN;
+    for (int i = 0; i < m; i++) {
+      if (test_mean) test_mean[(size_t)b * m + i] = NAN;
+      if (test_varf) test_varf[(size_t)b * m + i] = NAN;
+      if (test_vard) test_vard[(size_t)b * m + i] = NAN;
+    }
+    if (train_mean) for (int i = 0; i < n; i++) train_mean[(size_t)b * n + i] = NAN;
+  }
+  return GPS_OK;
+}
+
+int gps_fit_batch(gps_handle h, const double* X, int n, int d, const double* y_log, const double* events,
+                  const double* par_start, int len, int method, int maxit, double tolerance, int max_count, int survival,
+                  const double* Xtest, int m, double* par_out, double* objective_out, double* logmarlik_out,
+                  int* rounds_out, double* targets_learned_out, double* test_mean, double* test_varf, double* test_vard,
+                  double* train_mean, long long* evaluations_out) {
+  int rc = check_handle(h);
+  if (rc) return rc;
+  h->tolerate_not_pd = true;
+  rc = fit_batch_impl(h, X, n, d, y_log, events, par_start, len, method, maxit, tolerance, max_count, survival, Xtest, m, par_out,
+                      objective_out, logmarlik_out, rounds_out, targets_learned_out, test_mean, test_varf, test_vard, train_mean,
+                      evaluations_out);
+  h->tolerate_not_pd = false;
+  return rc;
+}
+
+int gps_fit_batch_status(gps_handle h, int* status_out) {
+  if (!h || !status_out) return fail(h, GPS_ERR_ARG, "gps_fit_batch_status: bad arguments");
+  for (int b = 0; b < h->batch; b++) status_out[b] = b < (int)h->fit_status.size() ? h->fit_status[b] : GPS_OK;
   return GPS_OK;
 }
 

@@ -202,8 +202,11 @@ class Fit:
                                         1 if survival else 0, dptr(Xtc), m, dptr(par), dptr(obj), dptr(lml), rounds,
                                         dptr(learned), dptr(tm), dptr(tvf), dptr(tvd), dptr(trm), C.byref(ticks)))
         self.n, self.d = n, d
+        st = (C.c_int * B)()
+        self._ck(self.lib.gps_fit_batch_status(self.h, st))
         return {"par": par, "objective": obj, "logMarLik": lml, "count": np.array(list(rounds)), "trainingTargetsLearned": learned,
-                "funcMeanPred": tm, "varFunction": tvf, "varData": tvd, "trainingSetPredictions": trm, "ticks": int(ticks.value)}
+                "funcMeanPred": tm, "varFunction": tvf, "varData": tvd, "trainingSetPredictions": trm, "ticks": int(ticks.value),
+                "status": np.array(list(st))}   # per fit: 0 = ok, 3 = lost (Ky not positive definite at the point optim returned)
 
     # -- measurement helpers -------------------------------------------------------------
     def launch_count(self):

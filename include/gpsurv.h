@@ -145,7 +145,8 @@ int gps_chol_matvec(gps_handle h, const double* par, int len, const double* v, d
  * method: 0 = 'Nelder-Mead' (R's nmmin), 1 = 'BFGS' (R's vmmin, dense state kept on the device).
  * par_start: batch x len start vectors as GPRegression.R:22-25 assembles them (restarts may differ per fit;
  * for GPS3 the start noise correction is rep(par_start[0], nCensored), ApplyGP.R:149).
- * A point whose Ky is not positive definite is a rejected point (+Inf) for the optimiser.
+ * A point whose Ky is not positive definite is a rejected point (+Inf) for the optimiser; a fit that cannot be
+ * finalised at all is reported through gps_fit_batch_status and does not abort the batch.
  * Outputs (any may be NULL): par_out batch x len = logHypChosen flattened; objective_out, logmarlik_out,
  * rounds_out: batch; targets_learned_out, train_mean: batch x n; test_*: batch x m;
  * evaluations_out: number of batched evaluations used. */
@@ -154,6 +155,12 @@ int gps_fit_batch(gps_handle h, const double* X, int n, int d, const double* y_l
                   const double* Xtest, int m, double* par_out, double* objective_out, double* logmarlik_out,
                   int* rounds_out, double* targets_learned_out, double* test_mean, double* test_varf, double* test_vard,
                   double* train_mean, long long* evaluations_out);
+
+/* Per-fit status of the last gps_fit_batch (`batch` ints): GPS_OK, or GPS_ERR_NOT_PD for a fit whose Ky could not be
+ * factorised at the point its optimiser returned (e.g. a non-finite start value) — that fit's numeric outputs are NaN and
+ * it was dropped from the remaining rounds; the other fits of the batch are unaffected (the reference, too, would lose
+ * only that one ApplyGP call). */
+int gps_fit_batch_status(gps_handle h, int* status_out);
 
 /* ---- introspection used by bench.py / tests ------------------------------------------- */
 /* Number of kernels this handle has launched since creation (bench.py's gpu_launches). */

@@ -53,6 +53,28 @@ def test_oracle_matches_mpmath_golden(c):
         assert np.allclose(pr["varData"], c["pred_vard"], rtol=0, atol=1e-11)
 
 
+GOLD_MID = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "golden_mid.json")))
+
+
+@pytest.mark.parametrize("c", GOLD_MID["cases"], ids=[c["name"] for c in GOLD_MID["cases"]])
+def test_oracle_matches_mpmath_golden_mid(c):
+    """n = 65 ... 600: the sizes that cross the CUDA Cholesky's leaf / leaf pair / 256-wide block (golden_mid.json)."""
+    X, y, ev = np.array(c["X"]), np.array(c["y"]), np.array(c["events"])
+    par = np.array(c["par"])
+    kw = _case_kw(c)
+    f = orc.nlml(par, X, y, ev, **kw)
+    assert abs(f - c["nlml"]) <= 1e-11 * abs(c["nlml"])
+    g = orc.nlml_grad(par, X, y, ev, **kw)
+    assert np.max(np.abs(g - np.array(c["grad"]))) <= 1e-10 * np.max(np.abs(c["grad"]))
+    reg = orc.regress_finalize(par, X, y, ev, **kw)
+    d = X.shape[1]
+    p = d if c["cov_form"] == "ARD" else 1
+    reg["logHypChosen"] = {"noise": par[0], "func": par[1], "length": par[2:2 + p], "mean": np.zeros(d + 1)}
+    pr = orc.predict(reg, X, y, ev, np.array(c["Xstar"]), c["cov_form"], "Zero", c["noise_corr"], c["log_sc2_vec"])
+    assert np.allclose(pr["funcMeanPred"], c["pred_mean"], rtol=1e-9, atol=1e-11)
+    assert np.allclose(pr["varFunction"], c["pred_varf"], rtol=0, atol=1e-10)
+
+
 def test_matern_closed_forms():
     """Matern 1/2 is the exponential kernel; all three equal sf2 at r = 0 and decrease in r."""
     x = np.array([[0.0], [0.7], [2.0]])
