@@ -412,7 +412,23 @@ def run_gpu(args):
     d2h = 8 * B * (1 + par0.size) + 4 * B
 
     line = None
-    if rank == 0:
+    if rank == 0 and args.quick:          # developer A/B runs: the device-timed value and the stage timers, nothing else
+        fit.time_stages()
+        stages = fit.time_stages()
+        one = gp.Fit(local)
+        one.set_options(CFG.cov_form, "Zero", CFG.noise_corr, "intended")
+        one.set_data(X[0], y[0], ev[0])
+        one.set_noise_corr(lnc[0])
+        for w in range(3):
+            one.nlml_grad(pars[w, 0])
+        single_ms, single_nlml_ms = one.time_eval(kind=1, reps=20), one.time_eval(kind=0, reps=20)
+        one.close()
+        print(json.dumps({"quick": True, "config": CFG.name, "batch": B, "value": value, "ms_per_step": dev_ms / K,
+                          "tflops": B * flops / (ms_per_step * 1e-3) / 1e12, "peak_tf": peak_tf, "e2e": e2e_val,
+                          "stages_ms": [float(v) for v in stages[:5]], "single_ms": single_ms,
+                          "single_nlml_ms": single_nlml_ms, "launches_per_step": launches // max(K, 1),
+                          "env": {k: v for k, v in os.environ.items() if k.startswith("GPS_")}}), flush=True)
+    elif rank == 0:
         fit.time_stages()                 # first pass pays one-time costs of kernel variants only this (ungrouped) path uses
         stages = fit.time_stages()
         gemm_ms = fit.bench_gemm(8192, 8192, 8192, 3)
@@ -534,6 +550,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=0, help="independent fits evaluated per step on each GPU "
                                                          "(default: 64 for C2, 32 for C3, 256 for C4)")
+    ap.add_argument("--quick", action="store_true", help="developer A/B runs: device-timed value + stage timers only")
     ap.add_argument("--config", default="C2", choices=["C2", "C3", "C4"],
                     help="workload shape; the default C2 is the configuration BASELINE.json's metric is quoted on")
     args = ap.parse_args()

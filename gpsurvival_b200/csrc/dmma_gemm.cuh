@@ -593,6 +593,28 @@ using CfgS3 = TileCfg<64, 64, 16, 2, 2, 3>;
 // 16 x 16 warps need ~60 registers and run 8+ CTAs per SM
 using CfgTiny = TileCfg<32, 32, 16, 2, 2, 2>;
 
+// Launch priority of the kernels issued by the calling host thread (0 = stream default).  The latency-bound kernels of
+// the Cholesky's diagonal blocks are launched with the device's greatest priority: when another stream group's GEMM is
+// draining, the block scheduler hands freed SM slots to them first.
+inline int& launch_priority() {
+  static thread_local int prio = 0;
+  return prio;
+}
+template <class... KArgs, class... Args>
+cudaError_t launch_kernel(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributePriority;
+  at[0].val.priority = launch_priority();
+  cfg.attrs = at;
+  cfg.numAttrs = launch_priority() != 0 ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
+
 template <class Cfg, bool A_KC, bool B_KC, class Epi>
 cudaError_t launch_gemm(const GemmParams& p, const Epi& epi, int batch, cudaStream_t st) {
   using SL = SmemLayout<Cfg, A_KC, B_KC>;
@@ -607,8 +629,7 @@ cudaError_t launch_gemm(const GemmParams& p, const Epi& epi, int batch, cudaStre
   }
   if (p.M <= 0 || p.N <= 0) return cudaSuccess;
   dim3 grid((p.M + Cfg::BM - 1) / Cfg::BM, (p.N + Cfg::BN - 1) / Cfg::BN, batch * p.nodes * p.ksplit);
-  kern<<<grid, Cfg::NT, SL::BYTES, st>>>(p, epi);
-  return cudaGetLastError();
+  return launch_kernel(kern, grid, dim3(Cfg::NT), SL::BYTES, st, p, epi);
 }
 
 }  // namespace gps

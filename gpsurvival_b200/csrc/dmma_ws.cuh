@@ -22,6 +22,8 @@
 // Requirements beyond dmma_gemm.cuh's: K even for k-contiguous operands (A_KC / B_KC) so that every bulk
 // copy is a multiple of 16 bytes; rows may be over-read by one element up to the (even) leading dimension.
 #pragma once
+#include <stdlib.h>
+
 #include "dmma_gemm.cuh"
 
 namespace gps {
@@ -176,7 +178,7 @@ struct WsSmem {
 // A fragments by it (CovFunc's x / ell without ever materialising the scaled copy of X).
 template <class Cfg, bool A_KC, bool B_KC, class Epi, bool KS = false>
 __global__ void __launch_bounds__(Cfg::NTHREADS, Cfg::CTAS_PER_SM)
-    dmma_ws_kernel(GemmParams p_in, Epi epi, int zcount, int rev_m, int rev_n, int* __restrict__ sched) {
+    dmma_ws_kernel(GemmParams p_in, Epi epi, int zcount, int rev_m, int rev_n, int* __restrict__ sched, int quota) {
   using SL = WsSmem<Cfg, A_KC, B_KC>;
   constexpr int BM = Cfg::BM, BN = Cfg::BN, BK = Cfg::BK, STAGES = Cfg::STAGES;
   constexpr int FM = Cfg::FM, FN = Cfg::FN;
@@ -210,13 +212,19 @@ __global__ void __launch_bounds__(Cfg::NTHREADS, Cfg::CTAS_PER_SM)
   ws::TileWork w;
 
   if (producer) {
-    for (;;) {
+    // quota: tiles this CTA may take before it retires.  One wave (quota = all) is the plain persistent kernel; with the
+    // grid oversubscribed (ws_waves() > 1) CTAs retire early and hand their SM slot back to the block scheduler, which
+    // lets another stream's higher-priority latency-bound kernels in while this launch is still running.
+    for (int taken = 0; taken < quota; taken++) {
       int t = 0;
       if (lane == 0) t = atomicAdd(&sched[0], 1);
       t = __shfl_sync(0xffffffffu, t, 0);
       if (t >= total) break;
       ws::decode_tile<BM, BN, BK>(p_in, te, t, w);
-      if (!w.valid) continue;
+      if (!w.valid) {
+        taken--;
+        continue;
+      }
       const GemmParams& p = w.p;
       const int m0 = w.m0, n0 = w.n0;
       const double* __restrict__ A = p.A + (size_t)w.batch * p.strideA + (size_t)w.node * p.nodeStrideA;
@@ -389,6 +397,15 @@ using WsCfg96x64 = WsCfg<96, 64, 16, 2, 2, 3, 3>;     // 4 consumer warps of 48 
 using WsCfgN32 = WsCfg<128, 32, 16, 4, 1, 4, 3>;      // narrow outputs (N <= 32): 4 warps of 32 x 32
 using WsCfgN24 = WsCfg<128, 24, 16, 4, 1, 4, 3>;      // N <= 24 (M * Xaug with d = 20: 21 columns): 4 warps of 32 x 24
 
+inline int& ws_waves() {   // GPS_WAVES: grid oversubscription of the persistent kernel (1 = plain persistent)
+  static int waves = [] {
+    const char* ev = getenv("GPS_WAVES");
+    const int v = ev ? atoi(ev) : 1;
+    return v < 1 ? 1 : (v > 16 ? 16 : v);
+  }();
+  return waves;
+}
+
 // `sched`: two ints in device memory, zero before the first launch that uses them (the kernel re-arms them);
 // launches that may overlap in time must not share them.
 template <class Cfg, bool A_KC, bool B_KC, class Epi, bool KS = false>
@@ -412,10 +429,10 @@ cudaError_t launch_gemm_ws(const GemmParams& p, const Epi& epi, int batch, int n
   te.init(p.M, p.N, Cfg::BM, Cfg::BN, p.lower, rev_m, rev_n);
   const int zcount = batch * p.nodes * p.ksplit;
   const long long total = (long long)te.per_z * zcount;
-  const long long slots = (long long)num_sms * Cfg::CTAS_PER_SM;
+  const long long slots = (long long)num_sms * Cfg::CTAS_PER_SM * ws_waves();
   const int grid = (int)(total < slots ? total : slots);
-  kern<<<grid, Cfg::NTHREADS, SL::BYTES, st>>>(p, epi, zcount, rev_m, rev_n, sched);
-  return cudaGetLastError();
+  const int quota = ws_waves() > 1 ? (int)((total + grid - 1) / grid) : 0x7fffffff;
+  return launch_kernel(kern, dim3(grid), dim3(Cfg::NTHREADS), SL::BYTES, st, p, epi, zcount, rev_m, rev_n, sched, quota);
 }
 
 }  // namespace gps

@@ -87,6 +87,7 @@ struct gps_handle_s {
   int fuse_k64 = 1;              // GPS_FUSE64=0: separate K = 64 GEMM between the panels of a leaf pair
   int ws_kmin = 128;             // GPS_WS_KMIN: shortest k-loop given to the persistent kernel
   int front_fused = 1;           // GPS_FRONT=0: never use the fused small-d front end (small_front_kernel)
+  int prio_high = 0;             // GPS_PRIO=1: launch the latency-bound kernels of the diagonal blocks with this (greatest) priority
   int fuse_wk = 1;               // GPS_FUSEWK=0: separate wk_kernel pass after Kinv = U U' (always so for Matern gradients)
   int nbig = 256;                // GPS_NBIG: diagonal block of the two-level Cholesky (64 = one-level recursion)
   bool nbig_forced = false;
@@ -479,11 +480,11 @@ void launch_panel(H* h, int e0, int nb, int M, long long* dbg, int kprev = 0) {
   const int tiles = ceil_div(Mr, best_rt);
   dim3 grid(ceil_div(tiles, best_T) + 1, B);
   if (best_rt == 32)
-    panel_kernel<32><<<grid, 256, kprev ? PANEL_SMEM_FUSED : PANEL_SMEM, h->st>>>(h->Ky, h->L, h->Linv, h->U, h->ld, h->strideM, e0, nb,
-                                                                                    M, best_T, h->info, dbg, kprev);
+    CKV(h, launch_kernel(panel_kernel<32>, grid, dim3(256), kprev ? PANEL_SMEM_FUSED : PANEL_SMEM, h->st, h->Ky, h->L, h->Linv, h->U,
+                         h->ld, h->strideM, e0, nb, M, best_T, h->info, dbg, kprev));
   else
-    panel_kernel<128><<<grid, 256, PANEL_SMEM, h->st>>>(h->Ky, h->L, h->Linv, h->U, h->ld, h->strideM, e0, nb, M, best_T, h->info,
-                                                         dbg, 0);
+    CKV(h, launch_kernel(panel_kernel<128>, grid, dim3(256), PANEL_SMEM, h->st, h->Ky, h->L, h->Linv, h->U, h->ld, h->strideM, e0, nb,
+                         M, best_T, h->info, dbg, 0));
   LAUNCHED(h);
   if (h->pending_join) {   // look-ahead: the rest of the previous trailing update ran beside this panel
     CKV(h, cudaEventRecord(h->ev_join, h->st2));
@@ -601,8 +602,10 @@ void potrf_big(H* h, int J0, int J1) {
   const long long sM = h->strideM;
   if (J1 - J0 == 1) {
     const int c0 = J0 * nbig, c1 = std::min(c0 + nbig, h->ne);
+    launch_priority() = h->prio_high;   // the block's panel chains and short products: latency-bound, ahead of other groups' GEMM tiles
     potrf_range(h, c0 / NB, ceil_div(c1, NB), c1);
     trtri_range(h, c0, c1, NB, nbig);
+    launch_priority() = 0;
     const int M = h->naug - c1;
     if (M > 0) {
       GemmParams p = gp(h->Ky + c1 + (size_t)c0 * ld, ld, sM, h->Linv + c0 + (size_t)c0 * ld, ld, sM, M, c1 - c0, c1 - c0);
@@ -1055,6 +1058,10 @@ int gps_create_batch(int device, int batch, gps_handle* out) {
   if (const char* ev = getenv("GPS_FUSE64")) h->fuse_k64 = atoi(ev) != 0;
   if (const char* ev = getenv("GPS_TINYCOV")) h->tiny_cov = atoi(ev) != 0;
   if (const char* ev = getenv("GPS_FUSEWK")) h->fuse_wk = atoi(ev) != 0;
+  if (const char* ev = getenv("GPS_PRIO")) {
+    int least = 0, greatest = 0;
+    if (atoi(ev) != 0 && cudaDeviceGetStreamPriorityRange(&least, &greatest) == cudaSuccess) h->prio_high = greatest;
+  }
   if (const char* ev = getenv("GPS_NBIG")) {
     const int v = atoi(ev);
     if (v == 64 || v == 128 || v == 256 || v == 512) {
