@@ -1010,6 +1010,19 @@ int copy_out_matrix(H* h, double* dst, const double* src, int rows, int cols, in
   return GPS_OK;
 }
 
+int grad_precheck(H* h) {   // what every gradient evaluation requires of the handle's options
+  if (h->o.cov_form >= GPS_COV_MATERN1 && h->have_data && !h->Kd)
+    return fail(h, GPS_ERR_STATE, "Matern gradient: call gps_set_options before gps_set_data (the derivative-factor buffer "
+                                  "is allocated with the data)");
+  if (h->have_data && h->o.cov_form == GPS_COV_ARD && h->o.ard_mode == GPS_ARD_AS_WRITTEN && h->d > 1)
+    return fail(h, GPS_ERR_UNSUPPORTED,
+                "the analytic ARD gradient is defined for ard_mode = INTENDED only.  The reference's as-written ARD "
+                "'gradient' (OptimisationGradientLog.R:58-69) is not the derivative of its own likelihood (SURVEY.md F4: "
+                "unscaled dist(X), exp(+r/4/ell^3), no chain-rule factors) and is deliberately not offered as a compat "
+                "mode: an optimiser fed with it does not descend");
+  return GPS_OK;
+}
+
 }  // namespace
 
 // =========================================================================================
@@ -1020,6 +1033,7 @@ int gps_nlml(gps_handle h, const double* par, int len, double* nlml_out);
 int gps_nlml_grad(gps_handle h, const double* par, int len, double* nlml_out, double* grad_out);
 }
 #include "fit_batch.cuh"
+#include "lbfgs.cuh"
 
 extern "C" {
 
@@ -1366,13 +1380,8 @@ int gps_nlml_grad(gps_handle h, const double* par, int len, double* nlml_out, do
   int rc = check_handle(h);
   if (rc) return rc;
   if (!grad_out) return fail(h, GPS_ERR_ARG, "grad_out is NULL");
-  if (h->o.cov_form >= GPS_COV_MATERN1 && h->have_data && !h->Kd)
-    return fail(h, GPS_ERR_STATE, "Matern gradient: call gps_set_options before gps_set_data (the derivative-factor buffer "
-                                  "is allocated with the data)");
-  if (h->have_data && h->o.cov_form == GPS_COV_ARD && h->o.ard_mode == GPS_ARD_AS_WRITTEN && h->d > 1)
-    return fail(h, GPS_ERR_UNSUPPORTED,
-                "the analytic ARD gradient is defined for ard_mode = INTENDED only (the reference's as-written ARD "
-                "gradient, OptimisationGradientLog.R:58-69, is not the derivative of its likelihood)");
+  rc = grad_precheck(h);
+  if (rc) return rc;
   if (fact_hit(h, par, len)) {   // optim() calls fn(par) then gr(par): reuse fn's factorisation
     CK(h, cudaEventRecord(h->ev0, h->st));
     if (h->fact_level < 2) {
@@ -1744,7 +1753,7 @@ static int fit_batch_impl(gps_handle h, const double* X, int n, int d, const dou
                   int* rounds_out, double* targets_learned_out, double* test_mean, double* test_varf, double* test_vard,
                   double* train_mean, long long* evaluations_out) {
   int rc = GPS_OK;
-  if (!X || !y_log || !events || !par_start || !Xtest || n < 1 || d < 1 || m < 1 || (method != 0 && method != 1))
+  if (!X || !y_log || !events || !par_start || !Xtest || n < 1 || d < 1 || m < 1 || method < 0 || method > 2)
     return fail(h, GPS_ERR_ARG, "gps_fit_batch: bad arguments");
   rc = gps_set_data(h, X, n, d, y_log, events);
   if (rc) return rc;
@@ -1765,7 +1774,8 @@ static int fit_batch_impl(gps_handle h, const double* X, int n, int d, const dou
       if ((int)cidx[b].size() != c) return fail(h, GPS_ERR_ARG, "gps_fit_batch: all fits of a batch need the same number of censored rows");
   FitEvaluator ev{h, len};
   auto run_opt = [&](const std::vector<double>& starts, const std::vector<char>& active, std::vector<OptResult>& res) {
-    return method == 0 ? run_nelder_mead(ev, starts, len, maxit, active, res) : run_bfgs(ev, starts, len, maxit, active, res);
+    return method == 0 ? run_nelder_mead(ev, starts, len, maxit, active, res)
+                       : (method == 1 ? run_bfgs(ev, starts, len, maxit, active, res) : run_lbfgs(ev, starts, len, maxit, active, res));
   };
   // logHypChosen: the reference stores log(exp(.)) of noise, func and length (GPRegression.R:39-52,73)
   auto chosen_vec = [&](const std::vector<double>& v, double* outv) {

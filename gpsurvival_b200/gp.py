@@ -198,7 +198,7 @@ class Fit:
         learned = np.empty((B, n)); tm = np.empty((B, m)); tvf = np.empty((B, m)); tvd = np.empty((B, m)); trm = np.empty((B, n))
         ticks = C.c_longlong()
         self._ck(self.lib.gps_fit_batch(self.h, dptr(Xc), n, d, dptr(y), dptr(ev), dptr(ps), ln,
-                                        {"Nelder-Mead": 0, "BFGS": 1}[method], int(maxit), float(tolerance), int(max_count),
+                                        {"Nelder-Mead": 0, "BFGS": 1, "L-BFGS": 2}[method], int(maxit), float(tolerance), int(max_count),
                                         1 if survival else 0, dptr(Xtc), m, dptr(par), dptr(obj), dptr(lml), rounds,
                                         dptr(learned), dptr(tm), dptr(tvf), dptr(tvd), dptr(trm), C.byref(ticks)))
         self.n, self.d = n, d

@@ -213,6 +213,96 @@ def bfgs_steps(par, maxit=100, abstol=-math.inf, reltol=RELTOL):
     return {"par": b, "value": float(fmin), "counts": (nf, ng), "convergence": 0 if it < maxit else 1}
 
 
+def lbfgs_steps(par, maxit=100, m=10, reltol=RELTOL):
+    """Limited-memory BFGS with vmmin's line search and stopping rules ("L-BFGS using the new
+    gradient").  Not one of R's optim methods: it is vmmin (Nash Alg. 21: backtracking by 0.2 from step 1, Armijo
+    constant 1e-4, `reltest` no-move test, relative-reduction test, restart from steepest descent before giving up) with
+    the dense inverse-Hessian replaced by the two-loop recursion over the last `m` (s, y) pairs, H0 = (s'y / y'y) I.
+    No len x len state: what the batched C-side driver keeps on the device is m x len per fit.  This generator is the
+    host twin of csrc/lbfgs.cuh (same state machine, same order of operations); protocol as bfgs_steps."""
+    stepredn, acctol, reltest = 0.2, 1.0e-4, 10.0
+    x = np.array(par, dtype=np.float64).ravel()
+    n = x.size
+    if maxit <= 0:
+        f, _ = yield ("f", x.copy())
+        return {"par": x, "value": float(f), "counts": (0, 0), "convergence": 0}
+    f, g_with_f = yield ("f", x.copy())
+    f = float(f)
+    if not math.isfinite(f):
+        raise RuntimeError("initial value in 'lbfgs' is not finite")
+    if g_with_f is None:
+        _, g_with_f = yield ("g", x.copy())
+    g = np.array(g_with_f, dtype=np.float64).ravel()
+    nf = ng = it = 1
+    S, Y, RHO = [], [], []            # oldest first
+    gamma = 1.0
+    conv = 0
+    while True:
+        # two-loop recursion: t = -H g
+        q = g.copy()
+        al = [0.0] * len(S)
+        for i in range(len(S) - 1, -1, -1):
+            al[i] = RHO[i] * float(S[i] @ q)
+            q -= al[i] * Y[i]
+        r = (gamma if S else 1.0) * q
+        for i in range(len(S)):
+            be = RHO[i] * float(Y[i] @ r)
+            r += (al[i] - be) * S[i]
+        t = -r
+        gradproj = float(t @ g)
+        if not gradproj < 0.0:
+            if S:                     # not a descent direction: forget the history, steepest descent
+                S, Y, RHO = [], [], []
+                t = -g
+                gradproj = float(t @ g)
+            if not gradproj < 0.0:
+                break
+        step = 1.0
+        moved = False
+        while True:
+            b = x + step * t
+            if int(np.sum((reltest + x) == (reltest + b))) == n:
+                break
+            fb, g_with_f = yield ("f", b.copy())
+            fb = float(fb)
+            nf += 1
+            if math.isfinite(fb) and fb <= f + gradproj * step * acctol:
+                moved = True
+                break
+            step *= stepredn
+        if not moved:
+            if S:                     # restart once from steepest descent (vmmin: reset B = I)
+                S, Y, RHO = [], [], []
+                continue
+            break
+        if g_with_f is None:
+            _, g_with_f = yield ("g", b.copy())
+        gb = np.array(g_with_f, dtype=np.float64).ravel()
+        ng += 1
+        it += 1
+        s, yv = b - x, gb - g
+        enough = abs(fb - f) > reltol * (abs(f) + reltol)
+        x, g, f = b, gb, fb
+        had = len(S) > 0
+        sy, yy = float(s @ yv), float(yv @ yv)
+        if sy > 0.0:
+            S.append(s); Y.append(yv); RHO.append(1.0 / sy)
+            gamma = sy / yy
+            if len(S) > m:
+                S.pop(0); Y.pop(0); RHO.pop(0)
+        else:
+            S, Y, RHO = [], [], []
+        if it >= maxit:
+            conv = 1
+            break
+        if not enough:
+            if had:
+                S, Y, RHO = [], [], []
+            else:
+                break
+    return {"par": x, "value": float(f), "counts": (nf, ng), "convergence": conv}
+
+
 def _drive(gen, fn, gr):
     """Run an optimiser generator to completion with plain callables."""
     try:
@@ -234,13 +324,19 @@ def bfgs(fn, gr, par, maxit=100, **kw):
     return _drive(bfgs_steps(par, maxit=maxit, **kw), fn, gr)
 
 
+def lbfgs(fn, gr, par, maxit=100, **kw):
+    return _drive(lbfgs_steps(par, maxit=maxit, **kw), fn, gr)
+
+
 def optim_steps(par, method="Nelder-Mead", maxit=None):
     """Generator form of optim() for the batched driver."""
     if method == "Nelder-Mead":
         return nelder_mead_steps(par, maxit=500 if maxit is None else maxit)
     if method == "BFGS":
         return bfgs_steps(par, maxit=100 if maxit is None else maxit)
-    raise NotImplementedError(f"optim method {method!r} (Nelder-Mead and BFGS are restated)")
+    if method == "L-BFGS":
+        return lbfgs_steps(par, maxit=100 if maxit is None else maxit)
+    raise NotImplementedError(f"optim method {method!r} (Nelder-Mead and BFGS are restated; L-BFGS is ours)")
 
 
 def optim(par, fn, gr=None, method="Nelder-Mead", maxit=None):
@@ -252,4 +348,8 @@ def optim(par, fn, gr=None, method="Nelder-Mead", maxit=None):
         if gr is None:
             raise ValueError("BFGS needs a gradient")
         return bfgs(fn, gr, par, maxit=100 if maxit is None else maxit)
-    raise NotImplementedError(f"optim method {method!r} (Nelder-Mead and BFGS are restated)")
+    if method == "L-BFGS":
+        if gr is None:
+            raise ValueError("L-BFGS needs a gradient")
+        return lbfgs(fn, gr, par, maxit=100 if maxit is None else maxit)
+    raise NotImplementedError(f"optim method {method!r} (Nelder-Mead and BFGS are restated; L-BFGS is ours)")

@@ -142,7 +142,9 @@ int gps_chol_matvec(gps_handle h, const double* par, int len, const double* v, d
  * target / noise-correction update }  (ApplyGP.R:162-214), otherwise one GPRegression (:224-232); then
  * the test-set and training-set predictions (:237-282).  Options (covariance, mean, noiseCorr) come
  * from gps_set_options; y_log are the log (and, for real data, median-shifted) targets of ApplyGP.R:77-96.
- * method: 0 = 'Nelder-Mead' (R's nmmin), 1 = 'BFGS' (R's vmmin, dense state kept on the device).
+ * method: 0 = 'Nelder-Mead' (R's nmmin), 1 = 'BFGS' (R's vmmin, dense state kept on the device),
+ * 2 = L-BFGS (not an R method: vmmin's line search and stopping rules over a 10-pair two-loop recursion; points, gradients,
+ * directions and phases stay on the device, a tick costs 16 bytes of host traffic, line-search trials are fn-only).
  * par_start: batch x len start vectors as GPRegression.R:22-25 assembles them (restarts may differ per fit;
  * for GPS3 the start noise correction is rep(par_start[0], nCensored), ApplyGP.R:149).
  * A point whose Ky is not positive definite is a rejected point (+Inf) for the optimiser; a fit that cannot be

@@ -174,3 +174,65 @@ def test_fit_batch_drops_only_the_failed_fit():
         assert relmax(res["funcMeanPred"][ok], r3["funcMeanPred"]) <= 1e-7
         fit.close()
         fit3.close()
+
+
+# ---- device-resident L-BFGS ---------------------------------------------------------------------
+def test_lbfgs_c_side_matches_python_twin_and_reaches_vmmin_optimum():
+    """gps_fit_batch(method = L-BFGS): (a) the device state machine follows optim.lbfgs_steps (host twin driven by the
+    same GPU evaluations) over the first iterations, (b) run to convergence it reaches the optimum R's vmmin finds."""
+    from gpsurvival_b200 import optim
+    B = 5
+    pbs = [synth.make_problem(90, 10, 3, 0, 1300 + b) for b in range(B)]
+    X = np.stack([p["trainingData"] for p in pbs])
+    y = np.log(np.stack([p["trainingTargets"] for p in pbs]))
+    ev = np.ones_like(y)
+    Xt = np.stack([p["testData"] for p in pbs])
+    rng = np.random.default_rng(8)
+    start = np.stack([np.concatenate([np.log([0.2, 0.8]), np.log(1.7 * np.sqrt(3)) + 0.2 * rng.standard_normal(3)]) for _ in range(B)])
+    fitb = gp.Fit(0, batch=B)
+    fitb.set_options("ARD", "Zero", False, "intended")
+    one = gp.Fit(0)
+    one.set_options("ARD", "Zero", False, "intended")
+    for maxit, tol_f, tol_p in ((4, 1e-9, 1e-7), (200, 1e-6, None)):
+        res = fitb.fit_batch(X, y, ev, start, Xt, method="L-BFGS", maxit=maxit, survival=False)
+        assert np.all(res["status"] == 0)
+        for b in range(B):
+            one.set_data(X[b], y[b], ev[b])
+            tw = optim.lbfgs(lambda p: one.nlml(p, not_pd="inf"), lambda p: one.nlml_grad(p)[1], start[b], maxit=maxit)
+            assert abs(res["objective"][b] - tw["value"]) <= tol_f * abs(tw["value"]), (maxit, b, res["objective"][b], tw["value"])
+            if tol_p is not None:
+                assert relmax(res["par"][b], tw["par"]) <= tol_p
+        if maxit == 200:
+            rb = fitb.fit_batch(X, y, ev, start, Xt, method="BFGS", maxit=200, survival=False)
+            # both stop on vmmin's relative-reduction test (1.5e-8): the optima agree to 1e-6 and L-BFGS is not worse
+            assert np.all(res["objective"] <= rb["objective"] + 1e-6 * np.abs(rb["objective"]))
+            assert relmax(res["objective"], rb["objective"]) <= 1e-5
+            assert relmax(res["funcMeanPred"], rb["funcMeanPred"]) <= 1e-2
+            assert res["ticks"] > 0
+    fitb.close()
+    one.close()
+
+
+def test_lbfgs_survival_rounds_follow_python_driver():
+    """GPS3 rounds with the device L-BFGS inside (ApplyGP.R:162-214): same round count, objectives and predictions as the
+    Python driver running optim.lbfgs_steps over the same batched handle."""
+    from gpsurvival_b200 import batchfit
+    B = 3
+    pbs = [synth.make_problem(70, 15, 2, 28, 2100 + b) for b in range(B)]
+    params = dict(modelType="survival", noiseCorr="noiseCorrVec", optimType="L-BFGS", maxit=100, maxitSurvival=4,
+                  meanFuncForm="Zero", covFuncForm="ARD", tolerance=0.02, maxCount=8,
+                  logHypStart=synth.start_log_hyp(2, "ARD"), burnIn=False, imposePriors=False)
+    ref = batchfit.apply_gp_batch(pbs, params)
+    X = np.stack([p["trainingData"] for p in pbs])
+    y = np.log(np.stack([p["trainingTargets"] for p in pbs]))
+    ev = np.stack([p["events"] for p in pbs])
+    Xt = np.stack([p["testData"] for p in pbs])
+    start = np.stack([gp._flatten(params["logHypStart"], 2, "Zero", "noiseCorrVec", None)] * B)
+    fit = gp.Fit(0, batch=B)
+    fit.set_options("ARD", "Zero", "noiseCorrVec", "intended")
+    res = fit.fit_batch(X, y, ev, start, Xt, method="L-BFGS", maxit=4, tolerance=0.02, max_count=8, survival=True)
+    for b in range(B):
+        assert res["count"][b] == ref[b]["count"]
+        assert abs(res["objective"][b] - ref[b]["objectiveTable"][-1]) <= 1e-6 * abs(res["objective"][b])
+        assert relmax(res["funcMeanPred"][b], ref[b]["funcMeanPred"]) <= 1e-5
+    fit.close()

@@ -261,3 +261,28 @@ def test_apply_gp_loop_runs_minimum_six_rounds_and_updates_targets():
     assert np.all(r["trainingTargetsLearned"][cens] >= ylog[cens] - 1e-12)
     assert np.array_equal(r["trainingTargetsLearned"][~cens], ylog[~cens])
     assert r["funcMeanPred"].shape == (pb["testData"].shape[0],)
+
+
+def test_lbfgs_twin_minimises_and_agrees_with_vmmin():
+    """optim.lbfgs (the host twin of csrc/lbfgs.cuh): Rosenbrock to machine precision, and on a GP likelihood the same
+    optimum as the vmmin restatement (both stop on vmmin's relative-reduction test)."""
+    from gpsurvival_b200 import optim
+
+    def fr(x):
+        return 100.0 * (x[1] - x[0] ** 2) ** 2 + (1.0 - x[0]) ** 2
+
+    def gr(x):
+        return np.array([-400.0 * x[0] * (x[1] - x[0] ** 2) - 2.0 * (1.0 - x[0]), 200.0 * (x[1] - x[0] ** 2)])
+    r = optim.lbfgs(fr, gr, [-1.2, 1.0], maxit=200)
+    assert r["convergence"] == 0 and r["value"] < 1e-15 and np.allclose(r["par"], 1.0, atol=1e-7)
+    pb = synth.make_problem(80, 10, 3, 30, 5)
+    X, y, ev = pb["trainingData"], np.log(pb["trainingTargets"]), pb["events"]
+    kw = dict(cov_form="ARD", mean_form="Zero", noise_corr=False)
+    p0 = np.concatenate([np.log([0.2, 0.8]), np.log(1.7 * np.sqrt(3)) * np.ones(3)])
+    a = optim.lbfgs(lambda p: orc.nlml(p, X, y, ev, **kw), lambda p: orc.nlml_grad(p, X, y, ev, **kw), p0, maxit=200)
+    b = optim.bfgs(lambda p: orc.nlml(p, X, y, ev, **kw), lambda p: orc.nlml_grad(p, X, y, ev, **kw), p0, maxit=200)
+    assert a["convergence"] == 0 and abs(a["value"] - b["value"]) <= 1e-5 * abs(b["value"])
+    assert a["value"] <= b["value"] + 1e-6 * abs(b["value"])
+    # maxit is a cap on gradient evaluations, as in vmmin
+    c = optim.lbfgs(lambda p: orc.nlml(p, X, y, ev, **kw), lambda p: orc.nlml_grad(p, X, y, ev, **kw), p0, maxit=3)
+    assert c["convergence"] == 1 and c["counts"][1] == 3
