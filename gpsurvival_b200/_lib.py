@@ -55,6 +55,18 @@ PROTOTYPES = {
                                 C.c_int, _dp, C.c_int, _dp, _dp, _dp, C.POINTER(C.c_int), _dp, _dp, _dp, _dp, _dp,
                                 C.POINTER(C.c_longlong)]),
     "gps_fit_batch_status": (C.c_int, [_h, C.POINTER(C.c_int)]),
+    "gps_set_data_indexed": (C.c_int, [_h, _dp, C.c_int, C.c_int, _dp, _dp, C.POINTER(C.c_int), C.c_int]),
+    "gps_predict_rows": (C.c_int, [_h, _dp, C.c_int, C.c_int, C.POINTER(C.c_int), C.c_int, _dp, _dp, _dp]),
+    "gps_partition_lpt": (C.c_int, [_dp, C.c_int, C.c_int, C.POINTER(C.c_int)]),
+    "gps_fit_batch_multi": (C.c_int, [C.POINTER(C.c_int), C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                                      _dp, C.c_int, C.c_int, _dp, _dp, _dp, C.c_int, C.c_int, C.c_int, C.c_double, C.c_int, C.c_int,
+                                      _dp, C.c_int, _dp, _dp, _dp, C.POINTER(C.c_int), _dp, _dp, _dp, _dp, _dp, C.POINTER(C.c_int),
+                                      C.POINTER(C.c_longlong)]),
+    "gps_fit_folds_multi": (C.c_int, [C.POINTER(C.c_int), C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                                      _dp, C.c_int, C.c_int, _dp, _dp, C.POINTER(C.c_int), C.c_int, C.POINTER(C.c_int), C.c_int,
+                                      _dp, C.c_int, C.c_int, C.c_int, C.c_double, C.c_int, C.c_int,
+                                      _dp, _dp, _dp, C.POINTER(C.c_int), _dp, _dp, _dp, _dp, _dp, C.POINTER(C.c_int),
+                                      C.POINTER(C.c_longlong)]),
     "gps_launch_count": (C.c_longlong, [_h]),
     "gps_last_device_ms": (C.c_double, [_h]),
     "gps_set_graphs": (C.c_int, [_h, C.c_int]),

@@ -110,6 +110,13 @@ struct gps_handle_s {
   double *Xs = nullptr, *Zs = nullptr, *snorm = nullptr, *snpart = nullptr, *Ks = nullptr, *V = nullptr, *mstar = nullptr,
          *pout = nullptr;
   int m_cap = 0, lds = 0;
+  // pooled data of gps_set_data_indexed (one upload per device; fits are row-index views)
+  double *pool = nullptr, *pool_y = nullptr, *pool_ev = nullptr;
+  int* pool_rows = nullptr;
+  size_t pool_cap = 0, pool_rows_cap = 0;
+  int pool_n = 0;
+  int* gather_rows = nullptr;   // row indices for predictions at training rows (censored rows, training-set predictions)
+  size_t gather_rows_cap = 0;
   // adjust scratch
   double* adj = nullptr;
   int adj_cap = 0;
@@ -1141,6 +1148,7 @@ int gps_destroy(gps_handle h) {
   drop_graphs(h);
   free_data(h);
   dfree(h->adj);
+  dfree(h->pool); dfree(h->pool_y); dfree(h->pool_ev); dfree(h->pool_rows); dfree(h->gather_rows);
   if (h->pin) cudaFreeHost(h->pin);
   if (h->pin_info) cudaFreeHost(h->pin_info);
   if (h->ws_sched) cudaFree(h->ws_sched);
@@ -1186,11 +1194,8 @@ int gps_set_options(gps_handle h, int cov_form, int mean_form, int noise_corr, i
   return GPS_OK;
 }
 
-int gps_set_data(gps_handle h, const double* X, int n, int d, const double* y, const double* events) {
-  int rc = check_handle(h);
-  if (rc) return rc;
-  if (!X || !y || n < 1 || d < 1) return fail(h, GPS_ERR_ARG, "gps_set_data: bad arguments");
-  CK(h, cudaStreamSynchronize(h->st));
+// Allocations for a (n, d) problem shape (kept, with the captured graphs, when the shape does not change).
+static int ensure_shape(gps_handle h, int n, int d) {
   const int B = h->batch;
   const bool same_shape = h->have_data && h->n == n && h->d == d;   // keep allocations and graphs
   if (!same_shape) {
@@ -1273,7 +1278,37 @@ int gps_set_data(gps_handle h, const double* X, int n, int d, const double* y, c
   }
   h->model_valid = false;
   h->fact_level = 0;
-  rc = ensure_matern_buffers(h);
+  return ensure_matern_buffers(h);
+}
+
+// After X (raw, uncentred), y and events are in place on the device: column means, centring, X', censored-row ranks.
+static int postprocess_data(gps_handle h) {
+  const int B = h->batch, n = h->n, d = h->d;
+  colmean_kernel<<<dim3(ceil_div(d, 8), B), 256, 0, h->st>>>(h->Xaug, n, d, h->ldx, h->strideX, h->mu, h->ldmu);
+  center_kernel<<<dim3(ceil_div(n, 256), d + 1, B), 256, 0, h->st>>>(h->Xaug, n, d, h->ldx, h->strideX, h->mu, h->ldmu);
+  transpose_kernel<<<dim3(ceil_div(n, 32), ceil_div(d + 1, 32), B), dim3(32, 8), 0, h->st>>>(
+      h->Xaug, n, d + 1, h->ldx, h->strideX, h->XaugT, h->ldxt, h->strideXT);
+  cens_rank_kernel<<<B, 32, 0, h->st>>>(h->events, n, h->ld, h->cens_rank, h->d_ncens, B);
+  h->launches += 4;
+  CK(h, cudaGetLastError());
+  h->ncens.assign(B, 0);
+  CK(h, cudaMemcpyAsync(h->ncens.data(), h->d_ncens, sizeof(int) * B, cudaMemcpyDeviceToHost, h->st));
+  CK(h, cudaStreamSynchronize(h->st));
+  h->ncens_max = 0;
+  for (int b = 0; b < B; b++) h->ncens_max = h->ncens[b] > h->ncens_max ? h->ncens[b] : h->ncens_max;
+  h->have_data = true;
+  h->targets_version++;
+  h->nc_version++;
+  return GPS_OK;
+}
+
+int gps_set_data(gps_handle h, const double* X, int n, int d, const double* y, const double* events) {
+  int rc = check_handle(h);
+  if (rc) return rc;
+  if (!X || !y || n < 1 || d < 1) return fail(h, GPS_ERR_ARG, "gps_set_data: bad arguments");
+  CK(h, cudaStreamSynchronize(h->st));
+  const int B = h->batch;
+  rc = ensure_shape(h, n, d);
   if (rc) return rc;
   // upload (host arrays are [batch][n x d] column-major, [batch][n]).  A fit's X is one contiguous run on both sides
   // when n needs no row padding, so the whole batch goes in ONE strided copy per array instead of one per fit
@@ -1297,22 +1332,60 @@ int gps_set_data(gps_handle h, const double* X, int n, int d, const double* y, c
                             (size_t)n * sizeof(double), B, cudaMemcpyHostToDevice, h->st));
     CK(h, cudaStreamSynchronize(h->st));   // `ones` goes out of scope
   }
-  colmean_kernel<<<dim3(ceil_div(d, 8), B), 256, 0, h->st>>>(h->Xaug, n, d, h->ldx, h->strideX, h->mu, h->ldmu);
-  center_kernel<<<dim3(ceil_div(n, 256), d + 1, B), 256, 0, h->st>>>(h->Xaug, n, d, h->ldx, h->strideX, h->mu, h->ldmu);
-  transpose_kernel<<<dim3(ceil_div(n, 32), ceil_div(d + 1, 32), B), dim3(32, 8), 0, h->st>>>(
-      h->Xaug, n, d + 1, h->ldx, h->strideX, h->XaugT, h->ldxt, h->strideXT);
-  cens_rank_kernel<<<B, 32, 0, h->st>>>(h->events, n, h->ld, h->cens_rank, h->d_ncens, B);
-  h->launches += 4;
-  CK(h, cudaGetLastError());
-  h->ncens.assign(B, 0);
-  CK(h, cudaMemcpyAsync(h->ncens.data(), h->d_ncens, sizeof(int) * B, cudaMemcpyDeviceToHost, h->st));
+  return postprocess_data(h);
+}
+
+namespace {
+// Xaug[b][i, k] = pool[rows[b][i], k], y / events likewise: the fits of a batch as row-index views of one uploaded pool
+__global__ void gather_rows_kernel(const double* __restrict__ pool, int npool, const double* __restrict__ py,
+                                   const double* __restrict__ pev, const int* __restrict__ rows, int n, int d,
+                                   double* __restrict__ X, int ldx, long long strideX, double* __restrict__ y,
+                                   double* __restrict__ ev, int ldn) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x, k = blockIdx.y, b = blockIdx.z;
+  if (i >= n) return;
+  const int r = rows[(size_t)b * n + i];
+  X[(size_t)b * strideX + (size_t)i + (size_t)k * ldx] = pool[(size_t)r + (size_t)k * npool];
+  if (k == 0) {
+    y[(size_t)b * ldn + i] = py[r];
+    ev[(size_t)b * ldn + i] = pev ? pev[r] : 1.0;
+  }
+}
+}  // namespace
+
+int gps_set_data_indexed(gps_handle h, const double* Xpool, int npool, int d, const double* ypool, const double* eventspool,
+                         const int* rows, int n) {
+  int rc = check_handle(h);
+  if (rc) return rc;
+  if (!Xpool || !ypool || !rows || npool < 1 || n < 1 || d < 1) return fail(h, GPS_ERR_ARG, "gps_set_data_indexed: bad arguments");
+  const int B = h->batch;
+  for (size_t i = 0; i < (size_t)B * n; i++)
+    if (rows[i] < 0 || rows[i] >= npool) return fail(h, GPS_ERR_ARG, "gps_set_data_indexed: row index outside the pool");
   CK(h, cudaStreamSynchronize(h->st));
-  h->ncens_max = 0;
-  for (int b = 0; b < B; b++) h->ncens_max = h->ncens[b] > h->ncens_max ? h->ncens[b] : h->ncens_max;
-  h->have_data = true;
-  h->targets_version++;
-  h->nc_version++;
-  return GPS_OK;
+  rc = ensure_shape(h, n, d);
+  if (rc) return rc;
+  if ((size_t)npool * d > h->pool_cap) {
+    dfree(h->pool); dfree(h->pool_y); dfree(h->pool_ev);
+    CK(h, dalloc(&h->pool, (size_t)npool * d, false));
+    CK(h, dalloc(&h->pool_y, (size_t)npool, false));
+    CK(h, dalloc(&h->pool_ev, (size_t)npool, false));
+    h->pool_cap = (size_t)npool * d;
+  }
+  if ((size_t)B * n > h->pool_rows_cap) {
+    dfree(h->pool_rows);
+    CK(h, dalloc(&h->pool_rows, (size_t)B * n, false));
+    h->pool_rows_cap = (size_t)B * n;
+  }
+  h->pool_n = npool;
+  CK(h, cudaMemcpyAsync(h->pool, Xpool, sizeof(double) * (size_t)npool * d, cudaMemcpyHostToDevice, h->st));
+  CK(h, cudaMemcpyAsync(h->pool_y, ypool, sizeof(double) * npool, cudaMemcpyHostToDevice, h->st));
+  if (eventspool) CK(h, cudaMemcpyAsync(h->pool_ev, eventspool, sizeof(double) * npool, cudaMemcpyHostToDevice, h->st));
+  CK(h, cudaMemcpyAsync(h->pool_rows, rows, sizeof(int) * (size_t)B * n, cudaMemcpyHostToDevice, h->st));
+  gather_rows_kernel<<<dim3(ceil_div(n, 256), d, B), 256, 0, h->st>>>(h->pool, npool, h->pool_y, eventspool ? h->pool_ev : nullptr,
+                                                                     h->pool_rows, n, d, h->Xaug, h->ldx, h->strideX, h->y,
+                                                                     h->events, h->ld);
+  h->launches++;
+  CK(h, cudaGetLastError());
+  return postprocess_data(h);
 }
 
 int gps_set_targets(gps_handle h, const double* y) {
@@ -1483,12 +1556,33 @@ int gps_regress_finalize(gps_handle h, const double* par, int len, double* K_out
   return GPS_OK;
 }
 
-int gps_predict(gps_handle h, const double* par, int len, int reuse_model, const double* Xstar, int m, double* mu_out,
-                double* varf_out, double* vard_out) {
+namespace {
+// Xs[b][j, k] = Xaug[b][rows[b][j], k]: prediction points that ARE training rows (already centred)
+__global__ void gather_train_rows_kernel(const double* __restrict__ Xaug, int ldx, long long strideX, const int* __restrict__ rows,
+                                         int m, double* __restrict__ Xs, int lds, long long strideXs) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x, k = blockIdx.y, b = blockIdx.z;
+  if (j >= m) return;
+  Xs[(size_t)b * strideXs + (size_t)j + (size_t)k * lds] = Xaug[(size_t)b * strideX + (size_t)rows[(size_t)b * m + j] + (size_t)k * ldx];
+}
+}  // namespace
+
+// GPPredict at Xstar (host, m x d per fit) or, with `rows`, at training rows of each fit ([batch][m] indices, 0-based):
+// then nothing but the indices crosses the bus — the censored rows every GPS round (ApplyGP.R:171) and the training-set
+// predictions (:272-280) are such views.
+static int predict_impl(gps_handle h, const double* par, int len, int reuse_model, const double* Xstar, const int* rows, int m,
+                        double* mu_out, double* varf_out, double* vard_out, int rows_in_pool = 0) {
+  // rows_in_pool: `rows` index the pool of gps_set_data_indexed (raw, uncentred rows — test folds) instead of the fit's
+  // own training rows
   int rc = check_handle(h);
   if (rc) return rc;
   if (!h->have_data) return fail(h, GPS_ERR_STATE, "gps_set_data has not been called");
-  if (!Xstar || m < 1 || !mu_out) return fail(h, GPS_ERR_ARG, "gps_predict: bad arguments");
+  if ((!Xstar && !rows) || m < 1 || !mu_out) return fail(h, GPS_ERR_ARG, "gps_predict: bad arguments");
+  if (rows && rows_in_pool && !h->pool) return fail(h, GPS_ERR_STATE, "gps_predict_rows: no pooled data (gps_set_data_indexed)");
+  if (rows) {
+    const int lim = rows_in_pool ? h->pool_n : h->n;
+    for (size_t i = 0; i < (size_t)h->batch * m; i++)
+      if (rows[i] < 0 || rows[i] >= lim) return fail(h, GPS_ERR_ARG, "gps_predict_rows: row index out of range");
+  }
   const int B = h->batch, n = h->n, d = h->d;
   bool fresh = h->model_valid && par && par_close(h->model_par, par, (size_t)len * B) &&
                h->model_tv == h->targets_version && h->model_ncv == h->nc_version;
@@ -1516,13 +1610,33 @@ int gps_predict(gps_handle h, const double* par, int len, int reuse_model, const
   }
   const int lds = h->lds;
   const long long sXs = (long long)lds * d, sKs = (long long)h->ld * m;
-  for (int b = 0; b < B; b++)
-    CK(h, cudaMemcpy2DAsync(h->Xs + (size_t)b * sXs, (size_t)lds * sizeof(double), Xstar + (size_t)b * m * d,
-                            (size_t)m * sizeof(double), (size_t)m * sizeof(double), d, cudaMemcpyHostToDevice, h->st));
+  if (rows) {
+    if ((size_t)B * m > h->gather_rows_cap) {
+      CK(h, cudaStreamSynchronize(h->st));
+      dfree(h->gather_rows);
+      CK(h, dalloc(&h->gather_rows, (size_t)B * m, false));
+      h->gather_rows_cap = (size_t)B * m;
+    }
+    CK(h, cudaMemcpyAsync(h->gather_rows, rows, sizeof(int) * (size_t)B * m, cudaMemcpyHostToDevice, h->st));
+  } else {
+    for (int b = 0; b < B; b++)
+      CK(h, cudaMemcpy2DAsync(h->Xs + (size_t)b * sXs, (size_t)lds * sizeof(double), Xstar + (size_t)b * m * d,
+                              (size_t)m * sizeof(double), (size_t)m * sizeof(double), d, cudaMemcpyHostToDevice, h->st));
+  }
   CK(h, cudaEventRecord(h->ev0, h->st));
   h->cu_err = cudaSuccess;
   h->seq_launches = 0;
-  center_test_kernel<<<dim3(ceil_div(m, 256), d, B), 256, 0, h->st>>>(h->Xs, m, d, lds, sXs, h->mu, h->ldmu);
+  if (rows && !rows_in_pool) {
+    gather_train_rows_kernel<<<dim3(ceil_div(m, 256), d, B), 256, 0, h->st>>>(h->Xaug, h->ldx, h->strideX, h->gather_rows, m, h->Xs,
+                                                                             lds, sXs);
+  } else {
+    if (rows) {   // raw pool rows: same gather with the pool as the (shared) source, then centred like any test point
+      gather_train_rows_kernel<<<dim3(ceil_div(m, 256), d, B), 256, 0, h->st>>>(h->pool, h->pool_n, 0, h->gather_rows, m, h->Xs, lds,
+                                                                               sXs);
+      LAUNCHED(h);
+    }
+    center_test_kernel<<<dim3(ceil_div(m, 256), d, B), 256, 0, h->st>>>(h->Xs, m, d, lds, sXs, h->mu, h->ldmu);
+  }
   LAUNCHED(h);
   // training rows re-scaled with the *model's* length-scales
   {
@@ -1581,6 +1695,18 @@ int gps_predict(gps_handle h, const double* par, int len, int reuse_model, const
   if (varf_out) memcpy(varf_out, h->pin + (size_t)m * B, sizeof(double) * m * B);
   if (vard_out) memcpy(vard_out, h->pin + (size_t)2 * m * B, sizeof(double) * m * B);
   return GPS_OK;
+}
+
+int gps_predict(gps_handle h, const double* par, int len, int reuse_model, const double* Xstar, int m, double* mu_out,
+                double* varf_out, double* vard_out) {
+  if (!Xstar) return fail(h, GPS_ERR_ARG, "gps_predict: Xstar is NULL");
+  return predict_impl(h, par, len, reuse_model, Xstar, nullptr, m, mu_out, varf_out, vard_out);
+}
+
+int gps_predict_rows(gps_handle h, const double* par, int len, int reuse_model, const int* rows, int m, double* mu_out,
+                     double* varf_out, double* vard_out) {
+  if (!rows) return fail(h, GPS_ERR_ARG, "gps_predict_rows: rows is NULL");
+  return predict_impl(h, par, len, reuse_model, nullptr, rows, m, mu_out, varf_out, vard_out);
 }
 
 int gps_adjust(gps_handle h, const double* a, const double* mu, const double* s, int c, double* mean_out,
@@ -1747,15 +1873,39 @@ int gps_chol_matvec(gps_handle h, const double* par, int len, const double* v, d
 }
 
 // ApplyGP.R:136-282 for every fit of the batch, in lock-step (C++ twin of batchfit.apply_gp_batch).
+// Pooled source of a batch of fits (CV folds / restarts of one data set): fit b trains on rows
+// train_rows[b][0..n) of the pool and is tested on rows test_rows[b][0..m); the pool is uploaded once per device.
+struct FoldSrc {
+  const double *Xpool, *ypool, *evpool;
+  int npool;
+  const int *train_rows, *test_rows;
+};
+
 static int fit_batch_impl(gps_handle h, const double* X, int n, int d, const double* y_log, const double* events,
                   const double* par_start, int len, int method, int maxit, double tolerance, int max_count, int survival,
                   const double* Xtest, int m, double* par_out, double* objective_out, double* logmarlik_out,
                   int* rounds_out, double* targets_learned_out, double* test_mean, double* test_varf, double* test_vard,
-                  double* train_mean, long long* evaluations_out) {
+                  double* train_mean, long long* evaluations_out, const FoldSrc* fs = nullptr) {
   int rc = GPS_OK;
-  if (!X || !y_log || !events || !par_start || !Xtest || n < 1 || d < 1 || m < 1 || method < 0 || method > 2)
+  if (!par_start || n < 1 || d < 1 || m < 1 || method < 0 || method > 2 || (!fs && (!X || !y_log || !events || !Xtest)))
     return fail(h, GPS_ERR_ARG, "gps_fit_batch: bad arguments");
-  rc = gps_set_data(h, X, n, d, y_log, events);
+  std::vector<double> y_own, ev_own;
+  if (fs) {   // the per-fit targets / events the host-side loop needs are views of the pool too
+    const size_t tot = (size_t)h->batch * n;
+    y_own.resize(tot);
+    ev_own.resize(tot);
+    for (size_t i = 0; i < tot; i++) {
+      const int r = fs->train_rows[i];
+      if (r < 0 || r >= fs->npool) return fail(h, GPS_ERR_ARG, "gps_fit_folds: row index outside the pool");
+      y_own[i] = fs->ypool[r];
+      ev_own[i] = fs->evpool ? fs->evpool[r] : 1.0;
+    }
+    y_log = y_own.data();
+    events = ev_own.data();
+    rc = gps_set_data_indexed(h, fs->Xpool, fs->npool, d, fs->ypool, fs->evpool, fs->train_rows, n);
+  } else {
+    rc = gps_set_data(h, X, n, d, y_log, events);
+  }
   if (rc) return rc;
   if (len != expected_len(h)) return fail(h, GPS_ERR_ARG, "gps_fit_batch: par_start has the wrong length for these options");
 
@@ -1795,14 +1945,13 @@ static int fit_batch_impl(gps_handle h, const double* X, int n, int d, const dou
   };
   if (survival) {
     std::vector<double> a_start((size_t)B * c), lnc((size_t)B * (c > 0 ? c : 1)), used_lnc(lnc.size()), used_targets(learned),
-        Xc((size_t)B * (c > 0 ? c : 1) * d), mu((size_t)B * (c > 0 ? c : 1)), vf(mu.size()), vd(mu.size()), em(mu.size()), evr(mu.size()),
-        change(B, 1.0);
+        mu((size_t)B * (c > 0 ? c : 1)), vf(mu.size()), vd(mu.size()), em(mu.size()), evr(mu.size()), change(B, 1.0);
+    std::vector<int> crow((size_t)B * (c > 0 ? c : 1));   // the censored rows as indices: predictions at them are device-side views
     for (int b = 0; b < B; b++)
       for (int r = 0; r < c; r++) {
         a_start[(size_t)b * c + r] = y_log[(size_t)b * n + cidx[b][r]];                    // ApplyGP.R:108
         lnc[(size_t)b * c + r] = par_start[(size_t)b * len];                               // :149 rep(logHypStart$noise, nCens)
-        for (int k = 0; k < d; k++)
-          Xc[((size_t)b * d + k) * c + r] = X[((size_t)b * d + k) * n + cidx[b][r]];
+        crow[(size_t)b * c + r] = cidx[b][r];
       }
     std::vector<char> active(B, 1);
     for (;;) {
@@ -1835,7 +1984,8 @@ static int fit_batch_impl(gps_handle h, const double* X, int n, int d, const dou
         chosen_vec(v, &pars_pred[(size_t)b * len]);
       }
       if (c > 0) {
-        rc = gps_predict(h, pars_pred.data(), len, nc == GPS_NC_NONE ? 1 : 0, Xc.data(), c, mu.data(), vf.data(), vd.data());   // :171
+        rc = predict_impl(h, pars_pred.data(), len, nc == GPS_NC_NONE ? 1 : 0, nullptr, crow.data(), c, mu.data(), vf.data(),
+                          vd.data());                                                                                           // :171
         if (rc) return rc;
         rc = gps_adjust(h, a_start.data(), mu.data(), vd.data(), B * c, em.data(), evr.data());                                  // :190
         if (rc) return rc;
@@ -1885,14 +2035,18 @@ static int fit_batch_impl(gps_handle h, const double* X, int n, int d, const dou
   }
   const int reuse = (nc == GPS_NC_NONE) ? 1 : 0;
   std::vector<double> tm((size_t)B * m), tvf((size_t)B * m), tvd((size_t)B * m);
-  rc = gps_predict(h, cur.data(), len, reuse, Xtest, m, tm.data(), tvf.data(), tvd.data());                   // :243 / :245
+  if (fs) rc = predict_impl(h, cur.data(), len, reuse, nullptr, fs->test_rows, m, tm.data(), tvf.data(), tvd.data(), 1);
+  else rc = gps_predict(h, cur.data(), len, reuse, Xtest, m, tm.data(), tvf.data(), tvd.data());              // :243 / :245
   if (rc) return rc;
   if (test_mean) std::copy(tm.begin(), tm.end(), test_mean);
   if (test_varf) std::copy(tvf.begin(), tvf.end(), test_varf);
   if (test_vard) std::copy(tvd.begin(), tvd.end(), test_vard);
   if (train_mean) {
     std::vector<double> t2((size_t)B * n), t3((size_t)B * n), t4((size_t)B * n);
-    rc = gps_predict(h, cur.data(), len, reuse, X, n, t2.data(), t3.data(), t4.data());                       // :272 / :280
+    std::vector<int> all_rows((size_t)B * n);
+    for (int b = 0; b < B; b++)
+      for (int i = 0; i < n; i++) all_rows[(size_t)b * n + i] = i;
+    rc = predict_impl(h, cur.data(), len, reuse, nullptr, all_rows.data(), n, t2.data(), t3.data(), t4.data());   // :272 / :280
     if (rc) return rc;
     std::copy(t2.begin(), t2.end(), train_mean);
   }
@@ -1929,6 +2083,186 @@ int gps_fit_batch(gps_handle h, const double* X, int n, int d, const double* y_l
                       evaluations_out);
   h->tolerate_not_pd = false;
   return rc;
+}
+
+// ---- multi-device: independent fits sharded over the GPUs of one box from ONE host process ------------
+// Longest-processing-time-first partition of `count` jobs with the given costs over `nparts` bins (pure host code).
+int gps_partition_lpt(const double* cost, int count, int nparts, int* part_out) {
+  if (!cost || !part_out || count < 0 || nparts < 1) return fail(nullptr, GPS_ERR_ARG, "gps_partition_lpt: bad arguments");
+  std::vector<int> order(count);
+  for (int i = 0; i < count; i++) order[i] = i;
+  std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return cost[a] > cost[b]; });
+  std::vector<double> load(nparts, 0.0);
+  std::vector<int> cnt(nparts, 0);
+  for (int i : order) {
+    int best = 0;
+    for (int g = 1; g < nparts; g++)
+      if (load[g] < load[best] || (load[g] == load[best] && cnt[g] < cnt[best])) best = g;
+    part_out[i] = best;
+    load[best] += cost[i];
+    cnt[best]++;
+  }
+  return GPS_OK;
+}
+
+}  // extern "C"  (the shared multi-device driver below is C++)
+
+#include <thread>
+
+namespace {
+
+struct MultiJob {
+  int total, n, d, m, len, method, maxit, max_count, survival;
+  int cov_form, mean_form, noise_corr, ard_mode;
+  double tolerance;
+  const double *X, *y_log, *events, *par_start, *Xtest;   // per-fit arrays ([total][...]) — or:
+  const FoldSrc* fs;                                      // pooled source (train_rows / test_rows are [total][...])
+  double *par_out, *objective_out, *logmarlik_out, *targets_learned_out, *test_mean, *test_varf, *test_vard, *train_mean;
+  int *rounds_out, *status_out;
+};
+
+// One device's share: its own handle (one handle per host thread per device), sub-batches sized to the free memory.
+void multi_worker(const MultiJob& J, int device, const std::vector<int>& mine, int* rc_out, std::string* err_out, long long* ticks_out) {
+  *rc_out = GPS_OK;
+  *ticks_out = 0;
+  if (mine.empty()) return;
+  size_t freeb = 0, totalb = 0;
+  if (cudaSetDevice(device) != cudaSuccess || cudaMemGetInfo(&freeb, &totalb) != cudaSuccess) {
+    *rc_out = GPS_ERR_CUDA;
+    *err_out = "gps_fit_batch_multi: cannot use device " + std::to_string(device);
+    (void)cudaGetLastError();
+    return;
+  }
+  const double per_fit = 8.0 * (10.0 * (double)(J.n + 18) * (J.n + 18) + 4.0 * (double)(J.n + 16) * (J.d + 17) + 24.0 * J.len * J.n / 8.0) + 1e6;
+  int cap = (int)std::max(1.0, std::min((double)mine.size(), 0.6 * (double)freeb / per_fit));
+  const int n = J.n, d = J.d, m = J.m, len = J.len;
+  for (size_t s0 = 0; s0 < mine.size(); s0 += cap) {
+    const int B = (int)std::min((size_t)cap, mine.size() - s0);
+    gps_handle h = nullptr;
+    int rc = gps_create_batch(device, B, &h);
+    if (!rc) rc = gps_set_options(h, J.cov_form, J.mean_form, J.noise_corr, J.ard_mode);
+    std::vector<double> X, y, ev, Xt, ps((size_t)B * len);
+    std::vector<int> tr, te;
+    std::vector<double> par((size_t)B * len), obj(B), lml(B, 0.0), learned((size_t)B * n), tm((size_t)B * m), tvf((size_t)B * m),
+        tvd((size_t)B * m), trm((size_t)B * n);
+    std::vector<int> rounds(B), status(B);
+    long long ticks = 0;
+    if (!rc) {
+      for (int b = 0; b < B; b++) {
+        const size_t f = (size_t)mine[s0 + b];
+        std::copy(J.par_start + f * len, J.par_start + (f + 1) * len, ps.begin() + (size_t)b * len);
+      }
+      FoldSrc fs_local;
+      if (J.fs) {
+        tr.resize((size_t)B * n);
+        te.resize((size_t)B * m);
+        for (int b = 0; b < B; b++) {
+          const size_t f = (size_t)mine[s0 + b];
+          std::copy(J.fs->train_rows + f * n, J.fs->train_rows + (f + 1) * n, tr.begin() + (size_t)b * n);
+          std::copy(J.fs->test_rows + f * m, J.fs->test_rows + (f + 1) * m, te.begin() + (size_t)b * m);
+        }
+        fs_local = *J.fs;
+        fs_local.train_rows = tr.data();
+        fs_local.test_rows = te.data();
+      } else {
+        X.resize((size_t)B * n * d); y.resize((size_t)B * n); ev.resize((size_t)B * n); Xt.resize((size_t)B * m * d);
+        for (int b = 0; b < B; b++) {
+          const size_t f = (size_t)mine[s0 + b];
+          std::copy(J.X + f * n * d, J.X + (f + 1) * n * d, X.begin() + (size_t)b * n * d);
+          std::copy(J.y_log + f * n, J.y_log + (f + 1) * n, y.begin() + (size_t)b * n);
+          std::copy(J.events + f * n, J.events + (f + 1) * n, ev.begin() + (size_t)b * n);
+          std::copy(J.Xtest + f * m * d, J.Xtest + (f + 1) * m * d, Xt.begin() + (size_t)b * m * d);
+        }
+      }
+      h->tolerate_not_pd = true;
+      rc = fit_batch_impl(h, J.fs ? nullptr : X.data(), n, d, J.fs ? nullptr : y.data(), J.fs ? nullptr : ev.data(), ps.data(), len,
+                          J.method, J.maxit, J.tolerance, J.max_count, J.survival, J.fs ? nullptr : Xt.data(), m, par.data(),
+                          obj.data(), lml.data(), rounds.data(), learned.data(), tm.data(), tvf.data(), tvd.data(),
+                          J.train_mean ? trm.data() : nullptr, &ticks, J.fs ? &fs_local : nullptr);
+      h->tolerate_not_pd = false;
+      if (!rc) rc = gps_fit_batch_status(h, status.data());
+    }
+    if (rc) {
+      *rc_out = rc;
+      *err_out = h ? h->err : g_tls_error;
+      gps_destroy(h);
+      return;
+    }
+    for (int b = 0; b < B; b++) {   // scatter to the caller's arrays at the fits' original positions
+      const size_t f = (size_t)mine[s0 + b];
+      if (J.par_out) std::copy(par.begin() + (size_t)b * len, par.begin() + (size_t)(b + 1) * len, J.par_out + f * len);
+      if (J.objective_out) J.objective_out[f] = obj[b];
+      if (J.logmarlik_out) J.logmarlik_out[f] = lml[b];
+      if (J.rounds_out) J.rounds_out[f] = rounds[b];
+      if (J.status_out) J.status_out[f] = status[b];
+      if (J.targets_learned_out) std::copy(learned.begin() + (size_t)b * n, learned.begin() + (size_t)(b + 1) * n, J.targets_learned_out + f * n);
+      if (J.test_mean) std::copy(tm.begin() + (size_t)b * m, tm.begin() + (size_t)(b + 1) * m, J.test_mean + f * m);
+      if (J.test_varf) std::copy(tvf.begin() + (size_t)b * m, tvf.begin() + (size_t)(b + 1) * m, J.test_varf + f * m);
+      if (J.test_vard) std::copy(tvd.begin() + (size_t)b * m, tvd.begin() + (size_t)(b + 1) * m, J.test_vard + f * m);
+      if (J.train_mean) std::copy(trm.begin() + (size_t)b * n, trm.begin() + (size_t)(b + 1) * n, J.train_mean + f * n);
+    }
+    *ticks_out += ticks;
+    gps_destroy(h);
+  }
+}
+
+int multi_run(const MultiJob& J, const int* devices, int ndev, long long* evaluations_out) {
+  if (!devices || ndev < 1 || J.total < 1) return fail(nullptr, GPS_ERR_ARG, "gps_fit_batch_multi: bad arguments");
+  // all fits have the same shape here, so the LPT partition by estimated cost (3 n^2 d + n^3 per evaluation) is an even
+  // split; fits keep their relative order inside a device's share
+  std::vector<double> cost(J.total, 3.0 * J.n * (double)J.n * J.d + (double)J.n * J.n * J.n);
+  std::vector<int> part(J.total);
+  int rc = gps_partition_lpt(cost.data(), J.total, ndev, part.data());
+  if (rc) return rc;
+  std::vector<std::vector<int>> mine(ndev);
+  for (int i = 0; i < J.total; i++) mine[part[i]].push_back(i);
+  std::vector<int> rcs(ndev, GPS_OK);
+  std::vector<std::string> errs(ndev);
+  std::vector<long long> ticks(ndev, 0);
+  std::vector<std::thread> th;
+  for (int g = 0; g < ndev; g++)
+    th.emplace_back(multi_worker, std::cref(J), devices[g], std::cref(mine[g]), &rcs[g], &errs[g], &ticks[g]);
+  for (auto& t : th) t.join();
+  long long worst = 0;
+  for (int g = 0; g < ndev; g++) {
+    if (rcs[g]) return fail(nullptr, rcs[g], "device " + std::to_string(devices[g]) + ": " + errs[g]);
+    worst = std::max(worst, ticks[g]);
+  }
+  if (evaluations_out) *evaluations_out = worst;
+  return GPS_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int gps_fit_batch_multi(const int* devices, int ndev, int total, int cov_form, int mean_form, int noise_corr, int ard_mode,
+                        const double* X, int n, int d, const double* y_log, const double* events, const double* par_start, int len,
+                        int method, int maxit, double tolerance, int max_count, int survival, const double* Xtest, int m,
+                        double* par_out, double* objective_out, double* logmarlik_out, int* rounds_out, double* targets_learned_out,
+                        double* test_mean, double* test_varf, double* test_vard, double* train_mean, int* status_out,
+                        long long* evaluations_out) {
+  if (!X || !y_log || !events || !par_start || !Xtest || n < 1 || d < 1 || m < 1 || len < 1)
+    return fail(nullptr, GPS_ERR_ARG, "gps_fit_batch_multi: bad arguments");
+  MultiJob J{total, n, d, m, len, method, maxit, max_count, survival, cov_form, mean_form, noise_corr, ard_mode, tolerance,
+             X, y_log, events, par_start, Xtest, nullptr,
+             par_out, objective_out, logmarlik_out, targets_learned_out, test_mean, test_varf, test_vard, train_mean, rounds_out, status_out};
+  return multi_run(J, devices, ndev, evaluations_out);
+}
+
+int gps_fit_folds_multi(const int* devices, int ndev, int total, int cov_form, int mean_form, int noise_corr, int ard_mode,
+                        const double* Xpool, int npool, int d, const double* y_log_pool, const double* events_pool,
+                        const int* train_rows, int n, const int* test_rows, int m, const double* par_start, int len, int method,
+                        int maxit, double tolerance, int max_count, int survival, double* par_out, double* objective_out,
+                        double* logmarlik_out, int* rounds_out, double* targets_learned_out, double* test_mean, double* test_varf,
+                        double* test_vard, double* train_mean, int* status_out, long long* evaluations_out) {
+  if (!Xpool || !y_log_pool || !train_rows || !test_rows || !par_start || npool < 1 || n < 1 || d < 1 || m < 1 || len < 1)
+    return fail(nullptr, GPS_ERR_ARG, "gps_fit_folds_multi: bad arguments");
+  FoldSrc fs{Xpool, y_log_pool, events_pool, npool, train_rows, test_rows};
+  MultiJob J{total, n, d, m, len, method, maxit, max_count, survival, cov_form, mean_form, noise_corr, ard_mode, tolerance,
+             nullptr, nullptr, nullptr, par_start, nullptr, &fs,
+             par_out, objective_out, logmarlik_out, targets_learned_out, test_mean, test_varf, test_vard, train_mean, rounds_out, status_out};
+  return multi_run(J, devices, ndev, evaluations_out);
 }
 
 int gps_fit_batch_status(gps_handle h, int* status_out) {

@@ -76,6 +76,29 @@ class Fit:
         self._ck(self.lib.gps_set_data(self.h, dptr(X), n, d, dptr(y), dptr(ev)))
         self.n, self.d = n, d
 
+    def set_data_indexed(self, Xpool, ypool, eventspool, rows):
+        """gps_set_data_indexed: the fits of this batch as row-index views (rows: [batch, n], 0-based) of one pooled data
+        set, uploaded once."""
+        Xp = f64(Xpool)
+        npool, d = Xp.shape
+        rows = np.ascontiguousarray(np.asarray(rows, dtype=np.int32)).reshape(self.batch, -1)
+        n = rows.shape[1]
+        yp = np.ascontiguousarray(np.asarray(ypool, dtype=np.float64))
+        evp = None if eventspool is None else np.ascontiguousarray(np.asarray(eventspool, dtype=np.float64))
+        self._ck(self.lib.gps_set_data_indexed(self.h, dptr(Xp), npool, d, dptr(yp), dptr(evp),
+                                               rows.ctypes.data_as(C.POINTER(C.c_int)), n))
+        self.n, self.d = n, d
+
+    def predict_rows(self, par, rows, reuse_model=False):
+        """gps_predict_rows: GPPredict at training rows of each fit (rows: [batch, m], 0-based)."""
+        p, ln = self._par(par)
+        rows = np.ascontiguousarray(np.asarray(rows, dtype=np.int32)).reshape(self.batch, -1)
+        m = rows.shape[1]
+        mu, vf, vd = (np.empty((self.batch, m)) for _ in range(3))
+        self._ck(self.lib.gps_predict_rows(self.h, dptr(p), ln, 1 if reuse_model else 0, rows.ctypes.data_as(C.POINTER(C.c_int)),
+                                           m, dptr(mu), dptr(vf), dptr(vd)))
+        return (mu, vf, vd) if self.batch > 1 else (mu[0], vf[0], vd[0])
+
     def set_targets(self, y):
         y = np.ascontiguousarray(np.asarray(y, dtype=np.float64)).reshape(self.batch, self.n)
         self._ck(self.lib.gps_set_targets(self.h, dptr(y)))
@@ -529,3 +552,84 @@ def ApplyGP(trainingTestStructure, dataOptionsStructure, parameterStructure, plo
                 "trainingSetPredictions": pred3["funcMeanPred"], "logMarLik": reg["logMarLik"],
                 "objective": reg["objective"]})
     return out
+
+
+# =========================================================================================
+# Several GPUs from one host process (gps_fit_batch_multi / gps_fit_folds_multi)
+# =========================================================================================
+_METHODS = {"Nelder-Mead": 0, "BFGS": 1, "L-BFGS": 2}
+
+
+def partition_lpt(cost, nparts):
+    """gps_partition_lpt: longest-processing-time-first assignment of jobs to `nparts` bins (pure host code in the library)."""
+    lib = _lib.load()
+    cost = np.ascontiguousarray(np.asarray(cost, dtype=np.float64))
+    out = (C.c_int * cost.size)()
+    check(lib.gps_partition_lpt(dptr(cost), cost.size, int(nparts), out))
+    return np.array(list(out), dtype=int)
+
+
+def _multi_outputs(T, n, m, ln):
+    return dict(par=np.empty((T, ln)), objective=np.empty(T), logMarLik=np.zeros(T), rounds=(C.c_int * T)(),
+                learned=np.empty((T, n)), tm=np.empty((T, m)), tvf=np.empty((T, m)), tvd=np.empty((T, m)), trm=np.empty((T, n)),
+                status=(C.c_int * T)(), ticks=C.c_longlong())
+
+
+def _multi_result(o):
+    return {"par": o["par"], "objective": o["objective"], "logMarLik": o["logMarLik"], "count": np.array(list(o["rounds"])),
+            "trainingTargetsLearned": o["learned"], "funcMeanPred": o["tm"], "varFunction": o["tvf"], "varData": o["tvd"],
+            "trainingSetPredictions": o["trm"], "status": np.array(list(o["status"])), "ticks": int(o["ticks"].value)}
+
+
+def fit_batch_multi(devices, X, y_log, events, par_start, Xtest, cov_form="SqExp", mean_form="Zero", noise_corr=False,
+                    ard_mode="intended", extra_param=None, method="Nelder-Mead", maxit=10, tolerance=1e-3, max_count=500,
+                    survival=True):
+    """gps_fit_batch_multi: `total` independent fits (X [T, n, d], Xtest [T, m, d]) over the listed devices, one host thread and
+    one handle per device behind the C ABI, no collective."""
+    lib = _lib.load()
+    X = np.asarray(X, dtype=np.float64)
+    Xt = np.asarray(Xtest, dtype=np.float64)
+    T, n, d = X.shape
+    m = Xt.shape[1]
+    Xc = np.ascontiguousarray(np.transpose(X, (0, 2, 1)))
+    Xtc = np.ascontiguousarray(np.transpose(Xt, (0, 2, 1)))
+    y = np.ascontiguousarray(np.asarray(y_log, dtype=np.float64)).reshape(T, n)
+    ev = np.ascontiguousarray(np.asarray(events, dtype=np.float64)).reshape(T, n)
+    ps = np.ascontiguousarray(np.asarray(par_start, dtype=np.float64)).reshape(T, -1)
+    ln = ps.shape[1]
+    o = _multi_outputs(T, n, m, ln)
+    dev = (C.c_int * len(devices))(*[int(v) for v in devices])
+    check(lib.gps_fit_batch_multi(dev, len(devices), T, cov_code(cov_form, extra_param), MEAN[mean_form], NOISE_CORR[noise_corr],
+                                  ARD_MODE[ard_mode], dptr(Xc), n, d, dptr(y), dptr(ev), dptr(ps), ln, _METHODS[method], int(maxit),
+                                  float(tolerance), int(max_count), 1 if survival else 0, dptr(Xtc), m, dptr(o["par"]),
+                                  dptr(o["objective"]), dptr(o["logMarLik"]), o["rounds"], dptr(o["learned"]), dptr(o["tm"]),
+                                  dptr(o["tvf"]), dptr(o["tvd"]), dptr(o["trm"]), o["status"], C.byref(o["ticks"])))
+    return _multi_result(o)
+
+
+def fit_folds_multi(devices, Xpool, y_log_pool, events_pool, train_rows, test_rows, par_start, cov_form="SqExp", mean_form="Zero",
+                    noise_corr=False, ard_mode="intended", extra_param=None, method="Nelder-Mead", maxit=10, tolerance=1e-3,
+                    max_count=500, survival=True):
+    """gps_fit_folds_multi: CV folds / restarts of ONE data set as row-index views (train_rows [T, n], test_rows [T, m]); the
+    pool crosses the bus once per device."""
+    lib = _lib.load()
+    Xp = f64(Xpool)
+    npool, d = Xp.shape
+    tr = np.ascontiguousarray(np.asarray(train_rows, dtype=np.int32))
+    te = np.ascontiguousarray(np.asarray(test_rows, dtype=np.int32))
+    T, n = tr.shape
+    m = te.shape[1]
+    yp = np.ascontiguousarray(np.asarray(y_log_pool, dtype=np.float64))
+    evp = np.ascontiguousarray(np.asarray(events_pool, dtype=np.float64))
+    ps = np.ascontiguousarray(np.asarray(par_start, dtype=np.float64)).reshape(T, -1)
+    ln = ps.shape[1]
+    o = _multi_outputs(T, n, m, ln)
+    dev = (C.c_int * len(devices))(*[int(v) for v in devices])
+    ip = C.POINTER(C.c_int)
+    check(lib.gps_fit_folds_multi(dev, len(devices), T, cov_code(cov_form, extra_param), MEAN[mean_form], NOISE_CORR[noise_corr],
+                                  ARD_MODE[ard_mode], dptr(Xp), npool, d, dptr(yp), dptr(evp), tr.ctypes.data_as(ip), n,
+                                  te.ctypes.data_as(ip), m, dptr(ps), ln, _METHODS[method], int(maxit), float(tolerance),
+                                  int(max_count), 1 if survival else 0, dptr(o["par"]), dptr(o["objective"]), dptr(o["logMarLik"]),
+                                  o["rounds"], dptr(o["learned"]), dptr(o["tm"]), dptr(o["tvf"]), dptr(o["tvd"]), dptr(o["trm"]),
+                                  o["status"], C.byref(o["ticks"])))
+    return _multi_result(o)

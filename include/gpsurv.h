@@ -79,6 +79,12 @@ int gps_set_options(gps_handle h, int cov_form, int mean_form, int noise_corr, i
 /* trainingData (n x d), trainingTargets (n), events (n) — GPRegression.R:7-11.  X is constant
  * over all evaluations of a fit and is uploaded once. */
 int gps_set_data(gps_handle h, const double* X, int n, int d, const double* y, const double* events);
+/* The same, with the fits of the batch given as ROW-INDEX VIEWS of one pooled data set (CV folds, restarts of one
+ * data set — the reference's runSyntheticExp1.R:208-213 / CV loops call ApplyGP once per fold on row subsets): Xpool is
+ * npool x d (column-major), ypool / eventspool length npool, rows[batch][n] the 0-based pool rows of every fit.  The
+ * pool is uploaded once; the per-fit copies are gathered on the device. */
+int gps_set_data_indexed(gps_handle h, const double* Xpool, int npool, int d, const double* ypool, const double* eventspool,
+                         const int* rows, int n);
 /* trainingTargetsLearned changes every GPS round (ApplyGP.R:201). */
 int gps_set_targets(gps_handle h, const double* y);
 /* logHypNoiseCorrection for GPS3: one value per censored row, in row order (ApplyGP.R:149,209;
@@ -122,6 +128,12 @@ int gps_regress_finalize(gps_handle h, const double* par, int len, double* K_out
 int gps_predict(gps_handle h, const double* par, int len, int reuse_model, const double* Xstar, int m,
                 double* mu_out, double* varf_out, double* vard_out);
 
+/* GPPredict at TRAINING rows of each fit: rows[batch][m], 0-based indices into the fit's own trainingData.  This is what
+ * ApplyGP asks for every GPS round (testData = the censored training rows, ApplyGP.R:165-171) and for the training-set
+ * predictions (:265-282); only the indices cross the bus. */
+int gps_predict_rows(gps_handle h, const double* par, int len, int reuse_model, const int* rows, int m,
+                     double* mu_out, double* varf_out, double* vard_out);
+
 /* ---- AdjustTrainingSurvivalMeanVariance.R:1-37 ------------------------------------------ */
 /* Lower-truncated-normal moments for c censored samples: a = censoring time, mu/s = predictive
  * mean and the value the reference passes as `sigma` (ApplyGP.R:173,190 pass the variance).
@@ -163,6 +175,30 @@ int gps_fit_batch(gps_handle h, const double* X, int n, int d, const double* y_l
  * it was dropped from the remaining rounds; the other fits of the batch are unaffected (the reference, too, would lose
  * only that one ApplyGP call). */
 int gps_fit_batch_status(gps_handle h, int* status_out);
+
+/* ---- several GPUs from one host process (the restart x fold loops of runSyntheticExp1.R:208-213) ---------
+ * `total` independent fits of identical shape are split over `devices[0..ndev)` (LPT by estimated cost 3 n^2 d + n^3,
+ * which for identical shapes is an even split), one host thread and one handle per device, sub-batches sized to the
+ * device's free memory, NO collective and no peer traffic: results are scattered back into the caller's arrays at the
+ * fits' positions.  Options as gps_set_options; every other argument as gps_fit_batch with `total` as the batch;
+ * status_out[total] as gps_fit_batch_status; evaluations_out = the largest per-device number of batched evaluations.
+ * A device may be listed more than once (two host threads sharing one GPU). */
+int gps_fit_batch_multi(const int* devices, int ndev, int total, int cov_form, int mean_form, int noise_corr, int ard_mode,
+                        const double* X, int n, int d, const double* y_log, const double* events, const double* par_start, int len,
+                        int method, int maxit, double tolerance, int max_count, int survival, const double* Xtest, int m,
+                        double* par_out, double* objective_out, double* logmarlik_out, int* rounds_out, double* targets_learned_out,
+                        double* test_mean, double* test_varf, double* test_vard, double* train_mean, int* status_out,
+                        long long* evaluations_out);
+/* The same for CV folds / restarts of ONE data set: the pool (npool x d) is uploaded once per device and fit t trains on
+ * pool rows train_rows[t][0..n) and is tested on test_rows[t][0..m) — no per-fit copy of X crosses the bus. */
+int gps_fit_folds_multi(const int* devices, int ndev, int total, int cov_form, int mean_form, int noise_corr, int ard_mode,
+                        const double* Xpool, int npool, int d, const double* y_log_pool, const double* events_pool,
+                        const int* train_rows, int n, const int* test_rows, int m, const double* par_start, int len, int method,
+                        int maxit, double tolerance, int max_count, int survival, double* par_out, double* objective_out,
+                        double* logmarlik_out, int* rounds_out, double* targets_learned_out, double* test_mean, double* test_varf,
+                        double* test_vard, double* train_mean, int* status_out, long long* evaluations_out);
+/* The partitioner itself (pure host code): part_out[i] in [0, nparts) for jobs with the given costs, longest first. */
+int gps_partition_lpt(const double* cost, int count, int nparts, int* part_out);
 
 /* ---- introspection used by bench.py / tests ------------------------------------------- */
 /* Number of kernels this handle has launched since creation (bench.py's gpu_launches). */

@@ -128,3 +128,19 @@ def test_batch_bfgs_follows_sequential_vmmin():
         return f, np.array([rosen_der(p) for p in P])
     r2, _ = batch_bfgs(ev2, x0[:3, :2] if x0.shape[1] >= 2 else x0, maxit=30, active=[True, False, True], device="cpu")
     assert r2[1] is None and r2[0] is not None and np.isfinite(r2[0]["value"])
+
+
+def test_c_abi_lpt_partitioner_balances_and_is_deterministic(lib):
+    """gps_partition_lpt (the host partitioner behind gps_fit_batch_multi): every job assigned, loads balanced to within the
+    largest job (the LPT guarantee), identical jobs split evenly, same answer on every call."""
+    import numpy as np
+    from gpsurvival_b200 import gp
+    rng = np.random.default_rng(0)
+    cost = rng.uniform(1.0, 10.0, 200)
+    for parts in (1, 2, 4, 8):
+        a = gp.partition_lpt(cost, parts)
+        assert a.min() >= 0 and a.max() < parts and np.array_equal(a, gp.partition_lpt(cost, parts))
+        loads = np.array([cost[a == g].sum() for g in range(parts)])
+        assert loads.max() - loads.min() <= cost.max() + 1e-9
+    even = gp.partition_lpt(np.full(512, 3.0), 8)
+    assert np.all(np.bincount(even, minlength=8) == 64)
