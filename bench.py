@@ -72,6 +72,113 @@ def step_pars(par0, count, seed):
     return par0[None, :] + 0.05 * rng.standard_normal((count, par0.size))
 
 
+def measure_extra_config(name, B, local, reps):
+    """One more BASELINE.json shape on the driver's clock (north_star's target shapes): `B` fits of config `name`
+    batched on this GPU, NLML+gradient evaluations device-timed like the headline, with per-stage rates and its own
+    clock sample."""
+    from gpsurvival_b200 import gp
+    global CFG
+    saved = CFG
+    CFG = synth.CONFIGS[name]
+    try:
+        X, y, ev, lnc, par0 = batch_workload(0, B)
+        n, d = X.shape[1], X.shape[2]
+        fit = gp.Fit(local, batch=B)
+        fit.set_options(CFG.cov_form, "Zero", CFG.noise_corr, "intended")
+        fit.set_data(X, y, ev)
+        fit.set_noise_corr(lnc)
+        rng = np.random.default_rng(23)
+        pars = par0[None, None, :] + 0.05 * rng.standard_normal((4, B, par0.size))
+        for w in range(3):
+            fit.nlml_grad(pars[w])
+        sampler = ClockSampler(local)
+        sampler.start()
+        ms = fit.time_eval(kind=1, reps=reps)
+        clocks = sampler.stop()
+        fit.time_stages()
+        st = fit.time_stages()
+        fl = algorithmic_flops(n, d, ard=True)
+        n3 = float(n) ** 3 / 3.0
+        out = {"workload": "%s: %d fits of n=%d d=%d, GPS3 ARD NLML+gradient" % (name, B, n, d), "evals_per_sec": B * 1e3 / ms,
+               "ms_per_step": ms, "tflops": B * fl / (ms * 1e-3) / 1e12, "clocks": clocks,
+               "stages_ms": {"gram": st[0], "cholesky": st[1], "tri_inverse": st[2], "kinv": st[3], "wk_grad": st[4]},
+               "stage_tflops": {"gram (n^2 d)": B * float(n) * n * d / (st[0] * 1e-3) / 1e12,
+                                "cholesky (n^3/3)": B * n3 / (st[1] * 1e-3) / 1e12,
+                                "tri_inverse (n^3/3)": B * n3 / (st[2] * 1e-3) / 1e12,
+                                "kinv (n^3/3)": B * n3 / (st[3] * 1e-3) / 1e12,
+                                "W o K + gradient contraction (2 n^2 (d+1))": B * 2.0 * n * n * (d + 1) / (st[4] * 1e-3) / 1e12}}
+        fit.close()
+        return out
+    finally:
+        CFG = saved
+
+
+def measure_extra_c5(local, n=16384, d=50, m=4096):
+    """BASELINE.json configs[4]: one large GPS1 / SqExp fit, n = 16384 — one NLML+gradient evaluation with per-stage rates
+    and one prediction at m = 4096 points (inputs are random: sampling GP targets at this n on the host would dominate)."""
+    from gpsurvival_b200 import gp
+    rng = np.random.default_rng(4)
+    X = np.asfortranarray(rng.standard_normal((n, d)))
+    Xs = np.asfortranarray(rng.standard_normal((m, d)))
+    y = rng.standard_normal(n)
+    ev = (rng.random(n) > 0.5).astype(np.float64)
+    par = np.log([0.2, 0.8, 1.7 * np.sqrt(d)])
+    fit = gp.Fit(local)
+    fit.set_options("SqExp", "Zero", False)
+    fit.set_data(X, y, ev)
+    for i in range(2):
+        fit.nlml_grad(par + 1e-3 * i)
+    sampler = ClockSampler(local)
+    sampler.start()
+    ms = fit.time_eval(kind=1, reps=3)
+    clocks = sampler.stop()
+    st = fit.time_stages()
+    n3 = float(n) ** 3 / 3.0
+    fit.finalize(par)
+    fit.predict(par, Xs)
+    pred_ms = fit.last_device_ms()
+    pred_flops = 2.0 * n * m * d + float(n) * n * m + 4.0 * n * m          # SURVEY.md §8d "Predict flops"
+    out = {"workload": "C5: one GPS1 SqExp fit n=%d d=%d; NLML+gradient evaluation and a prediction at m=%d" % (n, d, m),
+           "eval_ms": ms, "tflops": (float(n) * n * d + float(n) ** 3) / (ms * 1e-3) / 1e12, "clocks": clocks,
+           "stages_ms": {"gram": st[0], "cholesky": st[1], "tri_inverse": st[2], "kinv": st[3], "wk_grad": st[4]},
+           "stage_tflops": {"cholesky (n^3/3)": n3 / (st[1] * 1e-3) / 1e12, "tri_inverse (n^3/3)": n3 / (st[2] * 1e-3) / 1e12,
+                            "kinv (n^3/3)": n3 / (st[3] * 1e-3) / 1e12},
+           "predict_m4096": {"device_ms": pred_ms, "tflops": pred_flops / (pred_ms * 1e-3) / 1e12,
+                             "flops": "2 n m d + n^2 m + 4 n m (cross-covariance, V = L^-1 K*, mean, variance)"}}
+    fit.close()
+    return out
+
+
+def measure_extra_c4_sweep(local, total=512, restarts=16, method="L-BFGS"):
+    """BASELINE.json configs[3] on one GPU: 512 GPS3 fits = 16 restarts x 32 folds of ONE Yuan-shaped data set, through
+    gps_fit_folds_multi (the pool crosses the bus once, fits are row-index views; sub-batches sized to free memory)."""
+    from gpsurvival_b200 import gp
+    cfg = synth.CONFIGS["C4"]
+    folds = total // restarts
+    pb = synth.make_problem(cfg.n + cfg.m, 4, cfg.d, int(round((cfg.n + cfg.m) * cfg.c / cfg.n)), 20160916 + 3)
+    Xp, yp, evp = pb["trainingData"], np.log(pb["trainingTargets"]), pb["events"]
+    rng = np.random.default_rng(9)
+    cens, died = np.where(evp == 0)[0], np.where(evp == 1)[0]
+    tr, te = [], []
+    for f in range(folds):                       # every fold: cfg.c censored + (n - c) uncensored training rows, the rest tests
+        rows = np.concatenate([rng.permutation(cens)[:cfg.c], rng.permutation(died)[:cfg.n - cfg.c]])
+        rest = np.setdiff1d(np.arange(Xp.shape[0]), rows)
+        tr.append(rng.permutation(rows))
+        te.append(rng.permutation(rest)[:cfg.m])
+    tr = np.array([tr[t % folds] for t in range(total)], dtype=np.int32)
+    te = np.array([te[t % folds] for t in range(total)], dtype=np.int32)
+    starts = np.stack([gp._flatten(synth.start_log_hyp(cfg.d, cfg.cov_form, rng), cfg.d, "Zero", cfg.noise_corr, None)
+                       for _ in range(total)])
+    t0 = time.perf_counter()
+    res = gp.fit_folds_multi([local], Xp, yp, evp, tr, te, starts, cov_form=cfg.cov_form, noise_corr=cfg.noise_corr,
+                             method=method, maxit=10, tolerance=1e300, max_count=6, survival=True)
+    dt = time.perf_counter() - t0
+    return {"workload": "C4: %d GPS3 ARD fits (%d restarts x %d folds of one n=%d+%d, d=%d data set), %s, 6 GPS rounds x maxit 10"
+                        % (total, restarts, folds, cfg.n, cfg.m, cfg.d, method),
+            "fits_per_sec": total / dt, "seconds": dt, "lost_fits": int(np.sum(res["status"] != 0)),
+            "h2d_note": "pool uploaded once per sub-batch; fits, censored rows and test folds are row-index views"}
+
+
 CONFIG_NOTES = {"C2": "BASELINE.json configs[1]", "C3": "BASELINE.json configs[2], Tothill shape",
                 "C4": "BASELINE.json configs[3], Yuan shape"}
 
@@ -465,7 +572,7 @@ def run_gpu(args):
             par_start = np.stack([gp._flatten(s0, d, "Zero", CFG.noise_corr, None) for s0 in starts])
             Xtest = X[:, :500, :]
             # Nelder-Mead needs one evaluation per simplex vertex (hyper-parameters + 1) before it moves: only sensible at d = 20
-            for method in (("Nelder-Mead", "BFGS") if CFG.name == "C2" else ("BFGS",)):
+            for method in (("Nelder-Mead", "BFGS", "L-BFGS") if CFG.name == "C2" else ("BFGS", "L-BFGS")):
                 tt = time.perf_counter()
                 rr = fit.fit_batch(X, y, ev, par_start, Xtest, method=method, maxit=10, tolerance=1e300, max_count=6,
                                    survival=True)                      # whole fits behind the C ABI (gps_fit_batch)
@@ -478,6 +585,19 @@ def run_gpu(args):
             f, g = fit.nlml_grad(pars[W + K - 1])
         except Exception as exc:        # never lose the headline line because of the extra measurement
             fits = {"error": repr(exc)}
+        # north_star's other target shapes on the same clock (each with its own clock sample); never lose the headline
+        extras = {}
+        fit.close()
+        fit = None
+        if not args.no_extras:
+            for key, fn in (("C3x32", lambda: measure_extra_config("C3", 32, local, 10)),
+                            ("C4x256", lambda: measure_extra_config("C4", 256, local, 5)),
+                            ("C5", lambda: measure_extra_c5(local)),
+                            ("C4_sweep_512_fits", lambda: measure_extra_c4_sweep(local))):
+                try:
+                    extras[key] = fn()
+                except Exception as exc:
+                    extras[key] = {"error": repr(exc)}
         # bounded CPU sample of the same workload (about 10-30 s of host work)
         blas_threads = pin_blas_threads()
         t0 = time.perf_counter()
@@ -532,8 +652,10 @@ def run_gpu(args):
                                                  "sample": "one single-threaded process per host core, one independent fit each"},
                              "note": "reference algorithm restated in numpy (as-written op sequence); R unavailable in image"},
             "parity_vs_oracle": parity,
+            "extras": extras,
         }
-    fit.close()
+    if fit is not None:
+        fit.close()
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()
@@ -550,6 +672,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=0, help="independent fits evaluated per step on each GPU "
                                                          "(default: 64 for C2, 32 for C3, 256 for C4)")
+    ap.add_argument("--no-extras", action="store_true", help="skip the C3 / C4 / C5 extras of the JSON line")
     ap.add_argument("--quick", action="store_true", help="developer A/B runs: device-timed value + stage timers only")
     ap.add_argument("--config", default="C2", choices=["C2", "C3", "C4"],
                     help="workload shape; the default C2 is the configuration BASELINE.json's metric is quoted on")
