@@ -50,6 +50,7 @@ PROTOTYPES = {
     "gps_regress_finalize": (C.c_int, [_h, _dp, C.c_int, _dp, _dp, _dp, _dp, _dp]),
     "gps_predict": (C.c_int, [_h, _dp, C.c_int, C.c_int, _dp, C.c_int, _dp, _dp, _dp]),
     "gps_adjust": (C.c_int, [_h, _dp, _dp, _dp, C.c_int, _dp, _dp]),
+    "gps_metrics": (C.c_int, [_h, _dp, _dp, _dp, C.c_int, _dp, _dp, C.POINTER(C.c_longlong)]),
     "gps_chol_matvec": (C.c_int, [_h, _dp, C.c_int, _dp, _dp]),
     "gps_fit_batch": (C.c_int, [_h, _dp, C.c_int, C.c_int, _dp, _dp, _dp, C.c_int, C.c_int, C.c_int, C.c_double, C.c_int,
                                 C.c_int, _dp, C.c_int, _dp, _dp, _dp, C.POINTER(C.c_int), _dp, _dp, _dp, _dp, _dp,

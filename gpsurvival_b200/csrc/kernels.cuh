@@ -1245,4 +1245,73 @@ __global__ void adjust_kernel(const double* __restrict__ a, const double* __rest
   var_out[i] = ev;
 }
 
+// ---------------------------------------------------------------------------------------
+// CalculateMetrics.R:18,21 — concordance index and RMSE of test predictions.
+// survcomp::concordance.index(x, surv.time, surv.event) (third-party, absent from the reference tree; defaults
+// method = "noether", outx = TRUE) restated from its published definition: a pair (i, j) is USABLE when the shorter
+// observed time is an event (time_i < time_j and event_i = 1; pairs tied in time are not usable); it is CONCORDANT when the
+// higher score x belongs to the shorter time (x is a risk score in survcomp's convention — the reference passes the
+// predicted log survival time as is), DISCORDANT when the lower one does; pairs tied in x are left out (outx = TRUE;
+// CalculateMetrics.R:12-16 jitters tied predictions beforehand anyway, with rnorm: that jitter is NOT restated, ties are
+// reported).  c.index = concordant / (concordant + discordant).  Integer pair counts: exact and order-independent.
+// grid (ceil(m/128), batch), block 128.  counts[b][3] must be zero on entry; sq_part[b][gridDim.x] gets the per-block
+// sums of (time - x)^2 (reduced in block order by metrics_finish_kernel).
+// ---------------------------------------------------------------------------------------
+__global__ void cindex_kernel(const double* __restrict__ x, const double* __restrict__ time, const double* __restrict__ event,
+                              int m, unsigned long long* __restrict__ counts, double* __restrict__ sq_part) {
+  __shared__ double sx[128], st[128];
+  __shared__ double sh[128];
+  __shared__ unsigned long long sc[3];
+  const int b = blockIdx.y, tid = threadIdx.x, i = blockIdx.x * 128 + tid;
+  const double* xb = x + (size_t)b * m;
+  const double* tb = time + (size_t)b * m;
+  const double* eb = event + (size_t)b * m;
+  const bool live = i < m;
+  const double xi = live ? xb[i] : 0.0, ti = live ? tb[i] : 0.0;
+  const bool ev_i = live && eb[i] == 1.0;
+  if (tid < 3) sc[tid] = 0ull;
+  unsigned long long conc = 0, disc = 0, tied = 0;
+  for (int j0 = 0; j0 < m; j0 += 128) {
+    __syncthreads();
+    const int j = j0 + tid;
+    sx[tid] = j < m ? xb[j] : 0.0;
+    st[tid] = j < m ? tb[j] : -INFINITY;      // never later than any time: padding is never the longer time of a pair
+    __syncthreads();
+    if (ev_i) {
+      const int lim = min(128, m - j0);
+      for (int q = 0; q < lim; q++) {
+        if (ti < st[q]) {
+          conc += xi > sx[q];
+          disc += xi < sx[q];
+          tied += xi == sx[q];
+        }
+      }
+    }
+  }
+  atomicAdd(&sc[0], conc);
+  atomicAdd(&sc[1], disc);
+  atomicAdd(&sc[2], tied);
+  const double dv = live ? (ti - xi) : 0.0;
+  sh[tid] = dv * dv;
+  __syncthreads();
+  for (int s2 = 64; s2 > 0; s2 >>= 1) {
+    if (tid < s2) sh[tid] += sh[tid + s2];
+    __syncthreads();
+  }
+  if (tid == 0) sq_part[(size_t)b * gridDim.x + blockIdx.x] = sh[0];
+  if (tid < 3) atomicAdd(&counts[(size_t)b * 3 + tid], sc[tid]);
+}
+
+// c.index = concordant / (concordant + discordant) (NaN without usable untied pairs), rmse = sqrt(sum / m).  grid (batch), block 32
+__global__ void metrics_finish_kernel(const unsigned long long* __restrict__ counts, const double* __restrict__ sq_part, int nblk,
+                                      int m, double* __restrict__ cindex, double* __restrict__ rmse) {
+  const int b = blockIdx.x;
+  if (threadIdx.x != 0) return;
+  const double c = (double)counts[(size_t)b * 3], d = (double)counts[(size_t)b * 3 + 1];
+  cindex[b] = (c + d > 0.0) ? c / (c + d) : NAN;
+  double s = 0.0;
+  for (int k = 0; k < nblk; k++) s += sq_part[(size_t)b * nblk + k];
+  rmse[b] = sqrt(s / (double)m);
+}
+
 }  // namespace gps

@@ -99,6 +99,17 @@ class Fit:
                                            m, dptr(mu), dptr(vf), dptr(vd)))
         return (mu, vf, vd) if self.batch > 1 else (mu[0], vf[0], vd[0])
 
+    def metrics(self, pred, time, event):
+        """gps_metrics: CalculateMetrics.R's c.index (survcomp semantics) and rmse for `batch` sets of m predictions."""
+        P = np.ascontiguousarray(np.asarray(pred, dtype=np.float64)).reshape(self.batch, -1)
+        m = P.shape[1]
+        T = np.ascontiguousarray(np.asarray(time, dtype=np.float64)).reshape(self.batch, m)
+        E = np.ascontiguousarray(np.asarray(event, dtype=np.float64)).reshape(self.batch, m)
+        ci, rm = np.empty(self.batch), np.empty(self.batch)
+        pairs = (C.c_longlong * (3 * self.batch))()
+        self._ck(self.lib.gps_metrics(self.h, dptr(P), dptr(T), dptr(E), m, dptr(ci), dptr(rm), pairs))
+        return {"c.index": ci, "rmse": rm, "pairs": np.array(list(pairs)).reshape(self.batch, 3)}
+
     def set_targets(self, y):
         y = np.ascontiguousarray(np.asarray(y, dtype=np.float64)).reshape(self.batch, self.n)
         self._ck(self.lib.gps_set_targets(self.h, dptr(y)))

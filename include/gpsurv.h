@@ -141,6 +141,16 @@ int gps_predict_rows(gps_handle h, const double* par, int len, int reuse_model, 
 int gps_adjust(gps_handle h, const double* a, const double* mu, const double* s, int c,
                double* mean_out, double* var_out);
 
+/* ---- CalculateMetrics.R:18,21 ---------------------------------------------------------------- */
+/* Concordance index and RMSE of m test predictions per fit (arrays [batch][m]): c.index with survcomp::concordance.index's
+ * semantics — a pair is usable when the shorter time is an event, concordant when the HIGHER score has the shorter time
+ * (x is a risk score there; the reference passes predicted log survival times as is), pairs tied in x excluded
+ * (outx = TRUE); rmse = sqrt(sum((time - pred)^2) / m).  The rnorm jitter CalculateMetrics.R:12-16 applies to tied
+ * predictions is not restated: pairs_out ([batch][3], optional) reports concordant / discordant / tied pair counts.
+ * survAUC::predErr (the Brier score of :23) stays on the host. */
+int gps_metrics(gps_handle h, const double* pred, const double* time, const double* event, int m, double* cindex_out,
+                double* rmse_out, long long* pairs_out);
+
 /* ---- MakeSyntheticData.R:41,148 (synthetic targets) ---------------------------------- */
 /* out = t(chol(Ky)) %*% v = L v, with Ky = K(par) + exp(par[0]) I built from the handle's data and options
  * (par[0] plays the role of the jitter the reference gets from nearPD when K is numerically singular).

@@ -844,3 +844,29 @@ def apply_gp(tts, params, data_source="Generate", ard_mode="intended", as_writte
                 "trainingSetPredictions": pred_train["funcMeanPred"],
                 "logMarLik": reg["logMarLik"], "objective": reg["objective"]})
     return out
+
+
+# --------------------------------------------------------------------------------------
+# CalculateMetrics.R:18,21 (the c-index comes from survcomp, which is not under /root/reference)
+# --------------------------------------------------------------------------------------
+def concordance_index(x, surv_time, surv_event):
+    """survcomp::concordance.index(x, surv.time, surv.event) with its defaults (method='noether', outx=TRUE), restated
+    from its published definition (third-party, version unpinned; call site CalculateMetrics.R:18): a pair is usable
+    when the shorter observed time is an event; it is concordant when the higher score x (a RISK score in survcomp's
+    convention) has the shorter time; pairs tied in x are excluded.  Returns (c.index, concordant, discordant, tied)."""
+    x, t, e = (np.asarray(v, dtype=np.float64).ravel() for v in (x, surv_time, surv_event))
+    conc = disc = tied = 0
+    for i in range(x.size):
+        if e[i] != 1.0:
+            continue
+        later = t[i] < t
+        conc += int(np.sum(later & (x[i] > x)))
+        disc += int(np.sum(later & (x[i] < x)))
+        tied += int(np.sum(later & (x[i] == x)))
+    return (conc / (conc + disc) if conc + disc > 0 else float("nan")), conc, disc, tied
+
+
+def rmse(pred, targets):
+    """CalculateMetrics.R:21."""
+    pred, targets = np.asarray(pred, dtype=np.float64).ravel(), np.asarray(targets, dtype=np.float64).ravel()
+    return float(np.sqrt(np.sum((targets - pred) ** 2) / pred.size))

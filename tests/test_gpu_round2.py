@@ -310,3 +310,24 @@ def test_multi_device_entry_points_equal_single_handle(method):
         assert relmax(res["funcMeanPred"], ref["funcMeanPred"]) <= 1e-6
         assert relmax(res["trainingSetPredictions"], ref["trainingSetPredictions"]) <= 1e-6
         assert relmax(res["par"], ref["par"]) <= 1e-6
+
+
+# ---- CalculateMetrics.R:18,21 on the device ------------------------------------------------------
+def test_metrics_match_oracle_exactly():
+    rng = np.random.default_rng(12)
+    B = 3
+    fit = gp.Fit(0, batch=B)
+    for m in (1, 7, 50, 129, 1000):
+        t = rng.standard_normal((B, m))
+        x = t + 0.5 * rng.standard_normal((B, m))
+        e = (rng.random((B, m)) > 0.3).astype(np.float64)
+        if m >= 50:                       # ties in the predictions and in the times
+            x[:, 5] = x[:, 9]
+            t[:, 11] = t[:, 3]
+        res = fit.metrics(x, t, e)
+        for b in range(B):
+            c, conc, disc, tied = orc.concordance_index(x[b], t[b], e[b])
+            assert list(res["pairs"][b]) == [conc, disc, tied]                     # integer pair counts: exact
+            assert (np.isnan(c) and np.isnan(res["c.index"][b])) or res["c.index"][b] == c
+            assert abs(res["rmse"][b] - orc.rmse(x[b], t[b])) <= 1e-14 * max(1.0, orc.rmse(x[b], t[b]))
+    fit.close()

@@ -286,3 +286,19 @@ def test_lbfgs_twin_minimises_and_agrees_with_vmmin():
     # maxit is a cap on gradient evaluations, as in vmmin
     c = optim.lbfgs(lambda p: orc.nlml(p, X, y, ev, **kw), lambda p: orc.nlml_grad(p, X, y, ev, **kw), p0, maxit=3)
     assert c["convergence"] == 1 and c["counts"][1] == 3
+
+
+def test_concordance_index_restatement_closed_forms():
+    """c-index semantics (survcomp defaults, restated): perfect risk ordering -> 1, reversed -> 0, censored short times
+    make pairs unusable, ties in x are excluded, ties in time are unusable."""
+    t = np.array([1.0, 2.0, 3.0, 4.0, 5.0])
+    e = np.ones(5)
+    assert orc.concordance_index(-t, t, e)[0] == 1.0            # higher risk = shorter time
+    assert orc.concordance_index(t, t, e)[0] == 0.0
+    c, conc, disc, tied = orc.concordance_index(-t, t, np.array([0.0, 1.0, 1.0, 1.0, 1.0]))
+    assert (conc, disc, tied) == (6, 0, 0) and c == 1.0          # the censored shortest time is never the "earlier event"
+    c, conc, disc, tied = orc.concordance_index(np.array([3.0, 3.0, 1.0]), np.array([1.0, 2.0, 3.0]), np.ones(3))
+    assert (conc, disc, tied) == (2, 0, 1) and c == 1.0
+    c, conc, disc, tied = orc.concordance_index(np.array([2.0, 1.0]), np.array([1.0, 1.0]), np.ones(2))
+    assert conc + disc + tied == 0 and np.isnan(c)
+    assert abs(orc.rmse([1.0, 2.0], [2.0, 4.0]) - np.sqrt(2.5)) < 1e-15
