@@ -37,6 +37,8 @@ PROTOTYPES = {
     "gps_last_error": (C.c_char_p, [_h]),
     "gps_last_pivot": (C.c_int, [_h]),
     "gps_batch_pivots": (C.c_int, [_h, C.POINTER(C.c_int)]),
+    "gps_set_near_pd": (C.c_int, [_h, C.c_int]),
+    "gps_near_pd_used": (C.c_int, [_h, C.POINTER(C.c_int)]),
     "gps_create": (C.c_int, [C.c_int, C.POINTER(_h)]),
     "gps_create_batch": (C.c_int, [C.c_int, C.c_int, C.POINTER(_h)]),
     "gps_destroy": (C.c_int, [_h]),

@@ -112,7 +112,15 @@ struct AccTile {
   int m_base, n_base;      // global (tile + warp + lane) coordinates of v[0][0][0]
   int m0, n0;              // tile origin
   int batch, split, node;
+  bool skip;               // this warp's sub-tile lies entirely above the diagonal of a lower-triangular product's diagonal
+                           // tile: its accumulators were not computed (zeros) and nothing of it may be stored
 };
+
+// Epilogues that tolerate (and honour) AccTile::skip declare `static constexpr bool kSkipUpper = true`.
+template <class Epi, class = void>
+struct epi_skips_upper { static constexpr bool value = false; };
+template <class Epi>
+struct epi_skips_upper<Epi, decltype((void)Epi::kSkipUpper)> { static constexpr bool value = Epi::kSkipUpper; };
 
 template <class Cfg, bool A_KC, bool B_KC>
 struct SmemLayout {
@@ -201,6 +209,9 @@ __global__ void __launch_bounds__(Cfg::NT) dmma_gemm_kernel(GemmParams p_in, Epi
 #pragma unroll
     for (int j = 0; j < FN; j++) acc.v[i][j][0] = acc.v[i][j][1] = 0.0;
 
+  // diagonal tile of a lower-triangular product: a warp whose sub-tile is entirely above the diagonal has nothing to do
+  const bool skip = epi_skips_upper<Epi>::value && p.lower && p.diag_off == 0 && m0 == n0 && (wm0 + Cfg::WM - 1 < wn0);
+
   auto issue = [&](int stage, int kt) {
     const int kbase = k_lo + kt * BK;
     load_tile<BM, BK, SL::LDA, NT, A_KC>(sA + stage * SL::A_STAGE, A, p.lda, m0, p.M, kbase, p.K, tid);
@@ -223,6 +234,7 @@ __global__ void __launch_bounds__(Cfg::NT) dmma_gemm_kernel(GemmParams p_in, Epi
     }
     const double* a_s = sA + (kt % STAGES) * SL::A_STAGE;
     const double* b_s = sB + (kt % STAGES) * SL::B_STAGE;
+    if (skip) continue;
 #pragma unroll
     for (int ks = 0; ks < BK / 4; ks++) {
       double af[FM], bf[FN];
@@ -252,6 +264,7 @@ __global__ void __launch_bounds__(Cfg::NT) dmma_gemm_kernel(GemmParams p_in, Epi
   acc.batch = batch;
   acc.split = split;
   acc.node = node;
+  acc.skip = skip;
   epi(p, acc, smem);
 }
 
@@ -274,8 +287,12 @@ struct EpiPlain {
   double* Ct;
   int ldct;
   long long nodeStrideCt;
+  // lower-triangular products (p.lower): what lies above the diagonal inside a diagonal tile is never read by any consumer
+  // of the Gram slices / the Cholesky's trailing matrix / Kinv, so warps that own only such entries skip the tile
+  static constexpr bool kSkipUpper = true;
   template <class Cfg>
   __device__ __forceinline__ void operator()(const GemmParams& p, AccTile<Cfg>& a, double*) const {
+    if (a.skip) return;
     double* __restrict__ Cb = C + (size_t)a.batch * strideC + (size_t)a.split * strideSplit + (size_t)a.node * nodeStrideC;
     if (Ct) {
       double* __restrict__ Tb = Ct + (size_t)a.batch * strideC + (size_t)a.node * nodeStrideCt;
@@ -502,6 +519,7 @@ struct EpiWK {
   double* wdiag;          // [batch][ldn]
   double* rs_part;        // [batch][nblk][ldn]
   int ldn, nblk, nvalid;  // nvalid = n (rows/columns >= n are identity padding and are skipped)
+  static constexpr bool kSkipUpper = true;
   template <class Cfg>
   __device__ __forceinline__ void operator()(const GemmParams& p, AccTile<Cfg>& a, double* smem) const {
     // (lower-tile products only ever run on square tiles; the non-square configurations merely have to compile)
@@ -522,15 +540,17 @@ struct EpiWK {
 #pragma unroll
         for (int e = 0; e < 2; e++) {
           const int m = a.m_base + 8 * i + e;
-          if (m >= nvalid || n >= nvalid) continue;
-          const int r = m > n ? m : n, c = m > n ? n : m;
+          if (m >= nvalid || n >= nvalid || m < n) continue;   // (m < n only inside a diagonal tile)
           const double w = al[m] * an - a.v[i][j][e];
-          const double mv = w * Kb[(size_t)r + (size_t)c * ldk];
+          const double mv = w * Kb[(size_t)m + (size_t)n * ldk];
           Mb[(size_t)m + (size_t)n * ldk] = mv;
-          if (!diag) Mb[(size_t)n + (size_t)m * ldk] = mv;
-          if (m == n) wdiag[(size_t)a.batch * ldn + m] = w;
           rsum[i][e] += mv;
-          cs += mv;
+          if (m == n) {
+            wdiag[(size_t)a.batch * ldn + m] = w;
+          } else {
+            Mb[(size_t)n + (size_t)m * ldk] = mv;
+            cs += mv;
+          }
         }
       }
       csum[j] = cs;
@@ -561,19 +581,17 @@ struct EpiWK {
     double* rp = rs_part + (size_t)a.batch * nblk * ldn;
     const int ti = a.m0 / Cfg::BM, tj = a.n0 / Cfg::BN;
     for (int c = threadIdx.x; c < Cfg::BM; c += Cfg::NT) {
-      const int m = a.m0 + c;
-      if (m < nvalid) {
-        double sr = 0.0;
+      const int m = a.m0 + c, n = a.n0 + c;
+      double sr = 0.0, sc = 0.0;
 #pragma unroll
-        for (int w = 0; w < Cfg::WARPS_N; w++) sr += rowp[w * Cfg::BM + c];
-        rp[(size_t)tj * ldn + m] = sr;
-      }
-      const int n = a.n0 + c;
-      if (!diag && n < nvalid) {
-        double sc = 0.0;
+      for (int w = 0; w < Cfg::WARPS_N; w++) sr += rowp[w * Cfg::BM + c];
 #pragma unroll
-        for (int w = 0; w < Cfg::WARPS_M; w++) sc += colp[w * Cfg::BN + c];
-        rp[(size_t)ti * ldn + n] = sc;
+      for (int w = 0; w < Cfg::WARPS_M; w++) sc += colp[w * Cfg::BN + c];
+      if (diag) {
+        if (m < nvalid) rp[(size_t)tj * ldn + m] = sr + sc;
+      } else {
+        if (m < nvalid) rp[(size_t)tj * ldn + m] = sr;
+        if (n < nvalid) rp[(size_t)ti * ldn + n] = sc;
       }
     }
   }

@@ -329,6 +329,9 @@ __global__ void __launch_bounds__(Cfg::NTHREADS, Cfg::CTAS_PER_SM)
       for (int i = 0; i < FM; i++)
 #pragma unroll
         for (int j = 0; j < FN; j++) acc.v[i][j][0] = acc.v[i][j][1] = 0.0;
+      // diagonal tile of a lower-triangular product: a warp whose sub-tile lies entirely above the diagonal only keeps the
+      // pipeline's barriers in step (it waits for each stage and releases it without touching the data)
+      const bool skip = epi_skips_upper<Epi>::value && w.p.lower && w.p.diag_off == 0 && w.m0 == w.n0 && (wm0 + Cfg::WM - 1 < wn0);
 
       if (w.nkt == 0) {
         __syncwarp();
@@ -342,6 +345,7 @@ __global__ void __launch_bounds__(Cfg::NTHREADS, Cfg::CTAS_PER_SM)
         }
         const double* a_s = sA + s * SL::A_STAGE;
         const double* b_s = sB + s * SL::B_STAGE;
+        if (!skip) {
 #pragma unroll
         for (int ks = 0; ks < BK / 4; ks++) {
           double af[FM], bf[FN];
@@ -365,9 +369,11 @@ __global__ void __launch_bounds__(Cfg::NTHREADS, Cfg::CTAS_PER_SM)
 #pragma unroll
             for (int j = 0; j < FN; j++) dmma884(acc.v[i][j][0], acc.v[i][j][1], bf[j], af[i]);
         }
+        }
         __syncwarp();
         if (lane == 0) ws::mbar_arrive(empty + s);
       }
+      acc.skip = skip;
       acc.m0 = w.m0;
       acc.n0 = w.n0;
       acc.m_base = w.m0 + wm0 + 2 * t4;

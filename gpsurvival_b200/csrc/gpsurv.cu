@@ -148,6 +148,9 @@ struct gps_handle_s {
   double last_ms = 0.0;
   int last_pivot = 0;
   std::vector<int> pivots;      // per-fit failing pivot of the last evaluation (0 = factorised)
+  int near_pd = 1;              // gps_set_near_pd: repair a non-positive-definite Ky with Matrix::nearPD's algorithm on the device
+                                // (ForOptimisationLog.R:43-51) instead of reporting GPS_ERR_NOT_PD
+  std::vector<int> near_used;   // per fit: 1 when the last evaluation's value came from the repaired matrix
   bool tolerate_not_pd = false; // inside gps_fit_batch: a fit that fails to factorise is dropped (NaN outputs, per-fit status),
                                 // the others go on — what the reference loses on such a fit is that one fit
   std::vector<int> fit_status;  // per-fit status of the last gps_fit_batch (GPS_OK / GPS_ERR_NOT_PD)
@@ -1041,6 +1044,7 @@ int gps_nlml_grad(gps_handle h, const double* par, int len, double* nlml_out, do
 }
 #include "fit_batch.cuh"
 #include "lbfgs.cuh"
+#include "nearpd.cuh"
 
 extern "C" {
 
@@ -1430,6 +1434,36 @@ int gps_set_noise_corr(gps_handle h, const double* log_sc2, int len) {
   return GPS_OK;
 }
 
+// ForOptimisationLog.R:43-51: for every fit whose Cholesky failed, repair Ky with nearPD on the device and re-evaluate.
+// Returns GPS_OK when every failed fit was recovered (outputs patched), else the first error (GPS_ERR_NOT_PD included).
+static int recover_not_pd(gps_handle h, int len, bool want_grad, double* nlml_out, double* grad_out) {
+  const int B = h->batch;
+  h->near_used.assign(B, 0);
+  int first_err = GPS_OK;
+  std::string first_msg;
+  for (int b = 0; b < B; b++) {
+    if (h->pivots[b] == 0) continue;
+    int rc = nearpd_recover(h, b, want_grad);
+    if (rc == GPS_OK) {
+      double f = 0.0;
+      if (cudaMemcpy(&f, h->d_nlml + b, sizeof(double), cudaMemcpyDeviceToHost) != cudaSuccess) return fail(h, GPS_ERR_CUDA, "nearPD: result copy failed");
+      if (nlml_out) nlml_out[b] = f;
+      if (want_grad && grad_out &&
+          cudaMemcpy(grad_out + (size_t)b * len, h->d_grad + (size_t)b * h->par_cap, sizeof(double) * len, cudaMemcpyDeviceToHost) != cudaSuccess)
+        return fail(h, GPS_ERR_CUDA, "nearPD: gradient copy failed");
+      h->pivots[b] = 0;
+      h->near_used[b] = 1;
+    } else if (first_err == GPS_OK) {
+      first_err = rc;
+      first_msg = h->err;
+    }
+  }
+  h->fact_level = 0;                    // the repaired factorisation must not be mistaken for chol(Ky) by finalize / predict
+  if (first_err != GPS_OK) return fail(h, first_err, first_msg);
+  h->last_pivot = 0;
+  return GPS_OK;
+}
+
 int gps_nlml(gps_handle h, const double* par, int len, double* nlml_out) {
   int rc = check_handle(h);
   if (rc) return rc;
@@ -1440,9 +1474,17 @@ int gps_nlml(gps_handle h, const double* par, int len, double* nlml_out) {
   rc = fetch_info(h);
   if (rc && rc != GPS_ERR_NOT_PD) return rc;
   memcpy(nlml_out, h->pin, sizeof(double) * h->batch);
+  h->near_used.assign(h->batch, 0);
   if (rc == GPS_ERR_NOT_PD) {   // outputs stay usable: +Inf marks the fits that failed to factorise
     for (int b = 0; b < h->batch; b++)
       if (h->pivots[b] != 0) nlml_out[b] = INFINITY;
+    if (h->near_pd) {           // ForOptimisationLog.R:43-51: nearPD(Ky), then carry on
+      const std::string msg = h->err;
+      const int r2 = recover_not_pd(h, len, false, nlml_out, nullptr);
+      if (r2 == GPS_OK) return GPS_OK;
+      if (r2 != GPS_ERR_NOT_PD) return r2;
+      if (h->err.empty()) h->err = msg;
+    }
     return rc;
   }
   remember_fact(h, par, len, 1);
@@ -1481,12 +1523,24 @@ int gps_nlml_grad(gps_handle h, const double* par, int len, double* nlml_out, do
   if (rc && rc != GPS_ERR_NOT_PD) return rc;
   if (nlml_out) memcpy(nlml_out, h->pin, sizeof(double) * h->batch);
   memcpy(grad_out, h->pin + h->batch, sizeof(double) * tot);
+  h->near_used.assign(h->batch, 0);
   if (rc == GPS_ERR_NOT_PD) {
     for (int b = 0; b < h->batch; b++)
       if (h->pivots[b] != 0) {
         if (nlml_out) nlml_out[b] = INFINITY;
         for (int k = 0; k < len; k++) grad_out[(size_t)b * len + k] = NAN;
       }
+    if (h->near_pd) {
+      // fn and gr must agree on which points are acceptable (optim calls them separately): the value comes from the
+      // repaired matrix exactly as in gps_nlml, and the gradient is the same contraction with the inverse of that matrix.
+      // (The reference's gr inverts the ORIGINAL, indefinite Ky by LU, OptimisationGradientLog.R:43-45 — a number that is
+      // not the slope of what its fn returned; this is the consistent choice.)
+      const std::string msg = h->err;
+      const int r2 = recover_not_pd(h, len, true, nlml_out, grad_out);
+      if (r2 == GPS_OK) return GPS_OK;
+      if (r2 != GPS_ERR_NOT_PD) return r2;
+      if (h->err.empty()) h->err = msg;
+    }
     return rc;
   }
   remember_fact(h, par, len, 2);
@@ -1873,6 +1927,18 @@ int gps_metrics(gps_handle h, const double* pred, const double* time, const doub
     if (pairs_out)
       for (int q = 0; q < 3; q++) pairs_out[(size_t)b * 3 + q] = (long long)cnt[(size_t)b * 3 + q];
   }
+  return GPS_OK;
+}
+
+int gps_set_near_pd(gps_handle h, int enable) {
+  if (!h) return fail(nullptr, GPS_ERR_ARG, "handle is NULL");
+  h->near_pd = enable != 0;
+  return GPS_OK;
+}
+
+int gps_near_pd_used(gps_handle h, int* used_out) {
+  if (!h || !used_out) return fail(h, GPS_ERR_ARG, "gps_near_pd_used: bad arguments");
+  for (int b = 0; b < h->batch; b++) used_out[b] = b < (int)h->near_used.size() ? h->near_used[b] : 0;
   return GPS_OK;
 }
 

@@ -142,6 +142,15 @@ class Fit:
             self._ck(rc)
         return (out, g) if self.batch > 1 else (float(out[0]), g[0])
 
+    def set_near_pd(self, enable=True):
+        """gps_set_near_pd: the device-side Matrix::nearPD repair of a non-positive-definite Ky (ForOptimisationLog.R:43-51)."""
+        self._ck(self.lib.gps_set_near_pd(self.h, 1 if enable else 0))
+
+    def near_pd_used(self):
+        out = (C.c_int * self.batch)()
+        self._ck(self.lib.gps_near_pd_used(self.h, out))
+        return list(out)
+
     def pivots(self):
         out = (C.c_int * self.batch)()
         self._ck(self.lib.gps_batch_pivots(self.h, out))

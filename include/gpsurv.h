@@ -63,6 +63,16 @@ int gps_last_pivot(gps_handle h);              /* failing pivot of the last GPS_
  * the reference would fall back to Matrix::nearPD (ForOptimisationLog.R:43-51). */
 int gps_batch_pivots(gps_handle h, int* pivots_out);
 
+/* ForOptimisationLog.R:43-51: when chol(Ky) fails the reference factorises Matrix::nearPD(Ky)$mat instead and carries on.
+ * The library does the same ON THE DEVICE (Higham's alternating projections with Matrix::nearPD's defaults over a Jacobi
+ * eigen-solver, csrc/nearpd.cuh; n <= 4096) for every fit of the batch whose factorisation failed, in gps_nlml and — so that
+ * optim's fn and gr agree on which points are acceptable — in gps_nlml_grad.  enable = 0 turns the repair off: such fits
+ * then report GPS_ERR_NOT_PD / +Inf as described above.  Default: on.  gps_regress_finalize and gps_predict never repair
+ * (GPRegression.R:65-69 and GPPredict.R:43 call plain chol).  gps_near_pd_used: per fit, 1 when the last evaluation's value
+ * came from a repaired matrix. */
+int gps_set_near_pd(gps_handle h, int enable);
+int gps_near_pd_used(gps_handle h, int* used_out);
+
 /* ---- lifetime ----------------------------------------------------------------------- */
 /* One handle = one fit (one trainingTestStructure) on one device.  `batch` > 1 makes it a
  * batch of `batch` independent fits of identical shape evaluated by the same launches

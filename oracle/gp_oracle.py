@@ -143,9 +143,47 @@ def _noise_diag(n, log_sn2, events, noise_corr, log_hyp_noise_corr):
 
 
 def _chol_lower(Ky):
-    """chol(K) then t() (ForOptimisationLog.R:41-42,54). Raises LinAlgError if not PD;
-    the nearPD fallback (:43-51) stays host-side and out of scope."""
+    """chol(K) then t() (ForOptimisationLog.R:41-42,54). Raises LinAlgError if not PD (the caller decides about the
+    nearPD fallback of :43-51)."""
     return np.linalg.cholesky(Ky)
+
+
+def near_pd(x, eig_tol=1e-6, conv_tol=1e-7, posd_tol=1e-8, maxit=100):
+    """Matrix::nearPD(x) with its defaults (corr=FALSE, keepDiag=FALSE, do2eigen=TRUE, doSym=FALSE, doDykstra=TRUE,
+    conv.norm.type="I") — third-party (Matrix is not under /root/reference, version unpinned; call site
+    ForOptimisationLog.R:43-44), restated from its published algorithm: Higham's (2002) alternating projections with
+    Dykstra's correction.  Each iteration projects R = Y - D_S onto the matrices whose eigenvalues exceed
+    eig.tol * lambda_max (smaller ones are DROPPED, not clipped), until the relative infinity-norm change is below
+    conv.tol; then (do2eigen) eigenvalues below posd.tol * lambda_max are raised to that value and the result is
+    rescaled to keep the diagonal.  Returns (mat, converged, iterations)."""
+    x = np.asarray(x, dtype=np.float64)
+    x = 0.5 * (x + x.T)                                    # ensureSymmetry (symmpart)
+    n = x.shape[0]
+    D_S = np.zeros_like(x)
+    X = x.copy()
+    it, converged = 0, False
+    while it < maxit and not converged:
+        Y = X
+        R = Y - D_S
+        d, Q = np.linalg.eigh(R)
+        p = d > eig_tol * d[-1]
+        if not np.any(p):
+            raise np.linalg.LinAlgError("Matrix seems negative semi-definite")
+        Qp = Q[:, p]
+        X = (Qp * d[p]) @ Qp.T
+        D_S = X - R
+        conv = np.linalg.norm(Y - X, np.inf) / np.linalg.norm(Y, np.inf)
+        it += 1
+        converged = conv <= conv_tol
+    d, Q = np.linalg.eigh(X)
+    eps = posd_tol * abs(d[-1])
+    if d[0] < eps:
+        d = np.where(d < eps, eps, d)
+        o_diag = np.diag(X).copy()
+        X = Q @ (d[:, None] * Q.T)
+        D = np.sqrt(np.maximum(eps, o_diag) / np.diag(X))
+        X = D[:, None] * X * D[None, :]
+    return X, converged, it
 
 
 def _solve_as_written(L, rhs):
@@ -158,11 +196,12 @@ def _solve_as_written(L, rhs):
 # ForOptimisationLog.R
 # --------------------------------------------------------------------------------------
 def nlml(par, X, y, events, cov_form="SqExp", mean_form="Zero", noise_corr=False,
-         log_hyp_noise_corr=None, ard_mode="intended", as_written_ops=True, extra_param=None):
+         log_hyp_noise_corr=None, ard_mode="intended", as_written_ops=True, extra_param=None, near_pd_fallback=False):
     """Negative log marginal likelihood (ForOptimisationLog.R:1-68, imposePriors=FALSE).
 
     ``as_written_ops=True`` repeats the reference's redundant work (Cholesky probed then
     recomputed, :41-42; general solves, :55) — this is what the CPU baseline times.
+    ``near_pd_fallback=True``: when chol(Ky) fails, factorise Matrix::nearPD(Ky)$mat instead (:43-51).
     """
     X = np.asarray(X, dtype=np.float64)
     y = np.asarray(y, dtype=np.float64).ravel()
@@ -172,9 +211,18 @@ def nlml(par, X, y, events, cov_form="SqExp", mean_form="Zero", noise_corr=False
     m = mean_func(mean_hyp, X, mean_form)                                    # :34
     K = cov_func(X, X, math.exp(log_sf2), np.exp(log_ell), cov_form, ard_mode, extra_param)
     Ky = K + np.diag(_noise_diag(n, log_sn2, events, noise_corr, lnc))       # :35-40
-    if as_written_ops:
-        _chol_lower(Ky)                                                      # :41 (probe)
-    L = _chol_lower(Ky)                                                      # :42,54
+    if near_pd_fallback:
+        try:
+            L = _chol_lower(Ky)                                              # :41-42
+        except np.linalg.LinAlgError:
+            near, converged, _ = near_pd(Ky)                                 # :43-45
+            if not converged:
+                raise
+            L = _chol_lower(near)                                            # :48
+    else:
+        if as_written_ops:
+            _chol_lower(Ky)                                                  # :41 (probe)
+        L = _chol_lower(Ky)                                                  # :42,54
     if as_written_ops:
         alpha = _solve_as_written(L, y - m)                                  # :55
     else:

@@ -314,6 +314,7 @@ def test_error_paths():
     # duplicate rows + vanishing noise => numerically singular Ky => NOT_PD with a pivot index
     Xd = np.vstack([X, X])
     fit.set_data(Xd, np.concatenate([y, y]), np.concatenate([ev, ev]))
+    fit.set_near_pd(False)                              # without the nearPD repair (tests/test_gpu_round2.py covers it)
     with pytest.raises(gp.NotPositiveDefinite) as e:
         fit.nlml(np.array([-800.0, 0.0, 0.0]))
     assert e.value.code == _lib.GPS_ERR_NOT_PD and 1 <= e.value.pivot <= 80
@@ -391,6 +392,7 @@ def test_not_pd_is_per_fit_and_non_fatal_for_optimisers():
     Xd = np.vstack([X, X])                       # duplicate rows: singular without noise
     yd, evd = np.concatenate([y, y]), np.concatenate([ev, ev])
     bf = gp.Fit(0, batch=2)
+    bf.set_near_pd(False)
     bf.set_data(np.stack([Xd, Xd]), np.stack([yd, yd]), np.stack([evd, evd]))
     par = np.array([[-800.0, 0.0, 0.0], np.log([0.2, 0.8, 2.0])])
     with pytest.raises(gp.NotPositiveDefinite):

@@ -331,3 +331,50 @@ def test_metrics_match_oracle_exactly():
             assert (np.isnan(c) and np.isnan(res["c.index"][b])) or res["c.index"][b] == c
             assert abs(res["rmse"][b] - orc.rmse(x[b], t[b])) <= 1e-14 * max(1.0, orc.rmse(x[b], t[b]))
     fit.close()
+
+
+# ---- Matrix::nearPD on the device (ForOptimisationLog.R:43-51) -----------------------------------
+@pytest.mark.parametrize("n_half", [40, 41])          # n = 80 (even) and 82 -> also an odd case below
+def test_near_pd_fallback_matches_oracle(n_half):
+    pb = synth.make_problem(n_half, 5, 2, 10, 1)
+    X, y, ev = pb["trainingData"], np.log(pb["trainingTargets"]), pb["events"]
+    Xd = np.vstack([X, X])                       # duplicate rows: Ky singular without noise
+    yd, evd = np.concatenate([y, y]), np.concatenate([ev, ev])
+    if n_half == 41:                             # odd n: the identity-padded route
+        Xd, yd, evd = Xd[:-1], yd[:-1], evd[:-1]
+    par = np.array([-800.0, 0.0, 0.0])
+    fo = orc.nlml(par, Xd, yd, evd, near_pd_fallback=True)
+    fit = gp.Fit(0)
+    fit.set_data(Xd, yd, evd)
+    f = fit.nlml(par)                            # chol fails -> nearPD(Ky) on the device -> chol -> NLML
+    assert fit.near_pd_used() == [1]
+    # the repaired matrix has condition 1e8 by construction (posd.tol): agreement is limited by that, not by the solver
+    assert abs(f - fo) <= 1e-6 * abs(fo), (f, fo)
+    f2, g2 = fit.nlml_grad(par)                  # fn and gr agree on the point: same value, finite gradient
+    assert abs(f2 - f) <= 1e-9 * abs(f) and np.all(np.isfinite(g2))
+    # a positive definite point on the same handle is untouched by the machinery
+    p_ok = np.log([0.2, 0.8, 2.0])
+    assert abs(fit.nlml(p_ok) - orc.nlml(p_ok, Xd, yd, evd)) <= 1e-9 * abs(orc.nlml(p_ok, Xd, yd, evd))
+    assert fit.near_pd_used() == [0]
+    fit.close()
+
+
+def test_near_pd_is_per_fit_in_a_batch():
+    pb = synth.make_problem(40, 5, 2, 10, 1)
+    X, y, ev = pb["trainingData"], np.log(pb["trainingTargets"]), pb["events"]
+    Xd, yd, evd = np.vstack([X, X]), np.concatenate([y, y]), np.concatenate([ev, ev])
+    bf = gp.Fit(0, batch=3)
+    bf.set_data(np.stack([Xd] * 3), np.stack([yd] * 3), np.stack([evd] * 3))
+    par = np.array([np.log([0.2, 0.8, 2.0]), [-800.0, 0.0, 0.0], np.log([0.3, 0.7, 1.5])])
+    f = bf.nlml(par)
+    assert bf.near_pd_used() == [0, 1, 0]
+    for b in (0, 2):
+        fo = orc.nlml(par[b], Xd, yd, evd)
+        assert abs(f[b] - fo) <= 1e-9 * abs(fo)
+    fo = orc.nlml(par[1], Xd, yd, evd, near_pd_fallback=True)
+    assert abs(f[1] - fo) <= 1e-6 * abs(fo)
+    # a whole Nelder-Mead fit that starts at the singular point now proceeds the way the reference would
+    res = bf.fit_batch(np.stack([Xd] * 3), np.stack([yd] * 3), np.stack([evd] * 3), par, np.stack([X[:7]] * 3),
+                       method="Nelder-Mead", maxit=15, survival=False)
+    assert np.all(np.isfinite(res["objective"])) and res["objective"][1] < f[1]
+    bf.close()
