@@ -53,6 +53,8 @@ PROTOTYPES = {
     "gps_predict": (C.c_int, [_h, _dp, C.c_int, C.c_int, _dp, C.c_int, _dp, _dp, _dp]),
     "gps_adjust": (C.c_int, [_h, _dp, _dp, _dp, C.c_int, _dp, _dp]),
     "gps_metrics": (C.c_int, [_h, _dp, _dp, _dp, C.c_int, _dp, _dp, C.POINTER(C.c_longlong)]),
+    "gps_synth_generate": (C.c_int, [_h, C.c_ulonglong, C.c_int, C.c_int, C.c_double, C.c_double, C.c_double, C.c_double, C.c_int,
+                                     C.c_double, C.c_double, _dp, _dp, _dp, _dp, C.POINTER(C.c_int)]),
     "gps_chol_matvec": (C.c_int, [_h, _dp, C.c_int, _dp, _dp]),
     "gps_fit_batch": (C.c_int, [_h, _dp, C.c_int, C.c_int, _dp, _dp, _dp, C.c_int, C.c_int, C.c_int, C.c_double, C.c_int,
                                 C.c_int, _dp, C.c_int, _dp, _dp, _dp, C.POINTER(C.c_int), _dp, _dp, _dp, _dp, _dp,

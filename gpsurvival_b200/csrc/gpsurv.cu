@@ -1045,6 +1045,7 @@ int gps_nlml_grad(gps_handle h, const double* par, int len, double* nlml_out, do
 #include "fit_batch.cuh"
 #include "lbfgs.cuh"
 #include "nearpd.cuh"
+#include "synthgen.cuh"
 
 extern "C" {
 
@@ -1973,6 +1974,76 @@ int gps_chol_matvec(gps_handle h, const double* par, int len, const double* v, d
   rc = fetch_info(h);
   if (rc) return rc;
   memcpy(out, h->pin + (size_t)n * B, sizeof(double) * n * B);
+  h->fact_level = 0;
+  return GPS_OK;
+}
+
+// MakeSyntheticData.R:40-41,145-149 + CensorData.R:36-48 on the device (csrc/synthgen.cuh): `batch` data sets of n samples x d
+// features with seeds (seed, data set index).  The handle's data and options are replaced by the generator's (SqExp, zero mean).
+int gps_synth_generate(gps_handle h, unsigned long long seed, int n, int d, double sn2, double sf2, double ell, double jitter,
+                       int n_censor, double cens_mean, double cens_sd, double* X_out, double* y_out, double* events_out,
+                       double* y_uncensored_out, int* n_censored_out) {
+  int rc = check_handle(h);
+  if (rc) return rc;
+  if (n < 1 || d < 1 || !(sn2 >= 0.0) || !(sf2 > 0.0) || !(ell > 0.0) || !(jitter > 0.0) || n_censor < 0 || n_censor > n || !X_out || !y_out ||
+      !events_out)
+    return fail(h, GPS_ERR_ARG, "gps_synth_generate: bad arguments");
+  rc = gps_set_options(h, GPS_COV_SQEXP, GPS_MEAN_ZERO, GPS_NC_NONE, GPS_ARD_INTENDED);
+  if (rc) return rc;
+  CK(h, cudaStreamSynchronize(h->st));
+  rc = ensure_shape(h, n, d);
+  if (rc) return rc;
+  const int B = h->batch;
+  double *d2 = nullptr, *y0 = nullptr, *yc = nullptr, *evc = nullptr;
+  int *rem = nullptr, *done = nullptr;
+  auto cleanup = [&]() { cudaStreamSynchronize(h->st); cudaFree(d2); cudaFree(y0); cudaFree(yc); cudaFree(evc); cudaFree(rem); cudaFree(done); };
+#define SG_CK(call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) { cleanup(); return fail(h, GPS_ERR_CUDA, std::string("gps_synth_generate: ") + cudaGetErrorString(e__)); } } while (0)
+  const size_t vecB = (size_t)h->ld * B;
+  SG_CK(dalloc(&d2, vecB)); SG_CK(dalloc(&y0, vecB)); SG_CK(dalloc(&yc, vecB)); SG_CK(dalloc(&evc, vecB));
+  SG_CK(dalloc(&rem, (size_t)n * B, false)); SG_CK(dalloc(&done, (size_t)B));
+  // x ~ N(0,1) straight into the (uncentred) data matrix, d2 aside
+  synth_normals_kernel<<<dim3(ceil_div(ceil_div(n * d, 2), 256), B), 256, 0, h->st>>>(h->Xaug, h->strideX, n * d, n, h->ldx, 0, seed);
+  synth_normals_kernel<<<dim3(ceil_div(ceil_div(n, 2), 256), B), 256, 0, h->st>>>(d2, h->ld, n, n, h->ld, 2, seed);
+  h->launches += 2;
+  for (int b = 0; b < B; b++)
+    SG_CK(cudaMemcpy2DAsync(X_out + (size_t)b * n * d, (size_t)n * sizeof(double), h->Xaug + (size_t)b * h->strideX,
+                            (size_t)h->ldx * sizeof(double), (size_t)n * sizeof(double), d, cudaMemcpyDeviceToHost, h->st));
+  SG_CK(cudaMemsetAsync(h->y, 0, sizeof(double) * vecB, h->st));
+  {
+    std::vector<double> ones((size_t)n * B, 1.0);
+    SG_CK(cudaMemcpy2DAsync(h->events, (size_t)h->ld * sizeof(double), ones.data(), (size_t)n * sizeof(double), (size_t)n * sizeof(double), B,
+                            cudaMemcpyHostToDevice, h->st));
+    SG_CK(cudaStreamSynchronize(h->st));
+  }
+  rc = postprocess_data(h);
+  if (rc) { cleanup(); return rc; }
+  // L = chol(K + jitter I) by the library's own factorisation (par[0] is the jitter), f = L d1
+  std::vector<double> par((size_t)3 * B);
+  for (int b = 0; b < B; b++) { par[3 * b] = log(jitter); par[3 * b + 1] = log(sf2); par[3 * b + 2] = log(ell); }
+  rc = do_factor(h, par.data(), 3, true);
+  if (!rc) rc = fetch_info(h);
+  if (rc) { cleanup(); return rc; }   // GPS_ERR_NOT_PD: raise the jitter (the reference calls nearPD there, MakeSyntheticData.R:42-51)
+  // d1 into the (now free) right-hand-side slot: the factorisation's NLML assembly has just used it
+  synth_normals_kernel<<<dim3(ceil_div(ceil_div(n, 2), 256), B), 256, 0, h->st>>>(h->zvec, 2 * (long long)h->ld, n, n, h->ld, 1, seed);
+  h->launches++;
+  trmv_lower_kernel<<<dim3(ceil_div(n, 128), B), 128, 0, h->st>>>(h->L, n, h->ld, h->strideM, h->zvec, 2 * h->ld, h->zvec + h->ld);
+  synth_targets_kernel<<<dim3(ceil_div(n, 256), B), 256, 0, h->st>>>(h->zvec + h->ld, d2, n, h->ld, sn2, y0);
+  synth_censor_kernel<<<B, 32, 0, h->st>>>(y0, n, h->ld, n_censor, cens_mean, cens_sd, seed, yc, evc, rem, done);
+  h->launches += 3;
+  SG_CK(cudaGetLastError());
+  SG_CK(cudaMemcpy2DAsync(y_out, (size_t)n * sizeof(double), yc, (size_t)h->ld * sizeof(double), (size_t)n * sizeof(double), B,
+                          cudaMemcpyDeviceToHost, h->st));
+  SG_CK(cudaMemcpy2DAsync(events_out, (size_t)n * sizeof(double), evc, (size_t)h->ld * sizeof(double), (size_t)n * sizeof(double), B,
+                          cudaMemcpyDeviceToHost, h->st));
+  if (y_uncensored_out)
+    SG_CK(cudaMemcpy2DAsync(y_uncensored_out, (size_t)n * sizeof(double), y0, (size_t)h->ld * sizeof(double), (size_t)n * sizeof(double), B,
+                            cudaMemcpyDeviceToHost, h->st));
+  std::vector<int> hdone(B);
+  SG_CK(cudaMemcpyAsync(hdone.data(), done, sizeof(int) * B, cudaMemcpyDeviceToHost, h->st));
+  SG_CK(cudaStreamSynchronize(h->st));
+#undef SG_CK
+  cleanup();
+  if (n_censored_out) std::copy(hdone.begin(), hdone.end(), n_censored_out);
   h->fact_level = 0;
   return GPS_OK;
 }

@@ -110,6 +110,17 @@ class Fit:
         self._ck(self.lib.gps_metrics(self.h, dptr(P), dptr(T), dptr(E), m, dptr(ci), dptr(rm), pairs))
         return {"c.index": ci, "rmse": rm, "pairs": np.array(list(pairs)).reshape(self.batch, 3)}
 
+    def synth_generate(self, seed, n, d, sn2=0.01, sf2=0.5, ell=1.1, jitter=1e-8, n_censor=0, cens_mean=0.0, cens_sd=50.0):
+        """gps_synth_generate: MakeSyntheticData ('likeRealData') + CensorData ('NormalLoopSample') on the device, `batch` data sets."""
+        B = self.batch
+        X = np.empty((B, d, n)); y = np.empty((B, n)); ev = np.empty((B, n)); y0 = np.empty((B, n)); nc = (C.c_int * B)()
+        self._ck(self.lib.gps_synth_generate(self.h, int(seed), n, d, float(sn2), float(sf2), float(ell), float(jitter), int(n_censor),
+                                             float(cens_mean), float(cens_sd), dptr(X), dptr(y), dptr(ev), dptr(y0), nc))
+        self.n, self.d = n, d
+        self.opts = ("SqExp", "Zero", False, "intended")
+        return {"data": np.transpose(X, (0, 2, 1)), "targets": y, "events": ev, "targetsPreCensoring": y0,
+                "numCensored": np.array(list(nc))}
+
     def set_targets(self, y):
         y = np.ascontiguousarray(np.asarray(y, dtype=np.float64)).reshape(self.batch, self.n)
         self._ck(self.lib.gps_set_targets(self.h, dptr(y)))

@@ -167,6 +167,17 @@ int gps_metrics(gps_handle h, const double* pred, const double* time, const doub
  * v, out: batch x n.  The caller finishes the recipe: y = exp(mean + out + sqrt(sn2_gen) * d2). */
 int gps_chol_matvec(gps_handle h, const double* par, int len, const double* v, double* out);
 
+/* The recipe itself on the device: MakeSyntheticData.R:40-41,145-149 ('likeRealData': x ~ N(0,1), K = CovFunc(x, x) SqExp,
+ * y = exp(t(chol(K)) %*% d1 + sqrt(sn2) d2)) and CensorData.R:36-48 ('NormalLoopSample': samples picked uniformly among the
+ * uncensored ones are censored at |N(cens_mean, cens_sd)| when that is shorter, until n_censor are) for `batch` data sets.
+ * Random stream: Philox4x32-10, counter = (block, stream, data set, 0), key = seed (R's wall-clock-seeded Mersenne-Twister
+ * cannot be reproduced).  `jitter` is added to K's diagonal before the Cholesky (GPS_ERR_NOT_PD: raise it; the reference
+ * calls nearPD there).  Outputs: X_out [batch][d][n] column-major, y_out / events_out [batch][n] after censoring (time scale),
+ * y_uncensored_out (optional), n_censored_out (optional, per data set).  The handle's data / options are replaced. */
+int gps_synth_generate(gps_handle h, unsigned long long seed, int n, int d, double sn2, double sf2, double ell, double jitter,
+                       int n_censor, double cens_mean, double cens_sd, double* X_out, double* y_out, double* events_out,
+                       double* y_uncensored_out, int* n_censored_out);
+
 /* ---- whole fits: ApplyGP.R:136-282 with stats::optim restated in C++ ---------- */
 /* Runs, for every fit of the batch in lock-step, what ApplyGP does after its target transforms: for a
  * survival model the GPS outer loop  while((change > tolerance & count < max_count) | count <= 5)

@@ -302,3 +302,17 @@ def test_concordance_index_restatement_closed_forms():
     c, conc, disc, tied = orc.concordance_index(np.array([2.0, 1.0]), np.array([1.0, 1.0]), np.ones(2))
     assert conc + disc + tied == 0 and np.isnan(c)
     assert abs(orc.rmse([1.0, 2.0], [2.0, 4.0]) - np.sqrt(2.5)) < 1e-15
+
+
+def test_philox_known_answers_and_synth_recipe():
+    """The synthetic-data restatement (oracle/synth_oracle.py): Philox4x32-10 against Random123's published known-answer
+    vectors, the normal stream's moments, and the censoring loop's contract (CensorData.R:36-48)."""
+    from oracle import synth_oracle as so
+    assert so.philox4x32_10((0, 0, 0, 0), (0, 0)) == (0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8)
+    assert so.philox4x32_10((0xffffffff,) * 4, (0xffffffff,) * 2) == (0x408f276d, 0x41c83b0e, 0xa20bc7c6, 0x6d5451fd)
+    assert so.philox4x32_10((0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344), (0xa4093822, 0x299f31d0)) == \
+        (0xd16cfe09, 0x94fdcceb, 0x5001e420, 0x24126ea1)
+    z = so.normals(20000, 0, 0, 1234)
+    assert abs(z.mean()) < 0.03 and abs(z.std() - 1.0) < 0.03
+    X, y0, y, ev, done = so.generate(7, 0, 60, 2, 0.01, 0.5, 1.5, 1e-6, 24, 0.0, 50.0)
+    assert done == 24 and int(np.sum(ev == 0)) == 24 and np.all(y[ev == 0] < y0[ev == 0]) and np.array_equal(y[ev == 1], y0[ev == 1])
