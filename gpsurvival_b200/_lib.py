@@ -72,6 +72,8 @@ PROTOTYPES = {
                                       _dp, C.c_int, C.c_int, C.c_int, C.c_double, C.c_int, C.c_int,
                                       _dp, _dp, _dp, C.POINTER(C.c_int), _dp, _dp, _dp, _dp, _dp, C.POINTER(C.c_int),
                                       C.POINTER(C.c_longlong)]),
+    "gps_model_token": (C.c_ulonglong, [_h]),
+    "gps_get_shape": (C.c_int, [_h, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     "gps_launch_count": (C.c_longlong, [_h]),
     "gps_last_device_ms": (C.c_double, [_h]),
     "gps_set_graphs": (C.c_int, [_h, C.c_int]),

@@ -117,6 +117,10 @@ struct gps_handle_s {
   int pool_n = 0;
   int* gather_rows = nullptr;   // row indices for predictions at training rows (censored rows, training-set predictions)
   size_t gather_rows_cap = 0;
+  unsigned long long model_token = 0;   // bumped by every successful gps_regress_finalize: identifies the resident model
+  // gps_cov scratch: one grow-only arena instead of a dozen cudaMalloc / cudaFree per call
+  double* cov_arena = nullptr;
+  size_t cov_arena_elems = 0;
   // adjust scratch
   double* adj = nullptr;
   int adj_cap = 0;
@@ -1153,6 +1157,7 @@ int gps_destroy(gps_handle h) {
   drop_graphs(h);
   free_data(h);
   dfree(h->adj);
+  dfree(h->cov_arena);
   dfree(h->pool); dfree(h->pool_y); dfree(h->pool_ev); dfree(h->pool_rows); dfree(h->gather_rows);
   if (h->pin) cudaFreeHost(h->pin);
   if (h->pin_info) cudaFreeHost(h->pin_info);
@@ -1369,7 +1374,8 @@ int gps_set_data_indexed(gps_handle h, const double* Xpool, int npool, int d, co
   rc = ensure_shape(h, n, d);
   if (rc) return rc;
   if ((size_t)npool * d > h->pool_cap) {
-    dfree(h->pool); dfree(h->pool_y); dfree(h->pool_ev);
+    dfree(h->cov_arena);
+  dfree(h->pool); dfree(h->pool_y); dfree(h->pool_ev);
     CK(h, dalloc(&h->pool, (size_t)npool * d, false));
     CK(h, dalloc(&h->pool_y, (size_t)npool, false));
     CK(h, dalloc(&h->pool_ev, (size_t)npool, false));
@@ -1605,6 +1611,7 @@ int gps_regress_finalize(gps_handle h, const double* par, int len, double* K_out
   CK(h, cudaStreamSynchronize(h->st));
   remember_fact(h, par, len, 2);
   h->model_valid = true;
+  h->model_token++;
   h->model_par.assign(par, par + (size_t)len * B);
   h->model_tv = h->targets_version;
   h->model_ncv = h->nc_version;
@@ -1764,8 +1771,11 @@ int gps_predict_rows(gps_handle h, const double* par, int len, int reuse_model, 
   return predict_impl(h, par, len, reuse_model, nullptr, rows, m, mu_out, varf_out, vard_out);
 }
 
+static gps_handle default_handle();
+
 int gps_adjust(gps_handle h, const double* a, const double* mu, const double* s, int c, double* mean_out,
                double* var_out) {
+  if (!h) h = default_handle();      // stateless: AdjustTrainingSurvivalMeanVariance needs no fit
   int rc = check_handle(h);
   if (rc) return rc;
   if (c < 0 || (c > 0 && (!a || !mu || !s || !mean_out || !var_out))) return fail(h, GPS_ERR_ARG, "gps_adjust: bad arguments");
@@ -1796,8 +1806,24 @@ int gps_adjust(gps_handle h, const double* a, const double* mu, const double* s,
   return GPS_OK;
 }
 
+// Handle of the calling thread for stateless calls with h == NULL (gps_cov, gps_adjust): created on first use on the
+// current device, kept until the process ends.
+static gps_handle default_handle() {
+  static thread_local gps_handle dh = nullptr;
+  if (!dh) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) { (void)cudaGetLastError(); dev = 0; }
+    if (gps_create(dev, &dh) != GPS_OK) dh = nullptr;
+  }
+  return dh;
+}
+
 int gps_cov(gps_handle h, const double* X1, int n1, const double* X2, int n2, int d, double sf2, const double* ell,
             int p, int cov_form, int ard_mode, double* K_out) {
+  if (!h) {                      // h_or_null — CovFunc.R needs no fit
+    h = default_handle();
+    if (!h) return fail(nullptr, GPS_ERR_CUDA, "gps_cov: no CUDA device available (libgpsurv has no CPU fallback)");
+  }
   int rc = check_handle(h);
   if (rc) return rc;
   if (!X1 || n1 < 1 || d < 1 || !ell || !K_out) return fail(h, GPS_ERR_ARG, "gps_cov: bad arguments");
@@ -1806,33 +1832,41 @@ int gps_cov(gps_handle h, const double* X1, int n1, const double* X2, int n2, in
   const bool sym = (X2 == nullptr);
   if (sym) n2 = n1;
   if (n2 < 1) return fail(h, GPS_ERR_ARG, "gps_cov: bad n2");
-  // temporary single-problem buffers (stateless utility path)
+  // single-problem scratch carved out of one grow-only arena kept in the handle
   const int ld1 = round_up(n1, 16), ld2 = round_up(n2, 16), ldk = round_up(n1 + 2, 16), lde = round_up(d > p ? d : p, 16);
   const int ldn = ldk > ld2 ? ldk : ld2;
-  double *dX1 = nullptr, *dX2 = nullptr, *dZ1 = nullptr, *dZ2 = nullptr, *dmu = nullptr, *dell = nullptr, *dn1 = nullptr,
-         *dn2 = nullptr, *dpart = nullptr, *dK = nullptr, *dhyp = nullptr, *dsplit = nullptr;
   int ks1 = ceil_div(24000, n1), ks2 = ceil_div(24000, n2);
   ks1 = ks1 < 1 ? 1 : (ks1 > d ? d : (ks1 > 64 ? 64 : ks1));
   ks2 = ks2 < 1 ? 1 : (ks2 > d ? d : (ks2 > 64 ? 64 : ks2));
   int saved_batch = h->batch, saved_ld = h->ld;
   double* saved_gsplit = h->gsplit;
+  h->batch = 1;
+  const int ksplit = pick_gram_ksplit(h, n1, n2, d, sym);
+  h->batch = saved_batch;
+  auto al = [](size_t e) { return (e + 31) & ~(size_t)31; };     // 256-byte granules
+  const size_t need = 2 * al((size_t)ld1 * d) + (sym ? 0 : 2 * al((size_t)ld2 * d)) + 2 * al(lde) + 2 * al(ldn) + al((size_t)ldn * 64) +
+                      al((size_t)ldk * n2) + al(4) + (ksplit > 1 ? al((size_t)ldk * n2 * ksplit) : 0);
+  if (need > h->cov_arena_elems) {
+    CK(h, cudaStreamSynchronize(h->st));
+    dfree(h->cov_arena);
+    h->cov_arena_elems = 0;
+    CK(h, dalloc(&h->cov_arena, need, false));
+    h->cov_arena_elems = need;
+  }
+  double* cur = h->cov_arena;
+  auto take = [&](size_t e) { double* r = cur; cur += al(e); return r; };
+  double *dX1 = take((size_t)ld1 * d), *dZ1 = take((size_t)ld1 * d), *dX2 = nullptr, *dZ2 = nullptr;
+  if (!sym) { dX2 = take((size_t)ld2 * d); dZ2 = take((size_t)ld2 * d); }
+  double *dmu = take(lde), *dell = take(lde), *dn1 = take(ldn), *dn2 = take(ldn), *dpart = take((size_t)ldn * 64),
+         *dK = take((size_t)ldk * n2), *dhyp = take(4), *dsplit = ksplit > 1 ? take((size_t)ldk * n2 * ksplit) : nullptr;
   int result = GPS_OK;
   auto cleanup = [&]() {
     cudaStreamSynchronize(h->st);
-    cudaFree(dX1); cudaFree(dX2); cudaFree(dZ1); cudaFree(dZ2); cudaFree(dmu); cudaFree(dell); cudaFree(dn1);
-    cudaFree(dn2); cudaFree(dpart); cudaFree(dK); cudaFree(dhyp); cudaFree(dsplit);
     h->batch = saved_batch; h->ld = saved_ld; h->gsplit = saved_gsplit;
   };
 #define CKC(call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) { result = fail(h, GPS_ERR_CUDA, std::string("gps_cov: ") + cudaGetErrorString(e__)); cleanup(); return result; } } while (0)
-  CKC(cudaStreamSynchronize(h->st));
-  CKC(dalloc(&dX1, (size_t)ld1 * d));
-  CKC(dalloc(&dZ1, (size_t)ld1 * d));
-  CKC(dalloc(&dmu, (size_t)lde));
-  CKC(dalloc(&dell, (size_t)lde));
-  CKC(dalloc(&dn1, (size_t)ldn));
-  CKC(dalloc(&dpart, (size_t)ldn * 64));
-  CKC(dalloc(&dK, (size_t)ldk * n2, false));
-  CKC(dalloc(&dhyp, (size_t)4));
+  // rows n..ld of the staged inputs and the tails of the small vectors are read by the kernels: keep them defined
+  CKC(cudaMemsetAsync(h->cov_arena, 0, sizeof(double) * (size_t)(dK - h->cov_arena), h->st));
   CKC(cudaMemcpy2DAsync(dX1, (size_t)ld1 * sizeof(double), X1, (size_t)n1 * sizeof(double), (size_t)n1 * sizeof(double), d,
                         cudaMemcpyHostToDevice, h->st));
   double hyp4[4] = {0.0, sf2, 0.0, 0.0};
@@ -1853,9 +1887,6 @@ int gps_cov(gps_handle h, const double* X1, int n1, const double* X2, int n2, in
   const double *Zb = dZ1, *nb = dn1;
   int ldb = ld1;
   if (!sym) {
-    CKC(dalloc(&dX2, (size_t)ld2 * d));
-    CKC(dalloc(&dZ2, (size_t)ld2 * d));
-    CKC(dalloc(&dn2, (size_t)ldn));
     CKC(cudaMemcpy2DAsync(dX2, (size_t)ld2 * sizeof(double), X2, (size_t)n2 * sizeof(double), (size_t)n2 * sizeof(double), d,
                           cudaMemcpyHostToDevice, h->st));
     if (!aw) {
@@ -1868,11 +1899,7 @@ int gps_cov(gps_handle h, const double* X1, int n1, const double* X2, int n2, in
     h->launches += 2;
     Zb = dZ2; nb = dn2; ldb = ld2;
   }
-  int ksplit = pick_gram_ksplit(h, n1, n2, d, sym);
-  if (ksplit > 1) {
-    CKC(dalloc(&dsplit, (size_t)ldk * n2 * ksplit, false));
-    h->gsplit = dsplit;
-  }
+  if (ksplit > 1) h->gsplit = dsplit;
   h->cu_err = cudaSuccess;
   h->seq_launches = 0;
   enqueue_cov(h, dZ1, n1, ld1, 0, dn1, Zb, n2, ldb, 0, nb, d, dhyp, nullptr, dK, nullptr, ldk, (long long)ldk * n2, sym,
@@ -1892,42 +1919,14 @@ int gps_cov(gps_handle h, const double* X1, int n1, const double* X2, int n2, in
   return GPS_OK;
 }
 
-// CalculateMetrics.R:18,21 on the device: concordance index (survcomp semantics, see cindex_kernel) and RMSE of `batch` sets
-// of m test predictions.  pairs_out (optional): [batch][3] = concordant, discordant, usable-but-tied-in-x pair counts.
-int gps_metrics(gps_handle h, const double* pred, const double* time, const double* event, int m, double* cindex_out,
-                double* rmse_out, long long* pairs_out) {
-  int rc = check_handle(h);
-  if (rc) return rc;
-  if (!pred || !time || !event || m < 1 || !cindex_out || !rmse_out) return fail(h, GPS_ERR_ARG, "gps_metrics: bad arguments");
-  const int B = h->batch, nblk = ceil_div(m, 128);
-  double *din = nullptr, *dpart = nullptr, *dout = nullptr;
-  unsigned long long* dcnt = nullptr;
-  auto cleanup = [&]() { cudaStreamSynchronize(h->st); cudaFree(din); cudaFree(dpart); cudaFree(dout); cudaFree(dcnt); };
-#define MT_CK(call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) { cleanup(); return fail(h, GPS_ERR_CUDA, std::string("gps_metrics: ") + cudaGetErrorString(e__)); } } while (0)
-  MT_CK(dalloc(&din, (size_t)3 * B * m, false));
-  MT_CK(dalloc(&dpart, (size_t)B * nblk, false));
-  MT_CK(dalloc(&dout, (size_t)2 * B, false));
-  MT_CK(dalloc(&dcnt, (size_t)3 * B));
-  MT_CK(cudaMemcpyAsync(din, pred, sizeof(double) * B * m, cudaMemcpyHostToDevice, h->st));
-  MT_CK(cudaMemcpyAsync(din + (size_t)B * m, time, sizeof(double) * B * m, cudaMemcpyHostToDevice, h->st));
-  MT_CK(cudaMemcpyAsync(din + (size_t)2 * B * m, event, sizeof(double) * B * m, cudaMemcpyHostToDevice, h->st));
-  cindex_kernel<<<dim3(nblk, B), 128, 0, h->st>>>(din, din + (size_t)B * m, din + (size_t)2 * B * m, m, dcnt, dpart);
-  metrics_finish_kernel<<<B, 32, 0, h->st>>>(dcnt, dpart, nblk, m, dout, dout + B);
-  h->launches += 2;
-  MT_CK(cudaGetLastError());
-  std::vector<unsigned long long> cnt((size_t)3 * B);
-  std::vector<double> out((size_t)2 * B);
-  MT_CK(cudaMemcpyAsync(out.data(), dout, sizeof(double) * 2 * B, cudaMemcpyDeviceToHost, h->st));
-  MT_CK(cudaMemcpyAsync(cnt.data(), dcnt, sizeof(unsigned long long) * 3 * B, cudaMemcpyDeviceToHost, h->st));
-  MT_CK(cudaStreamSynchronize(h->st));
-#undef MT_CK
-  cleanup();
-  for (int b = 0; b < B; b++) {
-    cindex_out[b] = out[b];
-    rmse_out[b] = out[B + b];
-    if (pairs_out)
-      for (int q = 0; q < 3; q++) pairs_out[(size_t)b * 3 + q] = (long long)cnt[(size_t)b * 3 + q];
-  }
+unsigned long long gps_model_token(gps_handle h) { return (h && h->model_valid) ? h->model_token : 0ull; }
+
+int gps_get_shape(gps_handle h, int* n_out, int* d_out, int* batch_out, int* ncens_out) {
+  if (!h) return fail(nullptr, GPS_ERR_ARG, "handle is NULL");
+  if (n_out) *n_out = h->have_data ? h->n : 0;
+  if (d_out) *d_out = h->have_data ? h->d : 0;
+  if (batch_out) *batch_out = h->batch;
+  if (ncens_out) *ncens_out = h->have_data ? h->ncens_max : 0;
   return GPS_OK;
 }
 

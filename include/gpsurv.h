@@ -105,7 +105,8 @@ int gps_set_noise_corr(gps_handle h, const double* log_sc2, int len);
 /* ---- CovFunc.R:1-54 (SqExp / ARD) ------------------------------------------------------ */
 /* K (n1 x n2) = sf2 * exp(-0.5 * ||x1_i/ell - x2_j/ell||^2).  X2 == NULL means X2 = X1
  * (the identical(x1,x2) branch, CovFunc.R:24-25).  Stateless: `h` only supplies the device
- * and scratch memory. */
+ * and scratch memory (one grow-only arena, no allocation per call); h may be NULL — the calling thread's default handle
+ * on the current device is then used (created on first use).  gps_adjust accepts NULL the same way. */
 int gps_cov(gps_handle h, const double* X1, int n1, const double* X2, int n2, int d,
             double sf2, const double* ell, int p, int cov_form, int ard_mode, double* K_out);
 
@@ -230,6 +231,13 @@ int gps_fit_folds_multi(const int* devices, int ndev, int total, int cov_form, i
                         double* test_vard, double* train_mean, int* status_out, long long* evaluations_out);
 /* The partitioner itself (pure host code): part_out[i] in [0, nparts) for jobs with the given costs, longest first. */
 int gps_partition_lpt(const double* cost, int count, int nparts, int* part_out);
+
+/* Identity of the model gps_regress_finalize left resident (0 = none): bumped by every finalize.  A drop-in GPPredict keeps
+ * the token GPRegression returned and refuses to predict GPR / GPS1 from a different resident model (GPPredict.R:12-13 uses
+ * the L / alpha of the regressionStructure it is given). */
+unsigned long long gps_model_token(gps_handle h);
+/* Shape of the resident data (0 before gps_set_data): n, d, batch, largest censored-row count.  NULL outputs are skipped. */
+int gps_get_shape(gps_handle h, int* n_out, int* d_out, int* batch_out, int* ncens_out);
 
 /* ---- introspection used by bench.py / tests ------------------------------------------- */
 /* Number of kernels this handle has launched since creation (bench.py's gpu_launches). */

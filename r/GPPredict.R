@@ -19,6 +19,12 @@ GPPredict <- function(regressionStructure,parameterStructure,trainingTestStructu
                  covFuncForm,meanFuncForm,noiseCorr,logHypNoiseCorrection,parameterStructure$extraParam)
     toReturn <- .Call('gps_r_predict', h, par, FALSE, testData)
   } else {
+    # GPR / GPS1 predict from regressionStructure$L / alpha (GPPredict.R:12-13).  Those live on the GPU as the model the
+    # finalize call of THAT GPRegression left resident; a regressionStructure from an earlier fit must not silently pick
+    # up whatever model is resident now.
+    if(is.null(regressionStructure$gpsToken) || is.null(.gps$handle) ||
+       !identical(as.double(regressionStructure$gpsToken), as.double(.Call('gps_r_model_token', .gps$handle))))
+      stop('GPPredict: the model resident on the GPU is not the one this regressionStructure came from; call GPRegression again (or predict before fitting another model)')
     toReturn <- .Call('gps_r_predict', .gps$handle, par, TRUE, testData)
   }
   return(toReturn)

@@ -6,7 +6,16 @@ OptimisationGradientLog <- function(logHyp,trainingData,trainingTargets,training
   # of its own likelihood).  NOT RUN IN THE BUILD IMAGE.
   #---------------------------------------------------------------------------------------------#
   if(imposePriors) stop('imposePriors=TRUE cannot run in the reference as shipped')
-  h <- GpsBind(trainingData,trainingTargets,trainingEvents,covFuncForm,meanFuncForm,noiseCorr,logHypNoiseCorrection,extraParam)
-  gradients <- .Call('gps_r_nlml_grad', h, as.double(logHyp))
+  h <- if(isTRUE(.gps$inOptim)) .gps$handle else
+       GpsBind(trainingData,trainingTargets,trainingEvents,covFuncForm,meanFuncForm,noiseCorr,logHypNoiseCorrection,extraParam)
+  # A non-positive-definite Ky is repaired by the library in BOTH fn and gr (same nearPD matrix, same value), so the two
+  # agree on every point optim can accept; where no repair is possible fn has returned +Inf (see ForOptimisationLog.R)
+  # and optim never asks for a gradient there.  If it happens anyway, say what is going on instead of a bare status.
+  gradients <- tryCatch(.Call('gps_r_nlml_grad', h, as.double(logHyp)),
+    error = function(e){
+      if(grepl('^gps_not_pd', conditionMessage(e)))
+        stop('OptimisationGradientLog: covariance matrix is not positive definite at a point the objective accepted, and it could not be repaired (n > 4096 or nearPD did not converge)')
+      stop(e)
+    })
   return(gradients)
 }

@@ -10,6 +10,11 @@
 .gps <- new.env()
 .gps$handle <- NULL
 .gps$ardMode <- 0L      # 0 = intended (per-dimension scaling), 1 = as written (recycled, CovFunc.R:25,27)
+.gps$device  <- 0L      # GPU of the interactive session; whole restart x fold sweeps go through GpsFitFoldsMulti (all GPUs)
+.gps$inOptim <- FALSE   # TRUE while GPRegression's optim() runs: fn / gr then trust the binding GPRegression made ONCE
+                        # (X, targets and options are constant across one optim run) instead of re-checking
+                        # as.matrix / storage.mode / identical(X, .gps$X) — an O(n d) compare — on every callback
+.gps$optimType <- NULL
 
 GpsCovCode  <- function(covFuncForm, extraParam=NULL) switch(covFuncForm, 'SqExp' = 0L, 'ARD' = 1L,
                  'Matern' = switch(as.character(extraParam), '1' = 2L, '3' = 3L, '5' = 4L,
@@ -19,7 +24,7 @@ GpsMeanCode <- function(meanFuncForm) switch(meanFuncForm, 'Zero' = 0L, 'Linear'
 GpsNcCode   <- function(noiseCorr) if(identical(noiseCorr, 'noiseCorrLearned')) 1L else if(identical(noiseCorr, 'noiseCorrVec')) 2L else 0L
 
 GpsBind <- function(trainingData, trainingTargets, trainingEvents, covFuncForm, meanFuncForm, noiseCorr, logHypNoiseCorrection, extraParam=NULL){
-  if(is.null(.gps$handle)) .gps$handle <- .Call('gps_r_create', 0L)
+  if(is.null(.gps$handle)) .gps$handle <- .Call('gps_r_create', .gps$device)
   opts <- c(GpsCovCode(covFuncForm, extraParam), GpsMeanCode(meanFuncForm), GpsNcCode(noiseCorr), .gps$ardMode)
   if(!identical(opts, .gps$opts)){
     .Call('gps_r_set_options', .gps$handle, opts[1], opts[2], opts[3], opts[4]); .gps$opts <- opts
@@ -69,4 +74,25 @@ GpsNlmlNearPD <- function(logHyp,trainingData,trainingTargets,trainingEvents,mea
   r     <- as.numeric(trainingTargets) - as.numeric(m)
   alpha <- backsolve(t(L), forwardsolve(L, r))
   matrix(0.5*sum(r*alpha) + sum(log(diag(L))) + (nSamples/2)*log(2*pi), 1, 1)
+}
+
+#-------------------------------------------------------------------------------------------------#
+# GpsFitFoldsMulti — the restart x fold loops of runSyntheticExp1.R:208-213 / a CV driver as ONE call over every GPU of the
+# box (gps_fit_folds_multi): fits are row-index views of one pooled data set, split over `devices` by the library (LPT, no
+# collective), one host thread and one handle per device.  trainRows / testRows: n x total / m x total integer matrices of
+# 1-based rows of xPool.  NOT RUN IN THE BUILD IMAGE.
+#-------------------------------------------------------------------------------------------------#
+GpsFitFoldsMulti <- function(devices, xPool, yLogPool, eventsPool, trainRows, testRows, parStart, parameterStructure,
+                             method=c('Nelder-Mead','BFGS','L-BFGS'), tolerance=parameterStructure$tolerance, maxCount=parameterStructure$maxCount){
+  method <- match.arg(method)
+  opts <- c(GpsCovCode(parameterStructure$covFuncForm, parameterStructure$extraParam), GpsMeanCode(parameterStructure$meanFuncForm),
+            GpsNcCode(parameterStructure$noiseCorr), .gps$ardMode)
+  survival <- as.integer(parameterStructure$modelType=='survival')
+  maxit <- if(survival==1L) parameterStructure$maxitSurvival else parameterStructure$maxit
+  ctrl <- c(switch(method,'Nelder-Mead'=0L,'BFGS'=1L,'L-BFGS'=2L), as.integer(maxit), as.integer(maxCount), survival)
+  X <- as.matrix(xPool); storage.mode(X) <- 'double'
+  storage.mode(trainRows) <- 'integer'; storage.mode(testRows) <- 'integer'
+  P <- as.matrix(parStart); storage.mode(P) <- 'double'
+  .Call('gps_r_fit_folds_multi', as.integer(devices), X, as.double(yLogPool), as.double(eventsPool), trainRows, testRows, P,
+        as.integer(opts), ctrl, as.double(tolerance))
 }

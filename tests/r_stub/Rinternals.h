@@ -36,6 +36,8 @@ Rboolean Rf_isNull(SEXP);
 Rboolean Rf_isMatrix(SEXP);
 int Rf_nrows(SEXP);
 int Rf_ncols(SEXP);
+int TYPEOF(SEXP);
+char* R_alloc(size_t, int);
 SEXP Rf_mkChar(const char*);
 SEXP Rf_mkString(const char*);
 SEXP Rf_setAttrib(SEXP, SEXP, SEXP);

@@ -403,3 +403,39 @@ def test_synth_generate_matches_cpu_restatement():
     f = fit.nlml(np.tile(np.log([0.2, 0.8, 1.7 * np.sqrt(d)]), (B, 1)))
     assert np.all(np.isfinite(f))
     fit.close()
+
+
+# ---- boundary details the R drop-in relies on -----------------------------------------------------------------------
+def test_null_handle_stateless_calls_model_token_and_shape():
+    import ctypes as C
+    lib = _lib.load()
+    rng = np.random.default_rng(2)
+    n, d = 70, 3
+    x = np.asfortranarray(rng.standard_normal((n, d)))
+    ell = np.array([1.3])
+    for _ in range(2):                                   # second call reuses the default handle's scratch arena
+        K = np.empty((n, n), order="F")
+        rc = lib.gps_cov(None, _lib.dptr(x), n, None, n, d, 0.8, _lib.dptr(ell), 1, 0, 0, _lib.dptr(K))
+        assert rc == 0
+        assert np.max(np.abs(K - orc.cov_func(x, x, 0.8, ell))) <= 1e-12 and np.array_equal(K, K.T)
+    a, mu, s = rng.standard_normal(9), rng.standard_normal(9), 0.5 + rng.random(9)
+    em, ev = np.empty(9), np.empty(9)
+    assert lib.gps_adjust(None, _lib.dptr(a), _lib.dptr(mu), _lib.dptr(s), 9, _lib.dptr(em), _lib.dptr(ev)) == 0
+    eo, vo = orc.adjust(a, mu, s)
+    assert np.allclose(em, eo, rtol=1e-12, atol=0) and np.allclose(ev, vo, rtol=1e-10, atol=1e-300)
+    fit = gp.Fit(0)
+    shp = [C.c_int() for _ in range(4)]
+    assert lib.gps_get_shape(fit.h, *[C.byref(v) for v in shp]) == 0 and shp[0].value == 0
+    y = rng.standard_normal(n)
+    evn = (rng.random(n) > 0.4).astype(float)
+    fit.set_data(x, y, evn)
+    assert lib.gps_get_shape(fit.h, *[C.byref(v) for v in shp]) == 0
+    assert [v.value for v in shp] == [n, d, 1, int(np.sum(evn == 0))]
+    assert lib.gps_model_token(fit.h) == 0
+    par = np.log([0.2, 0.8, 1.5])
+    fit.finalize(par)
+    t1 = lib.gps_model_token(fit.h)
+    fit.finalize(par + 0.1)
+    t2 = lib.gps_model_token(fit.h)
+    assert t1 >= 1 and t2 == t1 + 1                      # a later fit replaces the resident model: GPPredict.R checks this
+    fit.close()
