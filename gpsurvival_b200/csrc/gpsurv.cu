@@ -1930,6 +1930,45 @@ int gps_get_shape(gps_handle h, int* n_out, int* d_out, int* batch_out, int* nce
   return GPS_OK;
 }
 
+// CalculateMetrics.R:18,21 on the device: concordance index (survcomp semantics, see cindex_kernel) and RMSE of `batch` sets
+// of m test predictions.  pairs_out (optional): [batch][3] = concordant, discordant, usable-but-tied-in-x pair counts.
+int gps_metrics(gps_handle h, const double* pred, const double* time, const double* event, int m, double* cindex_out,
+                double* rmse_out, long long* pairs_out) {
+  int rc = check_handle(h);
+  if (rc) return rc;
+  if (!pred || !time || !event || m < 1 || !cindex_out || !rmse_out) return fail(h, GPS_ERR_ARG, "gps_metrics: bad arguments");
+  const int B = h->batch, nblk = ceil_div(m, 128);
+  double *din = nullptr, *dpart = nullptr, *dout = nullptr;
+  unsigned long long* dcnt = nullptr;
+  auto cleanup = [&]() { cudaStreamSynchronize(h->st); cudaFree(din); cudaFree(dpart); cudaFree(dout); cudaFree(dcnt); };
+#define MT_CK(call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) { cleanup(); return fail(h, GPS_ERR_CUDA, std::string("gps_metrics: ") + cudaGetErrorString(e__)); } } while (0)
+  MT_CK(dalloc(&din, (size_t)3 * B * m, false));
+  MT_CK(dalloc(&dpart, (size_t)B * nblk, false));
+  MT_CK(dalloc(&dout, (size_t)2 * B, false));
+  MT_CK(dalloc(&dcnt, (size_t)3 * B));
+  MT_CK(cudaMemcpyAsync(din, pred, sizeof(double) * B * m, cudaMemcpyHostToDevice, h->st));
+  MT_CK(cudaMemcpyAsync(din + (size_t)B * m, time, sizeof(double) * B * m, cudaMemcpyHostToDevice, h->st));
+  MT_CK(cudaMemcpyAsync(din + (size_t)2 * B * m, event, sizeof(double) * B * m, cudaMemcpyHostToDevice, h->st));
+  cindex_kernel<<<dim3(nblk, B), 128, 0, h->st>>>(din, din + (size_t)B * m, din + (size_t)2 * B * m, m, dcnt, dpart);
+  metrics_finish_kernel<<<B, 32, 0, h->st>>>(dcnt, dpart, nblk, m, dout, dout + B);
+  h->launches += 2;
+  MT_CK(cudaGetLastError());
+  std::vector<unsigned long long> cnt((size_t)3 * B);
+  std::vector<double> out((size_t)2 * B);
+  MT_CK(cudaMemcpyAsync(out.data(), dout, sizeof(double) * 2 * B, cudaMemcpyDeviceToHost, h->st));
+  MT_CK(cudaMemcpyAsync(cnt.data(), dcnt, sizeof(unsigned long long) * 3 * B, cudaMemcpyDeviceToHost, h->st));
+  MT_CK(cudaStreamSynchronize(h->st));
+#undef MT_CK
+  cleanup();
+  for (int b = 0; b < B; b++) {
+    cindex_out[b] = out[b];
+    rmse_out[b] = out[B + b];
+    if (pairs_out)
+      for (int q = 0; q < 3; q++) pairs_out[(size_t)b * 3 + q] = (long long)cnt[(size_t)b * 3 + q];
+  }
+  return GPS_OK;
+}
+
 int gps_set_near_pd(gps_handle h, int enable) {
   if (!h) return fail(nullptr, GPS_ERR_ARG, "handle is NULL");
   h->near_pd = enable != 0;
