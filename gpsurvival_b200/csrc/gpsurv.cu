@@ -30,6 +30,7 @@
 #include "dmma_gemm.cuh"
 #include "dmma_ws.cuh"
 #include "kernels.cuh"
+#include "dmma_dag.cuh"
 
 using namespace gps;
 
@@ -87,6 +88,14 @@ struct gps_handle_s {
   int fuse_k64 = 1;              // GPS_FUSE64=0: separate K = 64 GEMM between the panels of a leaf pair
   int ws_kmin = 128;             // GPS_WS_KMIN: shortest k-loop given to the persistent kernel
   int front_fused = 1;           // GPS_FRONT=0: never use the fused small-d front end (small_front_kernel)
+  // one-kernel Cholesky (dmma_dag.cuh): segments recorded instead of launched while dag_rec is set (per group view)
+  std::vector<DagSeg>* dag_rec = nullptr;
+  int dag_enabled = 0;           // GPS_DAG=1
+  int dag_groups = 4, dag_skew = 9;   // GPS_DAG_GROUPS / GPS_DAG_SKEW: logical groups of fits and their offset (in segments) in the merged list
+  DagSeg* dag_table = nullptr;   // device copy of the merged segment list (static per shape / options; dropped with the graphs)
+  int dag_nseg = 0, dag_total = 0, dag_done_elems = 0;
+  int* dag_done = nullptr;       // per (segment, fit) completion counters
+  int* dag_sched = nullptr;      // the DAG kernel's task counter (2 ints)
   int prio_high = 0;             // GPS_PRIO=1: launch the latency-bound kernels of the diagonal blocks with this (greatest) priority
   int fuse_wk = 1;               // GPS_FUSEWK=0: separate wk_kernel pass after Kinv = U U' (always so for Matern gradients)
   int nbig = 256;                // GPS_NBIG: diagonal block of the two-level Cholesky (64 = one-level recursion)
@@ -237,6 +246,14 @@ void free_data(H* h) {
 }
 
 void drop_graphs(H* h) {
+  if (h->dag_table) {            // the segment list bakes in shapes, options and buffer addresses
+    cudaStreamSynchronize(h->st);
+    cudaFree(h->dag_table);
+    cudaFree(h->dag_done);
+    h->dag_table = nullptr;
+    h->dag_done = nullptr;
+    h->dag_nseg = h->dag_total = h->dag_done_elems = 0;
+  }
   if (h->g_factor) cudaGraphExecDestroy(h->g_factor);
   if (h->g_inverse) cudaGraphExecDestroy(h->g_inverse);
   if (h->g_grad) cudaGraphExecDestroy(h->g_grad);
@@ -286,6 +303,10 @@ bool use_ws128(const H* h, const GemmParams& p) {
 // un-overlapped epilogue dominates; and every developer override).
 int pick_nt_tile(const H* h, const GemmParams& p) {
   if (h->force_tile >= 0 || !h->ws_enabled || !h->ws_sched || p.K < h->ws_kmin) return 0;
+  {
+    static const int forced = getenv("GPS_WSTILE") ? atoi(getenv("GPS_WSTILE")) : 0;   // developer A/B: 64 / 80 / 96 / 128 for square-tile products
+    if ((forced == 64 || forced == 80 || forced == 96 || forced == 128) && p.M >= forced && p.N >= forced) return forced;
+  }
   if (use_ws128(h, p)) return 128;
   if (p.N <= 32 && !p.lower && (long long)ceil_div(p.M, 128) * h->batch * p.nodes * p.ksplit >= h->num_sms) return p.N <= 24 ? 24 : 32;
   {   // a launch that cannot even fill the persistent grid once (a lone mid-size fit) is latency-bound: the plain
@@ -318,8 +339,41 @@ inline int tile_bm(const H* h, int code) {   // rows of the tile a pick_nt_tile(
          : (h->force_tile == 2 ? 128 : 64);
 }
 
+// DAG mode: a product is recorded as a segment of the one-kernel Cholesky instead of being launched
+void dag_record_gemm(H* h, const GemmParams& p, const EpiPlain& epi) {
+  DagSeg sg;
+  memset(&sg, 0, sizeof sg);
+  sg.p = p;
+  sg.epi = epi;
+  sg.kind = 0;
+  sg.zcount = h->batch * p.nodes * p.ksplit;
+  sg.rev_m = (p.khi_m && !p.lower) ? 1 : 0;
+  sg.rev_n = (p.khi_n && !p.lower) ? 1 : 0;
+  ws::TileEnum te;
+  te.init(p.M, p.N, 64, 64, p.lower, sg.rev_m, sg.rev_n);
+  sg.ntasks = (p.M > 0 && p.N > 0) ? te.per_z * sg.zcount : 0;
+  sg.dep_need = te.per_z * p.nodes * p.ksplit;      // (temporarily) this segment's own tasks per fit
+  h->dag_rec->push_back(sg);
+}
+void dag_record_leaf(H* h, int e0, int nb) {
+  DagSeg sg;
+  memset(&sg, 0, sizeof sg);
+  sg.kind = 1;
+  sg.ntasks = h->batch;
+  sg.dep_need = 1;
+  sg.A = h->Ky; sg.L = h->L; sg.Linv = h->Linv; sg.Uinv = h->U; sg.ld = h->ld; sg.e0 = e0; sg.nb = nb; sg.stride = h->strideM;
+  sg.info = h->info;
+  h->dag_rec->push_back(sg);
+}
+
 template <bool A_KC, bool B_KC, class Epi>
 void gemm(H* h, const GemmParams& p, const Epi& epi) {
+  if constexpr (!A_KC && !B_KC && std::is_same<Epi, EpiPlain>::value) {
+    if (h->dag_rec) {
+      dag_record_gemm(h, p, epi);
+      return;
+    }
+  }
   cudaError_t e;
   if constexpr (!A_KC && !B_KC) {
     const int tile = pick_nt_tile(h, p);
@@ -478,6 +532,16 @@ void enqueue_cov(H* h, const double* Za, int n1, int lda, long long sA, const do
 // ~5.2 us per 128-row tile, one CTA per SM) picks the tile height RT and the tiles per CTA T that
 // minimise  waves * (chain + T * tile).  +1 CTA per fit publishes L11 / X11.
 void launch_panel(H* h, int e0, int nb, int M, long long* dbg, int kprev = 0) {
+  if (h->dag_rec) {   // one-kernel Cholesky: the 64 x 64 leaf is a task of its own, the panel solve L21 = A21 X11' a K = nb product
+    dag_record_leaf(h, e0, nb);
+    if (M > 0) {
+      const int e1 = e0 + nb, ld = h->ld;
+      GemmParams p = gp(h->Ky + e1 + (size_t)e0 * ld, ld, h->strideM, h->Linv + e0 + (size_t)e0 * ld, ld, h->strideM, M, nb, nb);
+      p.khi_n = 1;    // X11 lower triangular: X11[n][k] = 0 for k > n
+      dag_record_gemm(h, p, plain(h->L + e1 + (size_t)e0 * ld, ld, h->strideM, 1.0, 0.0));
+    }
+    return;
+  }
   const int B = h->batch;
   const int Mr = M > 0 ? M : 1;
   double best = 1e300;
@@ -523,7 +587,7 @@ void potrf_range(H* h, int j0, int j1, int row_end) {
     launch_panel(h, e0, nb, M, nullptr);
     return;
   }
-  if (j1 - j0 == 2 && h->fuse_k64 && !h->lookahead && (h->batch < 8 || row_end < h->naug)) {
+  if (j1 - j0 == 2 && h->fuse_k64 && !h->lookahead && !h->dag_rec && (h->batch < 8 || row_end < h->naug)) {
     // leaf pair: the second panel applies the first one's rank-64 update itself (panel_kernel, kprev = 64) —
     // one launch less per pair; for lone fits and inside the diagonal blocks of the two-level scheme, where the
     // 32-row panel tiles it needs are what the cost model picks anyway
@@ -617,8 +681,11 @@ void potrf_big(H* h, int J0, int J1) {
   if (J1 - J0 == 1) {
     const int c0 = J0 * nbig, c1 = std::min(c0 + nbig, h->ne);
     launch_priority() = h->prio_high;   // the block's panel chains and short products: latency-bound, ahead of other groups' GEMM tiles
-    potrf_range(h, c0 / NB, ceil_div(c1, NB), c1);
-    trtri_range(h, c0, c1, NB, nbig);
+    static const bool skip_diag = getenv("GPS_DEBUG_SKIPDIAG") != nullptr;   // TIMING EXPERIMENT ONLY (wrong results): GEMM-only cost
+    if (!skip_diag) {
+      potrf_range(h, c0 / NB, ceil_div(c1, NB), c1);
+      trtri_range(h, c0, c1, NB, nbig);
+    }
     launch_priority() = 0;
     const int M = h->naug - c1;
     if (M > 0) {
@@ -641,7 +708,72 @@ void potrf_big(H* h, int J0, int J1) {
 // lone fit gets SLOWER (C2 1.84 -> 2.22 ms, n = 8192 Cholesky 10.8 -> 12.5 ms): its launches are latency-bound and
 // the scheme trades wide short-k products for more, smaller launches.  GPS_NBIG=64 turns it off everywhere.
 inline bool two_level(const H* h) { return h->nbig > NB && h->ne > h->nbig && (h->batch >= 8 || h->nbig_forced); }
+void make_view(const H* h, int g0, int cnt, cudaStream_t st, H* v);
+
+// The whole factorisation as ONE persistent kernel (dmma_dag.cuh): the launches potrf_big would issue are recorded per
+// logical group of fits, merged with a skew, and consumed as a task list with per-fit dependency counters.
+bool enqueue_potrf_dag(H* h) {
+  const int G = std::max(1, std::min(h->dag_groups, h->batch / 8));
+  if (!h->dag_table) {
+    std::vector<std::vector<DagSeg>> rec(G);
+    std::vector<int> fits(G);
+    for (int g = 0; g < G; g++) {
+      const int g0 = (int)((long long)h->batch * g / G), g1 = (int)((long long)h->batch * (g + 1) / G);
+      H v;
+      make_view(h, g0, g1 - g0, h->st, &v);
+      v.dag_rec = &rec[g];
+      fits[g] = g1 - g0;
+      if (two_level(&v)) potrf_big(&v, 0, ceil_div(v.ne, v.nbig));
+      else potrf_range(&v, 0, ceil_div(v.ne, NB), v.naug);
+    }
+    const int S = (int)rec[0].size();
+    for (int g = 1; g < G; g++)
+      if ((int)rec[g].size() != S) return false;
+    // merged order: step k emits segment (k - g * skew) of group g; counters and dependencies follow the group's own chain
+    std::vector<DagSeg> all;
+    std::vector<int> prev_cnt(G, -1), prev_need(G, 0);
+    int tile = 0, cnt = 0;
+    for (int k = 0; k < S + (G - 1) * h->dag_skew; k++)
+      for (int g = 0; g < G; g++) {
+        const int idx = k - g * h->dag_skew;
+        if (idx < 0 || idx >= S) continue;
+        DagSeg sg = rec[g][idx];
+        const int own_need = sg.dep_need;
+        if (sg.ntasks == 0) continue;      // empty product (M == 0): nothing to run, nothing to wait for
+        sg.tile_begin = tile;
+        sg.cnt = cnt;
+        sg.dep_cnt = prev_cnt[g];
+        sg.dep_need = prev_need[g];
+        tile += sg.ntasks;
+        prev_cnt[g] = cnt;
+        prev_need[g] = own_need;
+        cnt += fits[g];
+        all.push_back(sg);
+      }
+    DagSeg sentinel;
+    memset(&sentinel, 0, sizeof sentinel);
+    sentinel.tile_begin = tile;
+    sentinel.ntasks = 0x3fffffff;
+    all.push_back(sentinel);
+    if (cudaMalloc((void**)&h->dag_table, sizeof(DagSeg) * all.size()) != cudaSuccess) return false;
+    if (cudaMalloc((void**)&h->dag_done, sizeof(int) * (size_t)std::max(cnt, 1)) != cudaSuccess) return false;
+    if (!h->dag_sched) {
+      if (cudaMalloc((void**)&h->dag_sched, 2 * sizeof(int)) != cudaSuccess) return false;
+      cudaMemset(h->dag_sched, 0, 2 * sizeof(int));
+    }
+    if (cudaMemcpy(h->dag_table, all.data(), sizeof(DagSeg) * all.size(), cudaMemcpyHostToDevice) != cudaSuccess) return false;
+    h->dag_nseg = (int)all.size() - 1;
+    h->dag_total = tile;
+    h->dag_done_elems = std::max(cnt, 1);
+  }
+  CKV(h, cudaMemsetAsync(h->dag_done, 0, sizeof(int) * (size_t)h->dag_done_elems, h->st));
+  CKV(h, launch_dag<WsCfg64>(h->dag_table, h->dag_nseg, h->dag_total, h->num_sms, h->dag_sched, h->dag_done, h->st));
+  h->seq_launches++;
+  return true;
+}
+
 void enqueue_potrf(H* h) {   // whole factorisation (+ the inverse levels below nbig in the two-level scheme)
+  if (h->dag_enabled && !h->dag_rec && h->batch >= 8 && two_level(h) && h->ws_sched && enqueue_potrf_dag(h)) return;
   if (two_level(h)) potrf_big(h, 0, ceil_div(h->ne, h->nbig));
   else potrf_range(h, 0, ceil_div(h->ne, NB), h->naug);
 }
@@ -1088,6 +1220,9 @@ int gps_create_batch(int device, int batch, gps_handle* out) {
   if (const char* ev = getenv("GPS_FUSE64")) h->fuse_k64 = atoi(ev) != 0;
   if (const char* ev = getenv("GPS_TINYCOV")) h->tiny_cov = atoi(ev) != 0;
   if (const char* ev = getenv("GPS_FUSEWK")) h->fuse_wk = atoi(ev) != 0;
+  if (const char* ev = getenv("GPS_DAG")) h->dag_enabled = atoi(ev);
+  if (const char* ev = getenv("GPS_DAG_GROUPS")) h->dag_groups = std::max(1, atoi(ev));
+  if (const char* ev = getenv("GPS_DAG_SKEW")) h->dag_skew = std::max(0, atoi(ev));
   if (const char* ev = getenv("GPS_PRIO")) {
     int least = 0, greatest = 0;
     if (atoi(ev) != 0 && cudaDeviceGetStreamPriorityRange(&least, &greatest) == cudaSuccess) h->prio_high = greatest;
@@ -1162,6 +1297,7 @@ int gps_destroy(gps_handle h) {
   if (h->pin) cudaFreeHost(h->pin);
   if (h->pin_info) cudaFreeHost(h->pin_info);
   if (h->ws_sched) cudaFree(h->ws_sched);
+  if (h->dag_sched) cudaFree(h->dag_sched);
   if (h->ev0) cudaEventDestroy(h->ev0);
   if (h->ev1) cudaEventDestroy(h->ev1);
   if (h->ev_fork) cudaEventDestroy(h->ev_fork);
