@@ -956,6 +956,8 @@ void make_view(const H* h, int g0, int cnt, cudaStream_t st, H* v) {
   v->st = v->cur = st;
   v->lookahead = false;
   v->seq_launches = 0;
+  v->dag_enabled = 0;     // a view never owns the one-kernel Cholesky's segment table
+  v->dag_table = nullptr;
   const size_t g = (size_t)g0;
   adv(v->Xaug, g * h->strideX); adv(v->Z, g * h->strideX); adv(v->XaugT, g * h->strideXT);
   adv(v->mu, g * h->ldmu); adv(v->ell, g * h->ldmu); adv(v->meanw, g * h->ldmu); adv(v->wsc, g * h->ldmu);
@@ -978,7 +980,8 @@ void make_view(const H* h, int g0, int cnt, cudaStream_t st, H* v) {
 
 // Enqueue a sequence for the whole batch: once, or once per stream group (fork from / join into h->st).
 void enqueue_grouped(H* h, SeqFn fn) {
-  const int G = (h->groups_forced || h->n >= 1024) ? std::min(h->groups, h->batch) : 1;
+  int G = (h->groups_forced || h->n >= 1024) ? std::min(h->groups, h->batch) : 1;
+  if (h->dag_enabled) G = 1;   // the one-kernel Cholesky interleaves its own logical groups of fits
   if (G <= 1 || h->lookahead) {
     fn(h);
     return;
