@@ -28,6 +28,7 @@ struct DagSeg {
   int zcount;            // fits * nodes * ksplit
   int rev_m, rev_n;
   int tile_begin;        // first global task index
+  int local0;            // first task of this SLICE within its product (a bulk product is listed as several slices)
   int ntasks;
   int dep_cnt;           // index of the predecessor's counters in done[] (-1: none); counter of fit f = done[dep_cnt + f]
   int dep_need;          // completed tasks per fit that release this segment
@@ -46,6 +47,16 @@ constexpr int LPS = NB + 4;    // leaf tile in shared memory, column-major: S[c 
 constexpr int LPT = 32 + 4;    // merge temporary, column-major: sT[n * LPT + m]
 constexpr int LEAF_SMEM_DOUBLES = NB * LPS + 32 * LPT + NB;
 
+__device__ __forceinline__ long long gtime() {
+  long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;\n" : "=l"(t));
+  return t;
+}
+__device__ __forceinline__ int smid() {
+  int r;
+  asm volatile("mov.u32 %0, %%smid;\n" : "=r"(r));
+  return r;
+}
 __device__ __forceinline__ int ld_acquire(const int* p) {
   int v;
   asm volatile("ld.acquire.gpu.global.s32 %0, [%1];\n" : "=r"(v) : "l"(p) : "memory");
@@ -192,7 +203,8 @@ __device__ void leaf_task(const DagSeg& sg, int fit, double* sm) {
 
 template <class Cfg>
 __global__ void __launch_bounds__(Cfg::NTHREADS, Cfg::CTAS_PER_SM)
-    dmma_dag_kernel(const DagSeg* __restrict__ segs, int nseg, int total, int* __restrict__ sched, int* __restrict__ done) {
+    dmma_dag_kernel(const DagSeg* __restrict__ segs, int nseg, int total, int* __restrict__ sched, int* __restrict__ done,
+                    long long* __restrict__ trace) {   // trace (developer): per task [picked, ready, done (ns), sm | leaf << 8 | K/16 << 9 | fit << 24 | segment << 32]
   using SL = WsSmem<Cfg, false, false>;
   constexpr int BM = Cfg::BM, BN = Cfg::BN, BK = Cfg::BK, STAGES = Cfg::STAGES;
   constexpr int FM = Cfg::FM, FN = Cfg::FN;
@@ -229,14 +241,16 @@ __global__ void __launch_bounds__(Cfg::NTHREADS, Cfg::CTAS_PER_SM)
       if (lane == 0) t = atomicAdd(&sched[0], 1);
       t = __shfl_sync(0xffffffffu, t, 0);
       if (t >= total) break;
+      if (trace && lane == 0) trace[4 * (size_t)t] = dag::gtime();
       while (t >= segs[cur].tile_begin + segs[cur].ntasks) cur++;
       const DagSeg& sg = segs[cur];
-      const int local = t - sg.tile_begin;
+      const int local = t - sg.tile_begin + sg.local0;
       if (sg.kind == 1) {                                 // LEAF: one task per fit, run by the whole CTA
         const int fit = local;
         if (sg.dep_cnt >= 0 && lane == 0)
           while (dag::ld_acquire(done + sg.dep_cnt + fit) < sg.dep_need) __nanosleep(100);
         __syncwarp();
+        if (trace && lane == 0) trace[4 * (size_t)t + 1] = dag::gtime();
         const int s = it % STAGES;
         ws::mbar_wait(empty + s, ((it / STAGES) & 1) ^ 1);
         if (lane == 0) {
@@ -252,6 +266,10 @@ __global__ void __launch_bounds__(Cfg::NTHREADS, Cfg::CTAS_PER_SM)
         if (lane == 0) {
           __threadfence();
           atomicAdd(done + sg.cnt + fit, 1);
+          if (trace) {
+            trace[4 * (size_t)t + 2] = dag::gtime();
+            trace[4 * (size_t)t + 3] = dag::smid() | (1 << 8) | ((long long)fit << 24) | ((long long)cur << 32);
+          }
         }
         continue;
       }
@@ -268,6 +286,7 @@ __global__ void __launch_bounds__(Cfg::NTHREADS, Cfg::CTAS_PER_SM)
         __syncwarp();
         asm volatile("fence.proxy.async;\n" ::: "memory");   // the bulk copies below read what other CTAs' generic stores wrote
       }
+      if (trace && lane == 0) trace[4 * (size_t)t + 1] = dag::gtime();
       const GemmParams& p = w.p;
       const int m0 = w.m0, n0 = w.n0;
       const double* __restrict__ A = p.A + (size_t)w.batch * p.strideA + (size_t)w.node * p.nodeStrideA;
@@ -330,10 +349,11 @@ __global__ void __launch_bounds__(Cfg::NTHREADS, Cfg::CTAS_PER_SM)
       ws::mbar_wait(full + s, (it / STAGES) & 1);
       const int t = stage_tile[s];
       if (t < 0) break;
-      const DagSeg& sg = segs[stage_seg[s]];
+      const int segi = stage_seg[s];
+      const DagSeg& sg = segs[segi];
       if (sg.kind == 1) {                                 // LEAF marker: the whole CTA factors the tile
         asm volatile("bar.sync 2, %0;\n" ::"n"(Cfg::NTHREADS) : "memory");
-        dag::leaf_task<Cfg::NTHREADS>(sg, t - sg.tile_begin, smem);
+        dag::leaf_task<Cfg::NTHREADS>(sg, t - sg.tile_begin + sg.local0, smem);
         __syncwarp();
         if (lane == 0) ws::mbar_arrive(empty + s);
         it++;
@@ -341,7 +361,7 @@ __global__ void __launch_bounds__(Cfg::NTHREADS, Cfg::CTAS_PER_SM)
       }
       ws::TileEnum te;
       te.init(sg.p.M, sg.p.N, BM, BN, sg.p.lower, sg.rev_m, sg.rev_n);
-      ws::decode_tile<BM, BN, BK>(sg.p, te, t - sg.tile_begin, w);
+      ws::decode_tile<BM, BN, BK>(sg.p, te, t - sg.tile_begin + sg.local0, w);
       AccTile<Cfg> acc;
 #pragma unroll
       for (int i = 0; i < FM; i++)
@@ -390,13 +410,17 @@ __global__ void __launch_bounds__(Cfg::NTHREADS, Cfg::CTAS_PER_SM)
       if (tid == 0) {
         __threadfence();                                  // ... and visible before the tile counts as done
         atomicAdd(done + sg.cnt + w.batch, 1);
+        if (trace) {
+          trace[4 * (size_t)t + 2] = dag::gtime();
+          trace[4 * (size_t)t + 3] = dag::smid() | ((long long)(sg.p.K >> 4) << 9) | ((long long)w.batch << 24) | ((long long)segi << 32);
+        }
       }
     }
   }
 }
 
 template <class Cfg>
-cudaError_t launch_dag(const DagSeg* d_segs, int nseg, int total, int num_sms, int* sched, int* done, cudaStream_t st) {
+cudaError_t launch_dag(const DagSeg* d_segs, int nseg, int total, int num_sms, int* sched, int* done, long long* trace, cudaStream_t st) {
   using SL = WsSmem<Cfg, false, false>;
   auto kern = dmma_dag_kernel<Cfg>;
   static bool attr_set[64] = {false};
@@ -410,7 +434,7 @@ cudaError_t launch_dag(const DagSeg* d_segs, int nseg, int total, int num_sms, i
   if (total <= 0) return cudaSuccess;
   const long long slots = (long long)num_sms * Cfg::CTAS_PER_SM;
   const int grid = (int)(total < slots ? total : slots);
-  kern<<<grid, Cfg::NTHREADS, SL::BYTES, st>>>(d_segs, nseg, total, sched, done);
+  kern<<<grid, Cfg::NTHREADS, SL::BYTES, st>>>(d_segs, nseg, total, sched, done, trace);
   return cudaGetLastError();
 }
 

@@ -90,11 +90,17 @@ struct gps_handle_s {
   int front_fused = 1;           // GPS_FRONT=0: never use the fused small-d front end (small_front_kernel)
   // one-kernel Cholesky (dmma_dag.cuh): segments recorded instead of launched while dag_rec is set (per group view)
   std::vector<DagSeg>* dag_rec = nullptr;
+  int left_looking = 0;          // GPS_LEFT=1: left-looking big level (potrf_left) instead of the recursive right-looking potrf_big (measured equal on C2 x 64: 7.98 vs 7.99 ms)
   int dag_enabled = 0;           // GPS_DAG=1
-  int dag_groups = 4, dag_skew = 9;   // GPS_DAG_GROUPS / GPS_DAG_SKEW: logical groups of fits and their offset (in segments) in the merged list
-  DagSeg* dag_table = nullptr;   // device copy of the merged segment list (static per shape / options; dropped with the graphs)
-  int dag_nseg = 0, dag_total = 0, dag_done_elems = 0;
-  int* dag_done = nullptr;       // per (segment, fit) completion counters
+  int dag_groups = 2, dag_slice = 48;   // GPS_DAG_GROUPS / GPS_DAG_SLICE: logical groups of fits; tiles per slice of a bulk product in the merged list
+  double dag_lat_scale = 1.0;           // GPS_DAG_LAT: scale of the latency estimates of the list scheduler (> 1: dependent steps are listed later)
+  double dag_offset_us = 0.0;           // GPS_DAG_OFFSET: group g may not start before g * offset (keeps the groups out of phase)
+  struct DagPlan {
+    DagSeg* table = nullptr;     // device copy of the merged segment list (static per shape / options; dropped with the graphs)
+    int nseg = 0, total = 0, done_elems = 0;
+    int* done = nullptr;         // per (segment, fit) completion counters
+    long long* trace = nullptr;  // GPS_DAG_TRACE=1 (developer): per-task time stamps of the last run (gps_debug_dag_trace)
+  } dag_plan[2];                 // [0] the factorisation, [1] the factorisation + the remaining levels of the triangular inverse
   int* dag_sched = nullptr;      // the DAG kernel's task counter (2 ints)
   int prio_high = 0;             // GPS_PRIO=1: launch the latency-bound kernels of the diagonal blocks with this (greatest) priority
   int fuse_wk = 1;               // GPS_FUSEWK=0: separate wk_kernel pass after Kinv = U U' (always so for Matern gradients)
@@ -246,14 +252,14 @@ void free_data(H* h) {
 }
 
 void drop_graphs(H* h) {
-  if (h->dag_table) {            // the segment list bakes in shapes, options and buffer addresses
-    cudaStreamSynchronize(h->st);
-    cudaFree(h->dag_table);
-    cudaFree(h->dag_done);
-    h->dag_table = nullptr;
-    h->dag_done = nullptr;
-    h->dag_nseg = h->dag_total = h->dag_done_elems = 0;
-  }
+  for (auto& pl : h->dag_plan)
+    if (pl.table) {              // the segment list bakes in shapes, options and buffer addresses
+      cudaStreamSynchronize(h->st);
+      cudaFree(pl.table);
+      cudaFree(pl.done);
+      if (pl.trace) cudaFree(pl.trace);
+      pl = H::DagPlan();
+    }
   if (h->g_factor) cudaGraphExecDestroy(h->g_factor);
   if (h->g_inverse) cudaGraphExecDestroy(h->g_inverse);
   if (h->g_grad) cudaGraphExecDestroy(h->g_grad);
@@ -704,6 +710,24 @@ void potrf_big(H* h, int J0, int J1) {
   potrf_big(h, mid, J1);
 }
 
+// Left-looking variant of the two-level scheme: block column J first receives ALL updates from the columns to its
+// left in ONE product (K = J * nbig: long k-loops, every output tile written once, and only the nbig-wide diagonal
+// block pays the triangular over-compute — the recursive right-looking form pads and over-computes the whole trailing
+// square at every level), then its diagonal block is factored and inverted and the rows below are solved as in potrf_big.
+void potrf_left(H* h) {
+  const int ld = h->ld, nbig = h->nbig, J = ceil_div(h->ne, nbig);
+  const long long sM = h->strideM;
+  for (int j = 0; j < J; j++) {
+    const int c0 = j * nbig, c1 = std::min(c0 + nbig, h->ne);
+    if (j > 0) {
+      GemmParams p = gp(h->L + c0, ld, sM, h->L + c0, ld, sM, h->naug - c0, c1 - c0, c0);
+      p.lower = 1;
+      gemm<false, false>(h, p, plain(h->Ky + c0 + (size_t)c0 * ld, ld, sM, -1.0, 1.0));
+    }
+    potrf_big(h, j, j + 1);
+  }
+}
+
 // Two-level only for batches: measured on B200, C2 x 64 fits 22.31 -> 22.00 ms (Cholesky stage 9.1 -> 8.1 ms), but a
 // lone fit gets SLOWER (C2 1.84 -> 2.22 ms, n = 8192 Cholesky 10.8 -> 12.5 ms): its launches are latency-bound and
 // the scheme trades wide short-k products for more, smaller launches.  GPS_NBIG=64 turns it off everywhere.
@@ -711,10 +735,15 @@ inline bool two_level(const H* h) { return h->nbig > NB && h->ne > h->nbig && (h
 void make_view(const H* h, int g0, int cnt, cudaStream_t st, H* v);
 
 // The whole factorisation as ONE persistent kernel (dmma_dag.cuh): the launches potrf_big would issue are recorded per
-// logical group of fits, merged with a skew, and consumed as a task list with per-fit dependency counters.
-bool enqueue_potrf_dag(H* h) {
-  const int G = std::max(1, std::min(h->dag_groups, h->batch / 8));
-  if (!h->dag_table) {
+// logical group of fits, merged by a list scheduler, and consumed as a task list with per-fit dependency counters.
+// with_trtri: the levels of the triangular inverse above the diagonal blocks follow in the same list — a group that has
+// finished its factorisation feeds the machine inverse tiles while the others sit in the pivot chains of their last
+// block columns (where the factorisation alone has nothing left to overlap them with).
+void trtri_range(H* h, int lo, int hi, int bs_from, int bs_to);
+bool enqueue_potrf_dag(H* h, bool with_trtri) {
+  const int G = std::max(1, std::min(h->dag_groups, h->batch));
+  H::DagPlan& pl = h->dag_plan[with_trtri ? 1 : 0];
+  if (!pl.table) {
     std::vector<std::vector<DagSeg>> rec(G);
     std::vector<int> fits(G);
     for (int g = 0; g < G; g++) {
@@ -722,60 +751,121 @@ bool enqueue_potrf_dag(H* h) {
       H v;
       make_view(h, g0, g1 - g0, h->st, &v);
       v.dag_rec = &rec[g];
+      v.nbig_forced = true;   // the scheme is the whole batch's, whatever the size of a logical group
       fits[g] = g1 - g0;
       if (two_level(&v)) potrf_big(&v, 0, ceil_div(v.ne, v.nbig));
       else potrf_range(&v, 0, ceil_div(v.ne, NB), v.naug);
+      if (with_trtri) trtri_range(&v, 0, v.ne, two_level(&v) ? v.nbig : NB, 1 << 30);
     }
     const int S = (int)rec[0].size();
     for (int g = 1; g < G; g++)
       if ((int)rec[g].size() != S) return false;
-    // merged order: step k emits segment (k - g * skew) of group g; counters and dependencies follow the group's own chain
+    // Merged order by LIST SCHEDULING on estimated time (tasks are handed out strictly in list order and a CTA that
+    // holds a task whose predecessor is not complete spins, so the list should follow the order in which tasks become
+    // ready).  A machine clock M advances with every bulk slice by its time on all CTAs; every group has a ready time R
+    // (when its chain allows its next segment).  A latency-bound segment (a leaf, a product with a few tiles per fit) is
+    // listed as soon as its group is ready and moves R by its latency; otherwise the ready group that has waited longest
+    // lists a SLICE of its bulk product.  While one group walks through the dependent steps of a diagonal block, the
+    // list therefore offers the CTAs the other groups' bulk tiles.  Counters and dependencies follow each group's own
+    // chain (slices of one product share their counter).
+    const double slots = (double)h->num_sms * WsCfg64::CTAS_PER_SM;
+    auto tile_us = [&](const DagSeg& sg) {
+      const bool tri = sg.p.klo_m || sg.p.klo_n || sg.p.khi_m || sg.p.khi_n;
+      return std::max(1.0, sg.p.K / 16.0 * (tri ? 0.6 : 1.0)) * 1.6 + 4.0;
+    };
     std::vector<DagSeg> all;
-    std::vector<int> prev_cnt(G, -1), prev_need(G, 0);
+    std::vector<int> prev_cnt(G, -1), prev_need(G, 0), pos(G, 0), done_local(G, 0), cur_cnt(G, -1);
+    std::vector<double> ready(G, 0.0);
+    for (int g = 0; g < G; g++) ready[g] = g * h->dag_offset_us;
+    for (int g = 0; g < G; g++) {          // skip empty products (M == 0): nothing to run, nothing to wait for
+      std::vector<DagSeg> keep;
+      for (const DagSeg& sg : rec[g])
+        if (sg.ntasks > 0) keep.push_back(sg);
+      rec[g].swap(keep);
+    }
+    const int S2 = (int)rec[0].size();
+    double M = 0.0;
     int tile = 0, cnt = 0;
-    for (int k = 0; k < S + (G - 1) * h->dag_skew; k++)
-      for (int g = 0; g < G; g++) {
-        const int idx = k - g * h->dag_skew;
-        if (idx < 0 || idx >= S) continue;
-        DagSeg sg = rec[g][idx];
-        const int own_need = sg.dep_need;
-        if (sg.ntasks == 0) continue;      // empty product (M == 0): nothing to run, nothing to wait for
-        sg.tile_begin = tile;
-        sg.cnt = cnt;
-        sg.dep_cnt = prev_cnt[g];
-        sg.dep_need = prev_need[g];
-        tile += sg.ntasks;
-        prev_cnt[g] = cnt;
-        prev_need[g] = own_need;
-        cnt += fits[g];
-        all.push_back(sg);
+    auto is_small = [&](int g) { const DagSeg& sg = rec[g][pos[g]]; return sg.kind == 1 || sg.ntasks <= 4 * fits[g]; };
+    for (;;) {
+      int pick = -1;
+      bool any = false;
+      for (int q = 0; q < G; q++) {        // 1. a ready latency-bound segment
+        if (pos[q] >= S2) continue;
+        any = true;
+        if (ready[q] <= M && is_small(q) && (pick < 0 || ready[q] < ready[pick])) pick = q;
       }
+      if (!any) break;
+      if (pick < 0)                        // 2. a slice of a ready bulk product
+        for (int q = 0; q < G; q++)
+          if (pos[q] < S2 && ready[q] <= M && (pick < 0 || ready[q] < ready[pick])) pick = q;
+      if (pick < 0) {                      // 3. nobody is ready: the machine waits
+        double next = 1e300;
+        for (int q = 0; q < G; q++)
+          if (pos[q] < S2) next = std::min(next, ready[q]);
+        M = next;
+        continue;
+      }
+      const int g = pick;
+      const DagSeg& src = rec[g][pos[g]];
+      const bool small = is_small(g);
+      if (done_local[g] == 0) {            // first slice of this segment: its own counters
+        cur_cnt[g] = cnt;
+        cnt += fits[g];
+      }
+      DagSeg sg = src;
+      sg.local0 = done_local[g];
+      sg.ntasks = small ? src.ntasks : std::min(src.ntasks - done_local[g], h->dag_slice);
+      sg.tile_begin = tile;
+      sg.cnt = cur_cnt[g];
+      sg.dep_cnt = prev_cnt[g];
+      sg.dep_need = prev_need[g];
+      tile += sg.ntasks;
+      all.push_back(sg);
+      done_local[g] += sg.ntasks;
+      if (small) {
+        ready[g] = M + h->dag_lat_scale * (src.kind == 1 ? 35.0 : tile_us(src) + 6.0);
+      } else {
+        M += sg.ntasks * tile_us(src) / slots;
+        if (done_local[g] >= src.ntasks) ready[g] = M + h->dag_lat_scale * tile_us(src);   // its last tiles are still running
+      }
+      if (done_local[g] >= src.ntasks) {
+        prev_cnt[g] = cur_cnt[g];
+        prev_need[g] = src.dep_need;
+        done_local[g] = 0;
+        pos[g]++;
+      }
+    }
     DagSeg sentinel;
     memset(&sentinel, 0, sizeof sentinel);
     sentinel.tile_begin = tile;
     sentinel.ntasks = 0x3fffffff;
     all.push_back(sentinel);
-    if (cudaMalloc((void**)&h->dag_table, sizeof(DagSeg) * all.size()) != cudaSuccess) return false;
-    if (cudaMalloc((void**)&h->dag_done, sizeof(int) * (size_t)std::max(cnt, 1)) != cudaSuccess) return false;
+    if (cudaMalloc((void**)&pl.table, sizeof(DagSeg) * all.size()) != cudaSuccess) return false;
+    if (cudaMalloc((void**)&pl.done, sizeof(int) * (size_t)std::max(cnt, 1)) != cudaSuccess) return false;
     if (!h->dag_sched) {
       if (cudaMalloc((void**)&h->dag_sched, 2 * sizeof(int)) != cudaSuccess) return false;
       cudaMemset(h->dag_sched, 0, 2 * sizeof(int));
     }
-    if (cudaMemcpy(h->dag_table, all.data(), sizeof(DagSeg) * all.size(), cudaMemcpyHostToDevice) != cudaSuccess) return false;
-    h->dag_nseg = (int)all.size() - 1;
-    h->dag_total = tile;
-    h->dag_done_elems = std::max(cnt, 1);
+    if (cudaMemcpy(pl.table, all.data(), sizeof(DagSeg) * all.size(), cudaMemcpyHostToDevice) != cudaSuccess) return false;
+    pl.nseg = (int)all.size() - 1;
+    pl.total = tile;
+    pl.done_elems = std::max(cnt, 1);
+    if (getenv("GPS_DAG_TRACE") && cudaMalloc((void**)&pl.trace, sizeof(long long) * 4 * (size_t)std::max(tile, 1)) != cudaSuccess) return false;
   }
-  CKV(h, cudaMemsetAsync(h->dag_done, 0, sizeof(int) * (size_t)h->dag_done_elems, h->st));
-  CKV(h, launch_dag<WsCfg64>(h->dag_table, h->dag_nseg, h->dag_total, h->num_sms, h->dag_sched, h->dag_done, h->st));
+  CKV(h, cudaMemsetAsync(pl.done, 0, sizeof(int) * (size_t)pl.done_elems, h->st));
+  CKV(h, launch_dag<WsCfg64>(pl.table, pl.nseg, pl.total, h->num_sms, h->dag_sched, pl.done, pl.trace, h->st));
   h->seq_launches++;
   return true;
 }
 
+inline bool dag_usable(const H* h) { return h->dag_enabled && !h->dag_rec && h->batch >= 8 && two_level(h) && h->ws_sched; }
 void enqueue_potrf(H* h) {   // whole factorisation (+ the inverse levels below nbig in the two-level scheme)
-  if (h->dag_enabled && !h->dag_rec && h->batch >= 8 && two_level(h) && h->ws_sched && enqueue_potrf_dag(h)) return;
-  if (two_level(h)) potrf_big(h, 0, ceil_div(h->ne, h->nbig));
-  else potrf_range(h, 0, ceil_div(h->ne, NB), h->naug);
+  if (dag_usable(h) && enqueue_potrf_dag(h, false)) return;
+  if (two_level(h)) {
+    if (h->left_looking) potrf_left(h);
+    else potrf_big(h, 0, ceil_div(h->ne, h->nbig));
+  } else potrf_range(h, 0, ceil_div(h->ne, NB), h->naug);
 }
 void trtri_levels(H* h) {    // what is left of the triangular inverse after enqueue_potrf
   trtri_range(h, 0, h->ne, two_level(h) ? h->nbig : NB, 1 << 30);
@@ -938,6 +1028,25 @@ void enqueue_grad(H* h) {
 typedef void (*SeqFn)(H*);
 
 void enqueue_full(H* h) {   // one whole NLML + gradient evaluation
+  if (dag_usable(h) && h->dag_enabled >= 2) {   // factorisation and triangular inverse as one task list
+    enqueue_front(h);
+    if (enqueue_potrf_dag(h, true)) {
+      nlml_finish_kernel<<<h->batch, 256, 0, h->st>>>(h->L, h->n, h->ne, h->ld, h->strideM, h->nrhs, h->zvec, h->ld, h->d_nlml,
+                                                       h->d_logdet);
+      LAUNCHED(h);
+      alpha_kernel<<<dim3(ceil_div(h->n, 8), h->nrhs, h->batch), 256, 0, h->st>>>(h->Linv, h->n, h->ld, h->strideM, h->zvec,
+                                                                                   h->ld, h->alpha);
+      LAUNCHED(h);
+    } else {
+      enqueue_potrf(h);
+      nlml_finish_kernel<<<h->batch, 256, 0, h->st>>>(h->L, h->n, h->ne, h->ld, h->strideM, h->nrhs, h->zvec, h->ld, h->d_nlml,
+                                                       h->d_logdet);
+      LAUNCHED(h);
+      enqueue_inverse(h);
+    }
+    enqueue_grad(h);
+    return;
+  }
   enqueue_factor(h);
   enqueue_inverse(h);
   enqueue_grad(h);
@@ -957,7 +1066,7 @@ void make_view(const H* h, int g0, int cnt, cudaStream_t st, H* v) {
   v->lookahead = false;
   v->seq_launches = 0;
   v->dag_enabled = 0;     // a view never owns the one-kernel Cholesky's segment table
-  v->dag_table = nullptr;
+  for (auto& pl : v->dag_plan) pl = H::DagPlan();
   const size_t g = (size_t)g0;
   adv(v->Xaug, g * h->strideX); adv(v->Z, g * h->strideX); adv(v->XaugT, g * h->strideXT);
   adv(v->mu, g * h->ldmu); adv(v->ell, g * h->ldmu); adv(v->meanw, g * h->ldmu); adv(v->wsc, g * h->ldmu);
@@ -1223,9 +1332,12 @@ int gps_create_batch(int device, int batch, gps_handle* out) {
   if (const char* ev = getenv("GPS_FUSE64")) h->fuse_k64 = atoi(ev) != 0;
   if (const char* ev = getenv("GPS_TINYCOV")) h->tiny_cov = atoi(ev) != 0;
   if (const char* ev = getenv("GPS_FUSEWK")) h->fuse_wk = atoi(ev) != 0;
+  if (const char* ev = getenv("GPS_LEFT")) h->left_looking = atoi(ev);
   if (const char* ev = getenv("GPS_DAG")) h->dag_enabled = atoi(ev);
   if (const char* ev = getenv("GPS_DAG_GROUPS")) h->dag_groups = std::max(1, atoi(ev));
-  if (const char* ev = getenv("GPS_DAG_SKEW")) h->dag_skew = std::max(0, atoi(ev));
+  if (const char* ev = getenv("GPS_DAG_SLICE")) h->dag_slice = std::max(8, atoi(ev));
+  if (const char* ev = getenv("GPS_DAG_LAT")) h->dag_lat_scale = atof(ev);
+  if (const char* ev = getenv("GPS_DAG_OFFSET")) h->dag_offset_us = atof(ev);
   if (const char* ev = getenv("GPS_PRIO")) {
     int least = 0, greatest = 0;
     if (atoi(ev) != 0 && cudaDeviceGetStreamPriorityRange(&least, &greatest) == cudaSuccess) h->prio_high = greatest;
@@ -2709,6 +2821,16 @@ __global__ void fill_pattern_kernel(double* p, size_t n, unsigned seed) {
 
 // Developer probe: run the panel kernel once on block column 0 of the current Ky with
 // clock64() stamps at its phase boundaries (cycles since kernel start in out[0..n)).
+// developer: per-task time stamps of the last run of the one-kernel Cholesky (plan 0) / Cholesky + inverse (plan 1):
+// 4 values per task [picked, ready, done (ns), sm | leaf << 8 | K/16 << 9 | fit << 24 | segment << 32]; returns the task count
+int gps_debug_dag_trace(gps_handle h, int plan, long long* out, long long cap) {
+  if (!h || plan < 0 || plan > 1 || !h->dag_plan[plan].trace) return -1;
+  cudaStreamSynchronize(h->st);
+  const long long nt = h->dag_plan[plan].total;
+  if (out && cap >= 4 * nt) cudaMemcpy(out, h->dag_plan[plan].trace, sizeof(long long) * 4 * (size_t)nt, cudaMemcpyDeviceToHost);
+  return (int)nt;
+}
+
 int gps_debug_panel_clocks(gps_handle h, long long* out, int n_out) {
   int rc = check_handle(h);
   if (rc) return rc;

@@ -259,6 +259,10 @@ int gps_bench_gemm(gps_handle h, int M, int N, int K, int reps, double* ms_out);
 /* Developer probe: clock64() stamps (cycles since kernel start) at the phase boundaries of the fused
  * Cholesky panel kernel, run once on block column 0 of the current Ky. */
 int gps_debug_panel_clocks(gps_handle h, long long* out, int n_out);
+/* Developer probe (GPS_DAG_TRACE=1): per-task time stamps of the last run of the one-kernel Cholesky (plan 0) or
+ * Cholesky + triangular inverse (plan 1): 4 values per task {picked, ready, done (globaltimer ns),
+ * sm | leaf << 8 | K/16 << 9 | fit << 24 | segment << 32}.  Returns the task count (-1: no trace). */
+int gps_debug_dag_trace(gps_handle h, int plan, long long* out, long long cap);
 
 #ifdef __cplusplus
 }

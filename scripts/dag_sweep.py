@@ -1,4 +1,5 @@
-"""Cholesky-stage time of the bench workload (C2 x 64) for the one-kernel Cholesky under several (groups, skew) settings."""
+"""Step and Cholesky-stage time of the bench workload (C2 x B) for the one-kernel Cholesky (GPS_DAG=1) / Cholesky + triangular
+inverse (GPS_DAG=2) under several scheduler settings: python scripts/dag_sweep.py B [dag,groups,slice,lat,offset ...]"""
 import os, sys
 import numpy as np
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -9,13 +10,12 @@ X, y, ev, lnc, par0 = bench.batch_workload(0, B)
 rng = np.random.default_rng(0)
 par = par0[None, :] + 0.05 * rng.standard_normal((B, par0.size))
 ref = None
-cfgs = [("0", 1, 0)] + [("1", g, s) for g in (1, 2, 4, 8) for s in (0, 6, 12, 20)]
-if len(sys.argv) > 2:
-    cfgs = [("0", 1, 0)] + [("1", int(a.split(",")[0]), int(a.split(",")[1])) for a in sys.argv[2:]]
-for dag, G, S in cfgs:
-    os.environ["GPS_DAG"] = dag
-    os.environ["GPS_DAG_GROUPS"] = str(G)
-    os.environ["GPS_DAG_SKEW"] = str(S)
+cfgs = [("0", 1, 48, 1.0, 0.0)]
+for a in sys.argv[2:]:
+    f = a.split(",")
+    cfgs.append((f[0], int(f[1]), int(f[2]), float(f[3]), float(f[4])))
+for dag, G, S, LAT, OFF in cfgs:
+    os.environ.update(GPS_DAG=dag, GPS_DAG_GROUPS=str(G), GPS_DAG_SLICE=str(S), GPS_DAG_LAT=str(LAT), GPS_DAG_OFFSET=str(OFF))
     fit = gp.Fit(0, batch=B)
     fit.set_options("ARD", "Zero", "noiseCorrVec", "intended")
     fit.set_data(X, y, ev)
@@ -28,5 +28,5 @@ for dag, G, S in cfgs:
     fit.time_stages()
     st = fit.time_stages()
     err = max(np.max(np.abs(f - ref[0]) / np.abs(ref[0])), np.max(np.abs(g - ref[1])) / np.max(np.abs(ref[1])))
-    print(f"dag={dag} groups={G} skew={S}: step {ms:.3f} ms, cholesky stage {st[1]:.3f} ms, rel diff vs multi-launch {err:.1e}", flush=True)
+    print(f"dag={dag} groups={G} slice={S} lat={LAT} offset={OFF}: step {ms:.3f} ms, cholesky stage {st[1]:.3f} ms, rel diff vs multi-launch {err:.1e}", flush=True)
     fit.close()
