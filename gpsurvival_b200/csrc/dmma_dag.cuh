@@ -373,6 +373,11 @@ __global__ void __launch_bounds__(Cfg::NTHREADS, Cfg::CTAS_PER_SM)
         if (lane == 0) ws::mbar_arrive(empty + s);
         it++;
       }
+      int wk_lo = 0, wk_hi = 0x7fffffff;                  // this warp's own k-range (see dmma_ws_kernel)
+      if (w.p.klo_m) wk_lo = max(wk_lo, w.m0 + wm0);
+      if (w.p.klo_n) wk_lo = max(wk_lo, w.n0 + wn0);
+      if (w.p.khi_m) wk_hi = min(wk_hi, w.m0 + wm0 + Cfg::WM);
+      if (w.p.khi_n) wk_hi = min(wk_hi, w.n0 + wn0 + Cfg::WN);
       for (int kt = 0; kt < w.nkt; kt++, it++) {
         if (kt > 0) {
           s = it % STAGES;
@@ -380,7 +385,8 @@ __global__ void __launch_bounds__(Cfg::NTHREADS, Cfg::CTAS_PER_SM)
         }
         const double* a_s = sA + s * SL::A_STAGE;
         const double* b_s = sB + s * SL::B_STAGE;
-        if (!skip) {
+        const int kb = w.k_lo + kt * BK;
+        if (!skip && kb + BK > wk_lo && kb < wk_hi) {
 #pragma unroll
           for (int ks = 0; ks < BK / 4; ks++) {
             double af[FM], bf[FN];

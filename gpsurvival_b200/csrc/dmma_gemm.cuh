@@ -122,6 +122,13 @@ struct epi_skips_upper { static constexpr bool value = false; };
 template <class Epi>
 struct epi_skips_upper<Epi, decltype((void)Epi::kSkipUpper)> { static constexpr bool value = Epi::kSkipUpper; };
 
+// Epilogues that never touch the shared scratch area declare `static constexpr bool kNoScratch = true`: the persistent
+// kernel then needs no barrier among its consumer warps between tiles.
+template <class Epi, class = void>
+struct epi_no_scratch { static constexpr bool value = false; };
+template <class Epi>
+struct epi_no_scratch<Epi, decltype((void)Epi::kNoScratch)> { static constexpr bool value = Epi::kNoScratch; };
+
 template <class Cfg, bool A_KC, bool B_KC>
 struct SmemLayout {
   static constexpr int LDA = (A_KC ? Cfg::BK : Cfg::BM) + 4;
@@ -290,6 +297,7 @@ struct EpiPlain {
   // lower-triangular products (p.lower): what lies above the diagonal inside a diagonal tile is never read by any consumer
   // of the Gram slices / the Cholesky's trailing matrix / Kinv, so warps that own only such entries skip the tile
   static constexpr bool kSkipUpper = true;
+  static constexpr bool kNoScratch = true;
   template <class Cfg>
   __device__ __forceinline__ void operator()(const GemmParams& p, AccTile<Cfg>& a, double*) const {
     if (a.skip) return;

@@ -338,6 +338,14 @@ __global__ void __launch_bounds__(Cfg::NTHREADS, Cfg::CTAS_PER_SM)
         if (lane == 0) ws::mbar_arrive(empty + s);
         it++;
       }
+      // triangular operands: the tile's k-range [k_lo, k_hi) is the union over its rows / columns; THIS warp's rows and
+      // columns need less, and the k-steps outside its own range only multiply the operand's stored zeros — it keeps the
+      // barriers in step for them and skips the math (same sums bit for bit: the skipped terms are exact zeros)
+      int wk_lo = 0, wk_hi = 0x7fffffff;
+      if (w.p.klo_m) wk_lo = max(wk_lo, w.m0 + wm0);
+      if (w.p.klo_n) wk_lo = max(wk_lo, w.n0 + wn0);
+      if (w.p.khi_m) wk_hi = min(wk_hi, w.m0 + wm0 + Cfg::WM);
+      if (w.p.khi_n) wk_hi = min(wk_hi, w.n0 + wn0 + Cfg::WN);
       for (int kt = 0; kt < w.nkt; kt++, it++) {
         if (kt > 0) {
           s = it % STAGES;
@@ -345,7 +353,8 @@ __global__ void __launch_bounds__(Cfg::NTHREADS, Cfg::CTAS_PER_SM)
         }
         const double* a_s = sA + s * SL::A_STAGE;
         const double* b_s = sB + s * SL::B_STAGE;
-        if (!skip) {
+        const int kb = w.k_lo + kt * BK;
+        if (!skip && kb + BK > wk_lo && kb < wk_hi) {
 #pragma unroll
         for (int ks = 0; ks < BK / 4; ks++) {
           double af[FM], bf[FN];
@@ -381,7 +390,7 @@ __global__ void __launch_bounds__(Cfg::NTHREADS, Cfg::CTAS_PER_SM)
       acc.batch = w.batch;
       acc.split = w.split;
       acc.node = w.node;
-      Cfg::sync();   // the epilogue scratch of the previous tile is no longer being read
+      if (!epi_no_scratch<Epi>::value) Cfg::sync();   // the epilogue scratch of the previous tile is no longer being read
       epi(w.p, acc, scratch);
     }
   }
@@ -396,7 +405,7 @@ __global__ void __launch_bounds__(Cfg::NTHREADS, Cfg::CTAS_PER_SM)
 // 128 x 128: least L2 traffic, best for large problems; 64 x 64: half the over-compute on triangular / ragged
 // problems and small CTAs that share an SM with other kernels; 80 x 80: for row counts that 80 divides better.
 using WsCfg128 = WsCfg<128, 128, 16, 2, 4, 5>;        // 8 consumer warps of 64 x 32, 5 stages, 170 KB smem
-using WsCfg64 = WsCfg<64, 64, 16, 2, 2, 3, 3>;        // 4 consumer warps of 32 x 32, 3 stages, 52 KB smem
+using WsCfg64 = WsCfg<64, 64, 16, 2, 2, 4, 3>;        // 4 consumer warps of 32 x 32, 3 stages, 52 KB smem
 using WsCfg80 = WsCfg<80, 80, 16, 2, 2, 4, 2>;        // 4 consumer warps of 40 x 40, 4 stages, 86 KB smem
 using WsCfg96 = WsCfg<96, 96, 16, 2, 4, 6, 1>;         // 8 consumer warps of 48 x 24: row counts just under a multiple of 96 (n = 285)
 using WsCfg96x64 = WsCfg<96, 64, 16, 2, 2, 3, 3>;     // 4 consumer warps of 48 x 32, 3 CTAs/SM: the same rows against a wide N (M * Xaug, d = 10^4)
