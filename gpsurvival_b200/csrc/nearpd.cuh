@@ -176,6 +176,7 @@ int jacobi_eigh(H* h, double* A, double* V, int n, int ld, double2* rot, double*
   h->launches++;
   std::vector<double> hp((size_t)2 * n);
   const size_t smem = (size_t)n * sizeof(double);
+  double prev_ratio = 1.0;
   for (int sweep = 0; sweep < 60; sweep++) {
     for (int step = 0; step < ne - 1; step++) {
       jacobi_cols_kernel<<<ne / 2, 256, 0, h->st>>>(A, V, n, ne, ld, step, rot);
@@ -191,9 +192,22 @@ int jacobi_eigh(H* h, double* A, double* V, int n, int ld, double2* rot, double*
       off += hp[2 * j];
       dg += hp[2 * j + 1];
     }
-    if (!(off > 1e-30 * (off + dg))) return GPS_OK;     // off-diagonal mass below 1e-15 of the Frobenius norm
+    // converged: off-diagonal mass below (n eps)^2 of the squared Frobenius norm (never tighter than 1e-15 of the norm) — or
+    // stagnated at the rounding noise the rotations themselves leave behind (n = 2000 with a thousand-fold zero eigenvalue
+    // can stall above the first bound): the spectrum is then as accurate as it gets, which is far inside nearPD's own eig.tol = 1e-6
+    const double ratio = off / (off + dg);
+    const double tol = std::max(1e-30, (double)n * (double)n * 4.93e-32);
+    if (!(ratio > tol)) return GPS_OK;
+    if (sweep >= 6 && ratio <= 1e-20 && ratio > 0.25 * prev_ratio) return GPS_OK;
+    prev_ratio = ratio;
   }
-  return fail(h, GPS_ERR_STATE, "nearPD: the Jacobi eigen-solver did not converge in 60 sweeps");
+  // no usable spectrum: the caller treats the point like any other that cannot be repaired (ForOptimisationLog.R:50, stop())
+  {
+    char buf[256];
+    snprintf(buf, sizeof buf, "covariance matrix is not positive definite; nearPD: the Jacobi eigen-solver did not converge in 60 sweeps "
+                              "(off-diagonal share of the squared Frobenius norm %.3g)", prev_ratio);
+    return fail(h, GPS_ERR_NOT_PD, buf);
+  }
 }
 
 // X = V diag(w) V' (full symmetric, n x n) on the DMMA engine: lower tiles of the weighted product, then mirrored
