@@ -81,6 +81,7 @@ PROTOTYPES = {
     "gps_time_stages": (C.c_int, [_h, _dp]),
     "gps_bench_gemm": (C.c_int, [_h, C.c_int, C.c_int, C.c_int, C.c_int, _dp]),
     "gps_debug_panel_clocks": (C.c_int, [_h, C.POINTER(C.c_longlong), C.c_int]),
+    "gps_multi_release": (C.c_int, []),
     "gps_debug_dag_trace": (C.c_int, [_h, C.c_int, C.POINTER(C.c_longlong), C.c_longlong]),
 }
 

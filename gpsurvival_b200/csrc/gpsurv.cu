@@ -93,6 +93,7 @@ struct gps_handle_s {
   int left_looking = 0;          // GPS_LEFT=1: left-looking big level (potrf_left) instead of the recursive right-looking potrf_big (measured equal on C2 x 64: 7.98 vs 7.99 ms)
   int dag_enabled = 0;           // GPS_DAG=1
   int dag_groups = 2, dag_slice = 48;   // GPS_DAG_GROUPS / GPS_DAG_SLICE: logical groups of fits; tiles per slice of a bulk product in the merged list
+  int dag_policy = 0;                   // GPS_DAG_POLICY: list-scheduler order among ready groups (0 = longest waiting, 1 = depth first, inverse as filler)
   double dag_lat_scale = 1.0;           // GPS_DAG_LAT: scale of the latency estimates of the list scheduler (> 1: dependent steps are listed later)
   double dag_offset_us = 0.0;           // GPS_DAG_OFFSET: group g may not start before g * offset (keeps the groups out of phase)
   struct DagPlan {
@@ -745,7 +746,7 @@ bool enqueue_potrf_dag(H* h, bool with_trtri) {
   H::DagPlan& pl = h->dag_plan[with_trtri ? 1 : 0];
   if (!pl.table) {
     std::vector<std::vector<DagSeg>> rec(G);
-    std::vector<int> fits(G);
+    std::vector<int> fits(G), split(G, 0);
     for (int g = 0; g < G; g++) {
       const int g0 = (int)((long long)h->batch * g / G), g1 = (int)((long long)h->batch * (g + 1) / G);
       H v;
@@ -755,6 +756,7 @@ bool enqueue_potrf_dag(H* h, bool with_trtri) {
       fits[g] = g1 - g0;
       if (two_level(&v)) potrf_big(&v, 0, ceil_div(v.ne, v.nbig));
       else potrf_range(&v, 0, ceil_div(v.ne, NB), v.naug);
+      split[g] = (int)rec[g].size();     // what follows is the triangular inverse: filler work for the list scheduler
       if (with_trtri) trtri_range(&v, 0, v.ne, two_level(&v) ? v.nbig : NB, 1 << 30);
     }
     const int S = (int)rec[0].size();
@@ -779,9 +781,14 @@ bool enqueue_potrf_dag(H* h, bool with_trtri) {
     for (int g = 0; g < G; g++) ready[g] = g * h->dag_offset_us;
     for (int g = 0; g < G; g++) {          // skip empty products (M == 0): nothing to run, nothing to wait for
       std::vector<DagSeg> keep;
-      for (const DagSeg& sg : rec[g])
-        if (sg.ntasks > 0) keep.push_back(sg);
+      int nsplit = 0;
+      for (int i = 0; i < (int)rec[g].size(); i++)
+        if (rec[g][i].ntasks > 0) {
+          if (i < split[g]) nsplit++;
+          keep.push_back(rec[g][i]);
+        }
       rec[g].swap(keep);
+      split[g] = nsplit;
     }
     const int S2 = (int)rec[0].size();
     double M = 0.0;
@@ -790,15 +797,26 @@ bool enqueue_potrf_dag(H* h, bool with_trtri) {
     for (;;) {
       int pick = -1;
       bool any = false;
+      // policy 0: the ready group that has waited longest goes first (the groups advance side by side);
+      // policy 1: DEPTH FIRST — the lowest-numbered ready group goes first, and the triangular inverse (class 1) is filler
+      // that runs only when no factorisation segment is ready: the groups finish their factorisations one after the
+      // other, so the latency-bound last block columns of one group sit beside the bulk of the groups behind it, and the
+      // last groups' beside the inverse tiles of the groups that are done
+      auto better = [&](int q, int cur) {
+        if (cur < 0) return true;
+        if (h->dag_policy == 0) return ready[q] < ready[cur];
+        const int cq = pos[q] >= split[q] ? 1 : 0, cc = pos[cur] >= split[cur] ? 1 : 0;
+        return cq != cc ? cq < cc : q < cur;
+      };
       for (int q = 0; q < G; q++) {        // 1. a ready latency-bound segment
         if (pos[q] >= S2) continue;
         any = true;
-        if (ready[q] <= M && is_small(q) && (pick < 0 || ready[q] < ready[pick])) pick = q;
+        if (ready[q] <= M && is_small(q) && better(q, pick)) pick = q;
       }
       if (!any) break;
       if (pick < 0)                        // 2. a slice of a ready bulk product
         for (int q = 0; q < G; q++)
-          if (pos[q] < S2 && ready[q] <= M && (pick < 0 || ready[q] < ready[pick])) pick = q;
+          if (pos[q] < S2 && ready[q] <= M && better(q, pick)) pick = q;
       if (pick < 0) {                      // 3. nobody is ready: the machine waits
         double next = 1e300;
         for (int q = 0; q < G; q++)
@@ -1337,6 +1355,7 @@ int gps_create_batch(int device, int batch, gps_handle* out) {
   if (const char* ev = getenv("GPS_DAG_GROUPS")) h->dag_groups = std::max(1, atoi(ev));
   if (const char* ev = getenv("GPS_DAG_SLICE")) h->dag_slice = std::max(8, atoi(ev));
   if (const char* ev = getenv("GPS_DAG_LAT")) h->dag_lat_scale = atof(ev);
+  if (const char* ev = getenv("GPS_DAG_POLICY")) h->dag_policy = atoi(ev);
   if (const char* ev = getenv("GPS_DAG_OFFSET")) h->dag_offset_us = atof(ev);
   if (const char* ev = getenv("GPS_PRIO")) {
     int least = 0, greatest = 0;
@@ -2572,6 +2591,8 @@ int gps_partition_lpt(const double* cost, int count, int nparts, int* part_out) 
 
 }  // extern "C"  (the shared multi-device driver below is C++)
 
+#include <map>
+#include <mutex>
 #include <thread>
 
 namespace {
@@ -2587,6 +2608,46 @@ struct MultiJob {
 };
 
 // One device's share: its own handle (one handle per host thread per device), sub-batches sized to the free memory.
+// One idle handle per device is kept between calls of the multi-device entry points: creating a handle, allocating its
+// per-fit buffers and capturing its graphs costs 0.2 - 0.3 s, which at 64 fits per GPU (512 C4 fits over 8 GPUs) is as long as
+// the fits themselves.  A worker takes the cached handle when its batch size matches (a handle re-binds data of any shape,
+// like the R session's), otherwise it frees it first, so that at most one idle handle's memory stays resident per device;
+// gps_multi_release() frees them all.
+std::mutex g_idle_mu;
+std::map<int, gps_handle> g_idle_handle;
+
+gps_handle take_idle_handle(int device, int batch) {
+  gps_handle h = nullptr;
+  {
+    std::lock_guard<std::mutex> lk(g_idle_mu);
+    auto it = g_idle_handle.find(device);
+    if (it != g_idle_handle.end()) {
+      h = it->second;
+      g_idle_handle.erase(it);
+    }
+  }
+  if (h && h->batch != batch) {
+    gps_destroy(h);
+    h = nullptr;
+  }
+  return h;
+}
+void park_idle_handle(int device, gps_handle h) {
+  static const bool off = getenv("GPS_MULTI_CACHE") && atoi(getenv("GPS_MULTI_CACHE")) == 0;   // developer A/B
+  if (off) {
+    gps_destroy(h);
+    return;
+  }
+  gps_handle old = nullptr;
+  {
+    std::lock_guard<std::mutex> lk(g_idle_mu);
+    auto it = g_idle_handle.find(device);
+    if (it != g_idle_handle.end()) old = it->second;
+    g_idle_handle[device] = h;
+  }
+  if (old) gps_destroy(old);
+}
+
 void multi_worker(const MultiJob& J, int device, const std::vector<int>& mine, int* rc_out, std::string* err_out, long long* ticks_out) {
   *rc_out = GPS_OK;
   *ticks_out = 0;
@@ -2603,8 +2664,8 @@ void multi_worker(const MultiJob& J, int device, const std::vector<int>& mine, i
   const int n = J.n, d = J.d, m = J.m, len = J.len;
   for (size_t s0 = 0; s0 < mine.size(); s0 += cap) {
     const int B = (int)std::min((size_t)cap, mine.size() - s0);
-    gps_handle h = nullptr;
-    int rc = gps_create_batch(device, B, &h);
+    gps_handle h = take_idle_handle(device, B);
+    int rc = h ? GPS_OK : gps_create_batch(device, B, &h);
     if (!rc) rc = gps_set_options(h, J.cov_form, J.mean_form, J.noise_corr, J.ard_mode);
     std::vector<double> X, y, ev, Xt, ps((size_t)B * len);
     std::vector<int> tr, te;
@@ -2667,7 +2728,7 @@ void multi_worker(const MultiJob& J, int device, const std::vector<int>& mine, i
       if (J.train_mean) std::copy(trm.begin() + (size_t)b * n, trm.begin() + (size_t)(b + 1) * n, J.train_mean + f * n);
     }
     *ticks_out += ticks;
-    gps_destroy(h);
+    park_idle_handle(device, h);
   }
 }
 
@@ -2713,6 +2774,16 @@ int gps_fit_batch_multi(const int* devices, int ndev, int total, int cov_form, i
              X, y_log, events, par_start, Xtest, nullptr,
              par_out, objective_out, logmarlik_out, targets_learned_out, test_mean, test_varf, test_vard, train_mean, rounds_out, status_out};
   return multi_run(J, devices, ndev, evaluations_out);
+}
+
+int gps_multi_release(void) {
+  std::map<int, gps_handle> take;
+  {
+    std::lock_guard<std::mutex> lk(g_idle_mu);
+    take.swap(g_idle_handle);
+  }
+  for (auto& kv : take) gps_destroy(kv.second);
+  return GPS_OK;
 }
 
 int gps_fit_folds_multi(const int* devices, int ndev, int total, int cov_form, int mean_form, int noise_corr, int ard_mode,

@@ -118,7 +118,12 @@ int gps_nlml(gps_handle h, const double* par, int len, double* nlml_out);
 /* ---- OptimisationGradientLog.R:1-94 ---------------------------------------------------- */
 /* Gradient w.r.t. `par`, same order as `par` (:88-89).  Reuses the factorisation of the last
  * gps_nlml when `par`, targets and noise correction are unchanged (optim calls fn and gr
- * separately — SURVEY.md §3.3).  nlml_out may be NULL. */
+ * separately — SURVEY.md §3.3).  nlml_out may be NULL.
+ * SqExp: the reference branch (:50-57) restated; ARD: the analytic contraction of north_star item 4 (ard_mode =
+ * INTENDED); Matern: derived (the reference has none, :6).  NOT offered: the reference's as-written ARD branch
+ * (:58-69) — it is not the derivative of its own likelihood (unscaled dist(X), exp(+r/4/ell^3), no chain-rule
+ * factors), an optimiser fed with it does not descend; with ard_mode = AS_WRITTEN and d > 1 the call returns
+ * GPS_ERR_UNSUPPORTED and says so.  The oracle keeps a restatement of it for the record. */
 int gps_nlml_grad(gps_handle h, const double* par, int len, double* nlml_out, double* grad_out);
 
 /* ---- GPRegression.R:60-82 (everything after optim) ------------------------------------- */
@@ -214,7 +219,10 @@ int gps_fit_batch_status(gps_handle h, int* status_out);
  * device's free memory, NO collective and no peer traffic: results are scattered back into the caller's arrays at the
  * fits' positions.  Options as gps_set_options; every other argument as gps_fit_batch with `total` as the batch;
  * status_out[total] as gps_fit_batch_status; evaluations_out = the largest per-device number of batched evaluations.
- * A device may be listed more than once (two host threads sharing one GPU). */
+ * A device may be listed more than once (two host threads sharing one GPU).
+ * Between calls ONE idle handle per device stays alive (creating a handle, its buffers and its graphs costs as much as 64
+ * C4-shaped fits); it is reused when the next call's per-device batch matches, replaced otherwise, and freed by
+ * gps_multi_release(). */
 int gps_fit_batch_multi(const int* devices, int ndev, int total, int cov_form, int mean_form, int noise_corr, int ard_mode,
                         const double* X, int n, int d, const double* y_log, const double* events, const double* par_start, int len,
                         int method, int maxit, double tolerance, int max_count, int survival, const double* Xtest, int m,
@@ -231,6 +239,8 @@ int gps_fit_folds_multi(const int* devices, int ndev, int total, int cov_form, i
                         double* test_vard, double* train_mean, int* status_out, long long* evaluations_out);
 /* The partitioner itself (pure host code): part_out[i] in [0, nparts) for jobs with the given costs, longest first. */
 int gps_partition_lpt(const double* cost, int count, int nparts, int* part_out);
+/* Free the idle handles the multi-device entry points keep between calls (device memory back to the caller). */
+int gps_multi_release(void);
 
 /* Identity of the model gps_regress_finalize left resident (0 = none): bumped by every finalize.  A drop-in GPPredict keeps
  * the token GPRegression returned and refuses to predict GPR / GPS1 from a different resident model (GPPredict.R:12-13 uses
