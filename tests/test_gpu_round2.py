@@ -312,6 +312,66 @@ def test_multi_device_entry_points_equal_single_handle(method):
         assert relmax(res["par"], ref["par"]) <= 1e-6
 
 
+def test_multi_device_idle_handle_is_reused_across_shapes_and_released():
+    """The multi-device entry points keep one idle handle per device between calls: a call with another data shape (same
+    per-device batch -> the SAME handle re-binds) and the first call repeated must give bit-identical results to runs on
+    fresh handles (gps_multi_release in between)."""
+    lib = _lib.load()
+    opts = dict(cov_form="ARD", mean_form="Zero", noise_corr="noiseCorrVec")
+    kw = dict(method="L-BFGS", maxit=4, tolerance=1e300, max_count=6, survival=True)
+
+    def run(shape):
+        Xp, yp, evp, tr, te = _fold_problem(T=5, **shape)
+        d = Xp.shape[1]
+        rng = np.random.default_rng(11)
+        start = np.stack([np.concatenate([np.log([0.2, 0.8]), np.log(1.7 * np.sqrt(d)) + 0.1 * rng.standard_normal(d)]) for _ in range(5)])
+        return gp.fit_folds_multi([0], Xp, yp, evp, tr, te, start, **opts, **kw)
+
+    a = dict(npool=90, n=60, m=20, d=3, seed=77)
+    b = dict(npool=120, n=84, m=24, d=5, seed=78)
+    assert lib.gps_multi_release() == 0
+    fresh_a = run(a)
+    assert lib.gps_multi_release() == 0
+    fresh_b = run(b)                      # leaves its handle idle
+    reused_a = run(a)                     # same batch, other n / d / m: the idle handle re-binds
+    reused_b = run(b)
+    assert lib.gps_multi_release() == 0
+    for fresh, reused in ((fresh_a, reused_a), (fresh_b, reused_b)):
+        assert np.all(reused["status"] == 0)
+        for key in ("objective", "par", "funcMeanPred", "varData", "trainingSetPredictions", "trainingTargetsLearned"):
+            assert np.array_equal(fresh[key], reused[key]), key
+
+
+def test_one_kernel_cholesky_agrees_with_the_multi_launch_path(monkeypatch):
+    """GPS_DAG=1 / 2 (csrc/dmma_dag.cuh: the factorisation, optionally with the triangular-inverse levels, as ONE persistent
+    task-list kernel — experimental, off by default) against the default path on a batch that takes the two-level scheme.
+    The two group partial sums differently (64 x 64 tiles everywhere, in-place leaf inverse): agreement to rounding."""
+    n, d, B = 600, 4, 16
+    pbs = [synth.make_problem(n, 4, d, n // 2, 100 + b) for b in range(3)]
+    X = np.stack([pbs[b % 3]["trainingData"] for b in range(B)])
+    y = np.log(np.stack([pbs[b % 3]["trainingTargets"] for b in range(B)]))
+    ev = np.stack([pbs[b % 3]["events"] for b in range(B)])
+    rng = np.random.default_rng(3)
+    lnc = np.log(0.2) + 0.3 * rng.standard_normal((B, int(np.sum(ev[0] == 0))))
+    par = np.concatenate([np.log([0.2, 0.8]), np.log(1.7 * np.sqrt(d)) * np.ones(d)])[None, :] + 0.05 * rng.standard_normal((B, 2 + d))
+    out = {}
+    for dag, groups in (("0", "1"), ("1", "1"), ("1", "16"), ("2", "4"), ("2", "16")):
+        monkeypatch.setenv("GPS_DAG", dag)
+        monkeypatch.setenv("GPS_DAG_GROUPS", groups)
+        fit = _make_fit(X, y, ev, "ARD", "Zero", "noiseCorrVec", lnc, batch=B)
+        res = [fit.nlml_grad(par) for _ in range(3)]            # direct run, graph capture, replay
+        fin = fit.finalize(par, want_L=True)
+        fit.close()
+        for f, g in res[1:]:
+            assert np.array_equal(f, res[0][0]) and np.array_equal(g, res[0][1])      # replays are bitwise reproducible
+        out[(dag, groups)] = (res[0][0], res[0][1], np.tril(fin["L"]))
+    ref = out[("0", "1")]
+    for key, (f, g, L) in out.items():
+        assert relmax(f, ref[0]) <= 1e-12 and relmax(g, ref[1]) <= 1e-10 and relmax(L, ref[2]) <= 1e-12, key
+    # the list order (groups) decides which CTA runs a tile, never what it computes
+    assert np.array_equal(out[("1", "1")][0], out[("1", "16")][0]) and np.array_equal(out[("2", "4")][1], out[("2", "16")][1])
+
+
 # ---- CalculateMetrics.R:18,21 on the device (SURVEY.md §8f-4) ------------------------------------------------------
 def test_metrics_match_oracle_exactly():
     rng = np.random.default_rng(12)
