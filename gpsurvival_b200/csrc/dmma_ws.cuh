@@ -406,6 +406,7 @@ __global__ void __launch_bounds__(Cfg::NTHREADS, Cfg::CTAS_PER_SM)
 // problems and small CTAs that share an SM with other kernels; 80 x 80: for row counts that 80 divides better.
 using WsCfg128 = WsCfg<128, 128, 16, 2, 4, 5>;        // 8 consumer warps of 64 x 32, 5 stages, 170 KB smem
 using WsCfg64 = WsCfg<64, 64, 16, 2, 2, 4, 3>;        // 4 consumer warps of 32 x 32, 3 stages, 52 KB smem
+using WsCfg48 = WsCfg<48, 48, 16, 2, 2, 4, 4>;        // 4 consumer warps of 24 x 24, 4 CTAs/SM: lower-triangular products of a few hundred rows (least diagonal-tile over-compute)
 using WsCfg80 = WsCfg<80, 80, 16, 2, 2, 4, 2>;        // 4 consumer warps of 40 x 40, 4 stages, 86 KB smem
 using WsCfg96 = WsCfg<96, 96, 16, 2, 4, 6, 1>;         // 8 consumer warps of 48 x 24: row counts just under a multiple of 96 (n = 285)
 using WsCfg96x64 = WsCfg<96, 64, 16, 2, 2, 3, 3>;     // 4 consumer warps of 48 x 32, 3 CTAs/SM: the same rows against a wide N (M * Xaug, d = 10^4)

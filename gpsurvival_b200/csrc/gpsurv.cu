@@ -313,6 +313,7 @@ int pick_nt_tile(const H* h, const GemmParams& p) {
   {
     static const int forced = getenv("GPS_WSTILE") ? atoi(getenv("GPS_WSTILE")) : 0;   // developer A/B: 64 / 80 / 96 / 128 for square-tile products
     if ((forced == 64 || forced == 80 || forced == 96 || forced == 128) && p.M >= forced && p.N >= forced) return forced;
+    if (forced == 48 && p.lower && p.M >= 48 && p.N >= 48) return 48;   // lower-triangular products only
   }
   if (use_ws128(h, p)) return 128;
   if (p.N <= 32 && !p.lower && (long long)ceil_div(p.M, 128) * h->batch * p.nodes * p.ksplit >= h->num_sms) return p.N <= 24 ? 24 : 32;
@@ -337,12 +338,24 @@ int pick_nt_tile(const H* h, const GemmParams& p) {
       const double w96w = (double)round_up(p.M, 96) * round_up(p.N, 64);
       if (w96w < best * 1.02) { best = w96w; pick = 97; }   // 96 x 64, three CTAs per SM
     }
+    if (p.lower && p.M == p.N && p.diag_off == 0) {
+      // symmetric outputs (Gram, Kinv): what is executed is the lower triangle of TILES, the diagonal ones at 3/4 (the warp
+      // above the diagonal skips) — at a few hundred rows the tile size decides the over-compute: n = 285 runs 44.9 K
+      // entries on 48-wide tiles, 48.4 K on 96-wide ones (40.6 K needed).  Small tiles pay in L2 traffic (twice the bytes per
+      // flop of 96-wide ones), hence the 4 % handicap.  Measured: C3 x 32 Gram 1.246 -> 1.167 ms.
+      auto lower_work = [&](int T) {
+        const int nt = ceil_div(p.N, T);
+        return (0.5 * nt * (nt - 1) + 0.75 * nt) * (double)T * T;
+      };
+      const int cur = pick == 97 ? 96 : pick;
+      if (1.04 * lower_work(48) < lower_work(cur)) pick = 48;
+    }
     return pick;
   }
   return 64;
 }
 inline int tile_bm(const H* h, int code) {   // rows of the tile a pick_nt_tile() code stands for
-  return code == 128 || code == 32 || code == 24 ? 128 : code == 80 ? 80 : code == 96 || code == 97 ? 96 : code == 64 ? 64
+  return code == 128 || code == 32 || code == 24 ? 128 : code == 80 ? 80 : code == 96 || code == 97 ? 96 : code == 64 ? 64 : code == 48 ? 48
          : (h->force_tile == 2 ? 128 : 64);
 }
 
@@ -390,6 +403,8 @@ void gemm(H* h, const GemmParams& p, const Epi& epi) {
         e = launch_gemm_ws<WsCfg128, false, false, Epi>(p, epi, h->batch, h->num_sms, sched, h->cur);
       else if (tile == 80)
         e = launch_gemm_ws<WsCfg80, false, false, Epi>(p, epi, h->batch, h->num_sms, sched, h->cur);
+      else if (tile == 48)
+        e = launch_gemm_ws<WsCfg48, false, false, Epi>(p, epi, h->batch, h->num_sms, sched, h->cur);
       else if (tile == 32)
         e = launch_gemm_ws<WsCfgN32, false, false, Epi>(p, epi, h->batch, h->num_sms, sched, h->cur);
       else if (tile == 24)
@@ -436,6 +451,8 @@ void gemm_ks(H* h, const GemmParams& p, const EpiPlain& epi) {
     e = launch_gemm_ws<WsCfg128, false, false, EpiPlain, true>(p, epi, h->batch, h->num_sms, sched, h->cur);
   else if (tile == 80)
     e = launch_gemm_ws<WsCfg80, false, false, EpiPlain, true>(p, epi, h->batch, h->num_sms, sched, h->cur);
+  else if (tile == 48)
+    e = launch_gemm_ws<WsCfg48, false, false, EpiPlain, true>(p, epi, h->batch, h->num_sms, sched, h->cur);
   else if (tile == 96)
     e = launch_gemm_ws<WsCfg96, false, false, EpiPlain, true>(p, epi, h->batch, h->num_sms, sched, h->cur);
   else if (tile == 97)
@@ -485,7 +502,7 @@ int pick_gram_ksplit(const H* h, int n1, int n2, int d, bool sym) {
   hv.batch = per_launch;
   const int code = pick_nt_tile(&hv, probe);
   const int bm = tile_bm(h, code), bn = (code == 97) ? 64 : (code == 32 ? 32 : (code == 24 ? 24 : bm));
-  const int cps = (code == 64 || code == 97 || code == 32 || code == 24) ? 3 : (code == 80 ? 2 : (code == 0 ? 4 : 1));
+  const int cps = (code == 64 || code == 97 || code == 32 || code == 24) ? 3 : (code == 80 ? 2 : (code == 0 || code == 48 ? 4 : 1));
   ws::TileEnum te;
   te.init(n1, n2, bm, bn, (sym && bm == bn) ? 1 : 0, 0);
   const long long tiles = (long long)te.per_z * per_launch;
