@@ -5,7 +5,9 @@
     python bench.py --gpus N --steps K --warmup W            # our CUDA path
     python bench.py --impl reference --steps K --warmup W    # the reference algorithm on host cores
 
-One "step" = one pass of the hot path over one BATCH of independent fits: `--batch` (default 64)
+One "step" = one pass of the hot path over one BATCH of independent fits: `--batch` (default 256: 74 GB of the
+180 GB of HBM; the diagonal-block phases of the Cholesky are latency-bound, so a larger batch amortises them — the same
+code does 3 077 / 3 190 / 3 230 evaluations/s at 64 / 128 / 256 fits per step)
 C2-shaped GPS3/ARD fits (distinct synthetic data sets and start hyper-parameters — restarts /
 CV folds / repetitions, which north_star batches per GPU) each get one evaluation of
 ForOptimisationLog + OptimisationGradientLog (NLML and its gradient w.r.t. all 22
@@ -676,7 +678,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=0, help="independent fits evaluated per step on each GPU "
-                                                         "(default: 64 for C2, 32 for C3, 256 for C4)")
+                                                         "(default: 256 for C2, 32 for C3, 256 for C4)")
     ap.add_argument("--no-extras", action="store_true", help="skip the C3 / C4 / C5 extras of the JSON line")
     ap.add_argument("--quick", action="store_true", help="developer A/B runs: device-timed value + stage timers only")
     ap.add_argument("--config", default="C2", choices=["C2", "C3", "C4"],
@@ -685,7 +687,7 @@ def main():
     global CFG
     CFG = synth.CONFIGS[args.config]
     if args.batch <= 0:
-        args.batch = {"C2": 64, "C3": 32, "C4": 256}[args.config]
+        args.batch = {"C2": 256, "C3": 32, "C4": 256}[args.config]
     if args.impl == "reference":
         return run_reference(args)
     return run_gpu(args)

@@ -2290,7 +2290,7 @@ int gps_chol_matvec(gps_handle h, const double* par, int len, const double* v, d
   // zvec (2 x ld per fit) is free after the factorisation: slot 0 = v, slot 1 = L v
   CK(h, cudaMemcpy2DAsync(h->zvec, (size_t)2 * h->ld * sizeof(double), h->pin, (size_t)n * sizeof(double),
                           (size_t)n * sizeof(double), B, cudaMemcpyHostToDevice, h->st));
-  trmv_lower_kernel<<<dim3(ceil_div(n, 128), B), 128, 0, h->st>>>(h->L, n, h->ld, h->strideM, h->zvec, 2 * h->ld,
+  trmv_lower_kernel<<<dim3(ceil_div(n, 32), B), dim3(32, 8), 0, h->st>>>(h->L, n, h->ld, h->strideM, h->zvec, 2 * h->ld,
                                                                    h->zvec + h->ld);
   h->launches++;
   CK(h, cudaGetLastError());
@@ -2351,7 +2351,7 @@ int gps_synth_generate(gps_handle h, unsigned long long seed, int n, int d, doub
   // d1 into the (now free) right-hand-side slot: the factorisation's NLML assembly has just used it
   synth_normals_kernel<<<dim3(ceil_div(ceil_div(n, 2), 256), B), 256, 0, h->st>>>(h->zvec, 2 * (long long)h->ld, n, n, h->ld, 1, seed);
   h->launches++;
-  trmv_lower_kernel<<<dim3(ceil_div(n, 128), B), 128, 0, h->st>>>(h->L, n, h->ld, h->strideM, h->zvec, 2 * h->ld, h->zvec + h->ld);
+  trmv_lower_kernel<<<dim3(ceil_div(n, 32), B), dim3(32, 8), 0, h->st>>>(h->L, n, h->ld, h->strideM, h->zvec, 2 * h->ld, h->zvec + h->ld);
   synth_targets_kernel<<<dim3(ceil_div(n, 256), B), 256, 0, h->st>>>(h->zvec + h->ld, d2, n, h->ld, sn2, y0);
   synth_censor_kernel<<<B, 32, 0, h->st>>>(y0, n, h->ld, n_censor, cens_mean, cens_sd, seed, yc, evc, rem, done);
   h->launches += 3;

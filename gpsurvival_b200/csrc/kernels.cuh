@@ -1076,16 +1076,28 @@ __global__ void predict_finish_kernel(const double* __restrict__ Ks, const doubl
 }
 
 // out[i] = sum_{k <= i} L[i,k] * v[k]   (t(chol(K)) %*% d1 of MakeSyntheticData.R:148; L lower, column-major).
-// One thread per row, serial over k (coalesced across the rows of a block). grid (ceil(n/128), batch), block 128.
-__global__ void trmv_lower_kernel(const double* __restrict__ L, int n, int ld, long long stride, const double* __restrict__ v,
-                                  int ldn, double* __restrict__ out) {
-  int i = blockIdx.x * blockDim.x + threadIdx.x, b = blockIdx.y;
-  if (i >= n) return;
-  const double* Lb = L + (size_t)b * stride + i;
-  const double* vb = v + (size_t)b * ldn;
+// Block (32, 8): 32 consecutive rows (every load of a column is one coalesced 256-byte run), the k range dealt to the
+// eight warps (k = ty, ty + 8, ...: each a fixed-order serial sum), partials added in warp order -> reproducible.
+// grid (ceil(n/32), batch).
+__global__ void __launch_bounds__(256) trmv_lower_kernel(const double* __restrict__ L, int n, int ld, long long stride,
+                                                         const double* __restrict__ v, int ldn, double* __restrict__ out) {
+  __shared__ double part[8][33];
+  const int tx = threadIdx.x, ty = threadIdx.y, b = blockIdx.y;
+  const int i = blockIdx.x * 32 + tx;
   double s = 0.0;
-  for (int k = 0; k <= i; k++) s += Lb[(size_t)k * ld] * vb[k];
-  out[(size_t)b * ldn + i] = s;
+  if (i < n) {
+    const double* Lb = L + (size_t)b * stride + i;
+    const double* vb = v + (size_t)b * ldn;
+    for (int k = ty; k <= i; k += 8) s += Lb[(size_t)k * ld] * vb[k];
+  }
+  part[ty][tx] = s;
+  __syncthreads();
+  if (ty == 0 && i < n) {
+    double t = part[0][tx];
+#pragma unroll
+    for (int w = 1; w < 8; w++) t += part[w][tx];
+    out[(size_t)b * ldn + i] = t;
+  }
 }
 
 // mstar[j] = Xc*[j,:] . w + b'  (MeanFunc.R on testData). grid (ceil(m/128), batch), block 128

@@ -299,6 +299,12 @@ SEXP gps_r_fit_folds_multi(SEXP devices, SEXP Xpool, SEXP ypool, SEXP evpool, SE
   return out;
 }
 
+/* Free the idle handles gps_fit_folds_multi keeps between calls (one per device): device memory back to the session. */
+SEXP gps_r_multi_release(void) {
+  check_status(gps_multi_release(), NULL);
+  return R_NilValue;
+}
+
 static const R_CallMethodDef call_methods[] = {
   {"gps_r_create", (DL_FUNC)&gps_r_create, 1},
   {"gps_r_set_options", (DL_FUNC)&gps_r_set_options, 5},
@@ -315,6 +321,7 @@ static const R_CallMethodDef call_methods[] = {
   {"gps_r_set_near_pd", (DL_FUNC)&gps_r_set_near_pd, 2},
   {"gps_r_metrics", (DL_FUNC)&gps_r_metrics, 4},
   {"gps_r_fit_folds_multi", (DL_FUNC)&gps_r_fit_folds_multi, 10},
+  {"gps_r_multi_release", (DL_FUNC)&gps_r_multi_release, 0},
   {NULL, NULL, 0}
 };
 

@@ -96,3 +96,7 @@ GpsFitFoldsMulti <- function(devices, xPool, yLogPool, eventsPool, trainRows, te
   .Call('gps_r_fit_folds_multi', as.integer(devices), X, as.double(yLogPool), as.double(eventsPool), trainRows, testRows, P,
         as.integer(opts), ctrl, as.double(tolerance))
 }
+
+# The library keeps one idle handle per device between GpsFitFoldsMulti calls (creating a handle, its buffers and its graphs
+# costs as much as 64 Yuan-shaped fits); this frees them.  NOT RUN IN THE BUILD IMAGE.
+GpsMultiRelease <- function() invisible(.Call('gps_r_multi_release'))

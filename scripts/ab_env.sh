@@ -4,7 +4,7 @@ tag=$1; shift
 i=0
 for e in "$@"; do
   i=$((i+1))
-  env $e python bench.py --quick --steps 10 --warmup 3 > gpurun_out/${tag}_$i.json 2> gpurun_out/${tag}_$i.err
+  env $e python bench.py --quick --steps 10 --warmup 3 $AB_ARGS > gpurun_out/${tag}_$i.json 2> gpurun_out/${tag}_$i.err
   python - "$e" gpurun_out/${tag}_$i.json <<'PY'
 import json, sys
 try:
