@@ -171,9 +171,10 @@ def measure_extra_c4_sweep(local, total=512, restarts=16, method="L-BFGS"):
     te = np.array([te[t % folds] for t in range(total)], dtype=np.int32)
     starts = np.stack([gp._flatten(synth.start_log_hyp(cfg.d, cfg.cov_form, rng), cfg.d, "Zero", cfg.noise_corr, None)
                        for _ in range(total)])
+    kw = dict(cov_form=cfg.cov_form, noise_corr=cfg.noise_corr, method=method, maxit=10, tolerance=1e300, max_count=6, survival=True)
+    gp.fit_folds_multi([local], Xp, yp, evp, tr[:restarts], te[:restarts], starts[:restarts], **kw)   # untimed: loads the kernels of this shape
     t0 = time.perf_counter()
-    res = gp.fit_folds_multi([local], Xp, yp, evp, tr, te, starts, cov_form=cfg.cov_form, noise_corr=cfg.noise_corr,
-                             method=method, maxit=10, tolerance=1e300, max_count=6, survival=True)
+    res = gp.fit_folds_multi([local], Xp, yp, evp, tr, te, starts, **kw)
     dt = time.perf_counter() - t0
     return {"workload": "C4: %d GPS3 ARD fits (%d restarts x %d folds of one n=%d+%d, d=%d data set), %s, 6 GPS rounds x maxit 10"
                         % (total, restarts, folds, cfg.n, cfg.m, cfg.d, method),

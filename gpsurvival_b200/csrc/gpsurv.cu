@@ -90,6 +90,7 @@ struct gps_handle_s {
   int front_fused = 1;           // GPS_FRONT=0: never use the fused small-d front end (small_front_kernel)
   // one-kernel Cholesky (dmma_dag.cuh): segments recorded instead of launched while dag_rec is set (per group view)
   std::vector<DagSeg>* dag_rec = nullptr;
+  int panel_merge = 1;           // GPS_PANEL_MERGE=0: always a separate publisher CTA in the panel launches
   int left_looking = 0;          // GPS_LEFT=1: left-looking big level (potrf_left) instead of the recursive right-looking potrf_big (measured equal on C2 x 64: 7.98 vs 7.99 ms)
   int dag_enabled = 0;           // GPS_DAG=1
   int dag_groups = 2, dag_slice = 48;   // GPS_DAG_GROUPS / GPS_DAG_SLICE: logical groups of fits; tiles per slice of a bulk product in the merged list
@@ -569,24 +570,26 @@ void launch_panel(H* h, int e0, int nb, int M, long long* dbg, int kprev = 0) {
   const int B = h->batch;
   const int Mr = M > 0 ? M : 1;
   double best = 1e300;
-  int best_rt = 32, best_T = 1;
+  int best_rt = 32, best_T = 1, best_merged = 0;
   for (int rt = 32; rt <= (kprev ? 32 : 128); rt += 96) {   // the fused rank-64 pre-update exists for 32-row tiles only
     const int tiles = ceil_div(Mr, rt);
     const double t_tile = (rt == 32) ? (kprev ? 2.0 : 1.4) : 5.2;
-    for (int T = 1; T <= tiles; T++) {
-      const long long ctas = (long long)(ceil_div(tiles, T) + 1) * B;
-      const double cost = (double)ceil_div((int)ctas, 148) * (17.0 + T * t_tile);
-      if (cost < best - 1e-9) { best = cost; best_rt = rt; best_T = T; }
-    }
+    for (int T = 1; T <= tiles; T++)
+      for (int merged = 0; merged <= (h->panel_merge ? 1 : 0); merged++) {
+        // separate publisher: one more CTA per fit, nobody waits for the 2.5 us of publishing; merged: CTA 0 does both
+        const long long ctas = (long long)(ceil_div(tiles, T) + (merged ? 0 : 1)) * B;
+        const double cost = (double)ceil_div((int)ctas, 148) * (17.0 + T * t_tile + (merged ? 2.5 : 0.0));
+        if (cost < best - 1e-9) { best = cost; best_rt = rt; best_T = T; best_merged = merged; }
+      }
   }
   const int tiles = ceil_div(Mr, best_rt);
-  dim3 grid(ceil_div(tiles, best_T) + 1, B);
+  dim3 grid(ceil_div(tiles, best_T) + (best_merged ? 0 : 1), B);
   if (best_rt == 32)
     CKV(h, launch_kernel(panel_kernel<32>, grid, dim3(256), kprev ? PANEL_SMEM_FUSED : PANEL_SMEM, h->st, h->Ky, h->L, h->Linv, h->U,
-                         h->ld, h->strideM, e0, nb, M, best_T, h->info, dbg, kprev));
+                         h->ld, h->strideM, e0, nb, M, best_T, h->info, dbg, kprev, best_merged));
   else
     CKV(h, launch_kernel(panel_kernel<128>, grid, dim3(256), PANEL_SMEM, h->st, h->Ky, h->L, h->Linv, h->U, h->ld, h->strideM, e0, nb,
-                         M, best_T, h->info, dbg, 0));
+                         M, best_T, h->info, dbg, 0, best_merged));
   LAUNCHED(h);
   if (h->pending_join) {   // look-ahead: the rest of the previous trailing update ran beside this panel
     CKV(h, cudaEventRecord(h->ev_join, h->st2));
@@ -1368,6 +1371,7 @@ int gps_create_batch(int device, int batch, gps_handle* out) {
   if (const char* ev = getenv("GPS_TINYCOV")) h->tiny_cov = atoi(ev) != 0;
   if (const char* ev = getenv("GPS_FUSEWK")) h->fuse_wk = atoi(ev) != 0;
   if (const char* ev = getenv("GPS_LEFT")) h->left_looking = atoi(ev);
+  if (const char* ev = getenv("GPS_PANEL_MERGE")) h->panel_merge = atoi(ev);
   if (const char* ev = getenv("GPS_DAG")) h->dag_enabled = atoi(ev);
   if (const char* ev = getenv("GPS_DAG_GROUPS")) h->dag_groups = std::max(1, atoi(ev));
   if (const char* ev = getenv("GPS_DAG_SLICE")) h->dag_slice = std::max(8, atoi(ev));

@@ -574,7 +574,7 @@ __global__ void __launch_bounds__(256) panel_kernel(const double* __restrict__ A
                                                     double* __restrict__ Linv, double* __restrict__ Uinv, int ld,
                                                     long long stride, int e0,
                                                     int nb, int M, int T, int* __restrict__ info,
-                                                    long long* __restrict__ dbg, int kprev) {
+                                                    long long* __restrict__ dbg, int kprev, int merged) {
   // kprev = 64 (RT = 32 only): the rank-64 update from the PREVIOUS block column is still pending for this one
   // (the second leaf of a leaf pair of the recursion).  It is applied here — to the diagonal block and to every
   // row tile, on DMMA from shared memory, before they are used — instead of by a separate K = 64 GEMM launch
@@ -595,9 +595,11 @@ __global__ void __launch_bounds__(256) panel_kernel(const double* __restrict__ A
   const double* Ab = A + (size_t)b * stride;
   const double* Lprev = L + (size_t)b * stride + (size_t)(e0 - kprev) * ld;   // columns e0-64 .. e0-1 of L (kprev only)
   const int e1 = e0 + nb;
-  const bool publisher = (cta == (int)gridDim.x - 1);
+  // merged != 0: no extra CTA — CTA 0 publishes and then takes its row tiles like the others (large batches: the launch is
+  // throughput-bound, every CTA of a fit repeats the pivot chain, and one CTA less per fit can be one wave less)
+  const bool publisher = merged ? (cta == 0) : (cta == (int)gridDim.x - 1);
   int row0 = e1 + cta * T * RT;                 // first panel row of this CTA
-  int rows = publisher ? 0 : min(RT, e1 + M - row0);
+  int rows = (publisher && !merged) ? 0 : min(RT, e1 + M - row0);
 
   // stage A11 (zero-filled to 64 x 64) and the A21 tile with coalesced 16-byte async copies
   for (int c = tid; c < NB * 32; c += 256) {
@@ -725,7 +727,7 @@ __global__ void __launch_bounds__(256) panel_kernel(const double* __restrict__ A
       }
     }
     PANEL_STAMP();
-    return;
+    if (!merged) return;
   }
   PANEL_STAMP();
 
