@@ -172,13 +172,21 @@ def measure_extra_c4_sweep(local, total=512, restarts=16, method="L-BFGS"):
     starts = np.stack([gp._flatten(synth.start_log_hyp(cfg.d, cfg.cov_form, rng), cfg.d, "Zero", cfg.noise_corr, None)
                        for _ in range(total)])
     kw = dict(cov_form=cfg.cov_form, noise_corr=cfg.noise_corr, method=method, maxit=10, tolerance=1e300, max_count=6, survival=True)
-    gp.fit_folds_multi([local], Xp, yp, evp, tr[:restarts], te[:restarts], starts[:restarts], **kw)   # untimed: loads the kernels of this shape
+    # first call: creates the handle (30 GB of per-fit buffers at 512 fits), captures its graphs, loads the kernels of this
+    # shape; the library keeps that handle idle for the next call (gps_multi_release frees it), which is the one timed —
+    # the steady state of a session that runs sweep after sweep (scripts/sweep_multi.py reports both the same way)
+    t0 = time.perf_counter()
+    gp.fit_folds_multi([local], Xp, yp, evp, tr, te, starts, **kw)
+    dt_first = time.perf_counter() - t0
     t0 = time.perf_counter()
     res = gp.fit_folds_multi([local], Xp, yp, evp, tr, te, starts, **kw)
     dt = time.perf_counter() - t0
+    from gpsurvival_b200 import _lib
+    _lib.load().gps_multi_release()
     return {"workload": "C4: %d GPS3 ARD fits (%d restarts x %d folds of one n=%d+%d, d=%d data set), %s, 6 GPS rounds x maxit 10"
                         % (total, restarts, folds, cfg.n, cfg.m, cfg.d, method),
             "fits_per_sec": total / dt, "seconds": dt, "lost_fits": int(np.sum(res["status"] != 0)),
+            "seconds_first_call": dt_first, "batched_evaluations": int(res["ticks"]),
             "h2d_note": "pool uploaded once per sub-batch; fits, censored rows and test folds are row-index views"}
 
 
@@ -597,10 +605,12 @@ def run_gpu(args):
         fit.close()
         fit = None
         if not args.no_extras:
-            for key, fn in (("C3x32", lambda: measure_extra_config("C3", 32, local, 10)),
-                            ("C4x256", lambda: measure_extra_config("C4", 256, local, 5)),
-                            ("C5", lambda: measure_extra_c5(local)),
-                            ("C4_sweep_512_fits", lambda: measure_extra_c4_sweep(local))):
+            order = os.environ.get("BENCH_EXTRAS_ORDER", "C3x32,C4x256,C5,C4_sweep_512_fits").split(",")   # developer knob
+            fns = {"C3x32": lambda: measure_extra_config("C3", 32, local, 10),
+                   "C4x256": lambda: measure_extra_config("C4", 256, local, 5),
+                   "C5": lambda: measure_extra_c5(local),
+                   "C4_sweep_512_fits": lambda: measure_extra_c4_sweep(local)}
+            for key, fn in ((k, fns[k.split("#")[0]]) for k in order):
                 try:
                     extras[key] = fn()
                 except Exception as exc:
