@@ -167,3 +167,59 @@ def truncated_moments(a, mu, s):
     al = (a - mu) / s
     lam = mp.npdf(al) / (mp.erfc(al / mp.sqrt(2)) / 2)
     return mu + s * lam, s ** 2 * (1 - lam * (lam - al))
+
+
+def near_pd(x, eig_tol="1e-6", conv_tol="1e-7", posd_tol="1e-8", maxit=100):
+    """Matrix::nearPD with the defaults the reference uses (call site ForOptimisationLog.R:43-44) in 50-digit arithmetic:
+    Higham (2002) alternating projections with Dykstra's correction, eigenvalues below eig.tol * lambda_max dropped, relative
+    infinity-norm convergence, then the posd.tol eigenvalue floor and the diagonal-preserving rescale.  Written from the
+    published algorithm with explicit loops (mp.eigsy for the symmetric eigenproblem) — an independent pin of the FP64
+    restatement gp_oracle.near_pd for tiny matrices.  Returns (matrix as nested lists of mpf, converged, iterations)."""
+    eig_tol, conv_tol, posd_tol = mp.mpf(eig_tol), mp.mpf(conv_tol), mp.mpf(posd_tol)
+    n = len(x)
+    X = mp.matrix(n, n)
+    for i in range(n):
+        for j in range(n):
+            X[i, j] = (mp.mpf(x[i][j]) + mp.mpf(x[j][i])) / 2
+
+    def inf_norm(A):
+        return max(sum(abs(A[i, j]) for j in range(n)) for i in range(n))
+
+    def rebuild(vals, Q, keep):
+        out = mp.zeros(n, n)
+        for k in range(n):
+            if not keep[k]:
+                continue
+            for i in range(n):
+                qik = Q[i, k] * vals[k]
+                for j in range(n):
+                    out[i, j] += qik * Q[j, k]
+        return out
+
+    D_S = mp.zeros(n, n)
+    it, converged = 0, False
+    while it < maxit and not converged:
+        Y = X.copy()
+        R = Y - D_S
+        vals, Q = mp.eigsy(R)
+        vals = [vals[k] for k in range(n)]
+        lam = max(vals)
+        keep = [v > eig_tol * lam for v in vals]
+        if not any(keep):
+            raise ArithmeticError("Matrix seems negative semi-definite")
+        X = rebuild(vals, Q, keep)
+        D_S = X - R
+        conv = inf_norm(Y - X) / inf_norm(Y)
+        it += 1
+        converged = conv <= conv_tol
+    vals, Q = mp.eigsy(X)
+    vals = [vals[k] for k in range(n)]
+    eps = posd_tol * abs(max(vals))
+    if min(vals) < eps:
+        o_diag = [X[i, i] for i in range(n)]
+        X = rebuild([v if v >= eps else eps for v in vals], Q, [True] * n)
+        D = [mp.sqrt(max(eps, o_diag[i]) / X[i, i]) for i in range(n)]
+        for i in range(n):
+            for j in range(n):
+                X[i, j] = D[i] * X[i, j] * D[j]
+    return [[X[i, j] for j in range(n)] for i in range(n)], converged, it

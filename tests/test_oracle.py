@@ -316,3 +316,31 @@ def test_philox_known_answers_and_synth_recipe():
     assert abs(z.mean()) < 0.03 and abs(z.std() - 1.0) < 0.03
     X, y0, y, ev, done = so.generate(7, 0, 60, 2, 0.01, 0.5, 1.5, 1e-6, 24, 0.0, 50.0)
     assert done == 24 and int(np.sum(ev == 0)) == 24 and np.all(y[ev == 0] < y0[ev == 0]) and np.array_equal(y[ev == 1], y0[ev == 1])
+
+
+def test_near_pd_restatement_properties_and_mpmath_pin():
+    """gp_oracle.near_pd (Matrix::nearPD's published algorithm with the reference's defaults, ForOptimisationLog.R:43-51):
+    independent 50-digit restatement on small indefinite / singular matrices, and the properties the algorithm guarantees."""
+    from oracle import mp_oracle as mpo
+    rng = np.random.default_rng(12)
+    cases = []
+    A = rng.standard_normal((6, 6)); A = A + A.T                          # indefinite
+    cases.append(A)
+    B = rng.standard_normal((5, 3)); B = B @ B.T                           # rank-deficient PSD
+    cases.append(np.vstack([np.hstack([B, B]), np.hstack([B, B])])[:7, :7])   # duplicated rows, as a singular Ky has them
+    C = np.eye(4) + 0.9 * (np.ones((4, 4)) - np.eye(4)); C[0, 1] = C[1, 0] = -0.9   # a broken correlation matrix
+    cases.append(C)
+    for x in cases:
+        got, conv, it = orc.near_pd(x)
+        ref, conv_mp, it_mp = mpo.near_pd(x.tolist())
+        ref = np.array([[float(v) for v in row] for row in ref])
+        assert conv and conv_mp and it == it_mp
+        assert np.max(np.abs(got - ref)) <= 1e-9 * np.max(np.abs(ref))
+        w = np.linalg.eigvalsh(got)
+        assert np.allclose(got, got.T, atol=1e-14 * np.max(np.abs(got)))
+        assert w[0] >= 0.99e-8 * w[-1]                                      # posd.tol floor
+        np.linalg.cholesky(got)                                             # what ForOptimisationLog.R:45 does next
+    # a well-conditioned positive definite matrix is a fixed point (one projection, nothing dropped, nothing raised)
+    P = B[:3, :3] + 3.0 * np.eye(3)
+    got, conv, it = orc.near_pd(P)
+    assert conv and it == 1 and np.max(np.abs(got - P)) <= 1e-13 * np.max(np.abs(P))
