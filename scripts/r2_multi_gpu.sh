@@ -3,7 +3,7 @@
 # point (one host process), the per-process sweep under torchrun, and the weak-scaling bench line at N = 2 / 4 / 8.
 O=gpurun_out; T=${1:-r2v}
 timeout 600 python scripts/sweep_multi.py 512 L-BFGS 1 2 4 8 > $O/${T}_sweep_multi.jsonl 2> $O/${T}_sweep_multi.err; echo "sweep_multi rc=$?"; cat $O/${T}_sweep_multi.jsonl | cut -c1-200
-for N in 2 4 8; do
+for N in ${NLIST:-2 4 8}; do
   timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 2950$N bench.py --gpus $N --no-extras > $O/${T}_bench_${N}gpu.json 2> $O/${T}_bench_${N}gpu.err; echo "bench $N rc=$?"
   tail -1 $O/${T}_bench_${N}gpu.json | cut -c1-160
 done
