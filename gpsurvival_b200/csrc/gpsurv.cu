@@ -220,10 +220,18 @@ int fail(H* h, int code, const std::string& msg) {
 // default stream is NOT ordered with it, and a "synchronous" pageable H2D copy may return
 // before its DMA has landed.
 thread_local cudaStream_t g_alloc_stream = nullptr;
+}  // namespace
+extern "C" int gps_multi_release(void);
+namespace {
 template <class T>
 cudaError_t dalloc(T** p, size_t elems, bool zero = true) {
   if (elems == 0) elems = 1;
   cudaError_t e = cudaMalloc((void**)p, elems * sizeof(T));
+  if (e == cudaErrorMemoryAllocation) {   // the idle handles of the multi-device entry points hold device memory: give it back, try again
+    (void)cudaGetLastError();
+    gps_multi_release();
+    e = cudaMalloc((void**)p, elems * sizeof(T));
+  }
   if (e != cudaSuccess) return e;
   if (zero) return cudaMemsetAsync(*p, 0, elems * sizeof(T), g_alloc_stream);
   return cudaSuccess;
