@@ -178,15 +178,18 @@ def measure_extra_c4_sweep(local, total=512, restarts=16, method="L-BFGS"):
     t0 = time.perf_counter()
     gp.fit_folds_multi([local], Xp, yp, evp, tr, te, starts, **kw)
     dt_first = time.perf_counter() - t0
-    t0 = time.perf_counter()
-    res = gp.fit_folds_multi([local], Xp, yp, evp, tr, te, starts, **kw)
-    dt = time.perf_counter() - t0
+    later = []
+    for _ in range(2):
+        t0 = time.perf_counter()
+        res = gp.fit_folds_multi([local], Xp, yp, evp, tr, te, starts, **kw)
+        later.append(time.perf_counter() - t0)
+    dt = min(later)                              # host-driven lock-step loop: run-to-run spread of a few tenths of a second
     from gpsurvival_b200 import _lib
     _lib.load().gps_multi_release()
     return {"workload": "C4: %d GPS3 ARD fits (%d restarts x %d folds of one n=%d+%d, d=%d data set), %s, 6 GPS rounds x maxit 10"
                         % (total, restarts, folds, cfg.n, cfg.m, cfg.d, method),
             "fits_per_sec": total / dt, "seconds": dt, "lost_fits": int(np.sum(res["status"] != 0)),
-            "seconds_first_call": dt_first, "batched_evaluations": int(res["ticks"]),
+            "seconds_first_call": dt_first, "seconds_later_calls": later, "batched_evaluations": int(res["ticks"]),
             "h2d_note": "pool uploaded once per sub-batch; fits, censored rows and test folds are row-index views"}
 
 
