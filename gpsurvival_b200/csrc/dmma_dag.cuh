@@ -11,8 +11,14 @@
 //     FOR ITS OWN FIT — a per-(segment, fit) counter in global memory, incremented with release semantics after the tile's
 //     stores, polled with acquire semantics by the producer warp before it issues the tile's first copy.  Fits are
 //     independent, so nothing ever waits for another fit: there is no launch boundary, no grid-wide barrier;
-//   * the groups' segment lists are merged with a skew, so that while one group's fits sit in their pivot chains the
-//     list offers the CTAs other groups' trailing-update tiles.
+//   * the groups' segment lists are merged on the host by a discrete-event LIST SCHEDULER (gpsurv.cu, enqueue_potrf_dag): a
+//     machine clock advanced by the bulk slices, a ready time per group advanced by the latency of its dependent steps; bulk
+//     products are cut into slices of a few dozen tiles, so that while one group's fits sit in their pivot chains the list
+//     offers the CTAs other groups' trailing-update tiles, and a dependent step is listed about when its predecessor is done.
+// Status: EXPERIMENTAL, off by default (GPS_DAG=1; =2 appends the triangular-inverse levels to the same list).  Measured
+// parity with the multi-launch path, not a win: a dependent hop through global counters costs 17 - 20 us where
+// a launch boundary costs 2 - 3, and the default path's two stream groups already overlap most of what the list overlaps.
+// GPS_DAG_TRACE=1 records per-task time stamps (scripts/dag_trace.py).
 // Deadlock freedom: a task only ever waits for tasks that precede it in the list, tasks are handed out in list order,
 // and a CTA that holds a task never waits for a later one.
 // Determinism: which CTA runs a tile is dynamic, what a tile computes is not (same k order as the multi-launch path).
